@@ -1,0 +1,228 @@
+/*
+ * mhap_b200.h -- C ABI of the B200-native MinHash overlap engine (libmhap_b200.so).
+ *
+ * The reference (marbl/MHAP 2.1.3, pure Java) has no FFI; its seams for this path are Java
+ * abstract methods and static deserialisers.  Each entry point below names the reference
+ * interface it replaces; paths are relative to
+ * /root/reference/src/main/java/edu/umd/marbl/mhap/ .  INTEGRATION.md shows the JNI shim and the
+ * Java subclass (GpuMinHashSearch extends AbstractMatchSearch) that bind these symbols.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every call returns 0 on success and a
+ * negative MHAPB_E* code on failure (text via mhapb_last_error); no exception crosses the ABI;
+ * the caller owns every buffer it passes in; buffers the library returns are released with
+ * mhapb_free.  One context drives one GPU (one process per GPU; multi-GPU jobs create one
+ * context per rank and exchange sketch blocks with NCCL above this ABI, see mhapb_store_*_device).
+ * Calls on one context are serialised by an internal mutex, so the reference's pool threads
+ * (AbstractMatchSearch.java:70,124,206) may call concurrently.
+ *
+ * There is NO CPU fallback: if no CUDA device is usable mhapb_create fails with MHAPB_ENODEV.
+ */
+#ifndef MHAP_B200_H
+#define MHAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHAPB_OK        0
+#define MHAPB_EINVAL   -1   /* bad argument (the reference throws MhapRuntimeException / SketchRuntimeException) */
+#define MHAPB_ENODEV   -2   /* no usable CUDA device / kernels not loadable */
+#define MHAPB_ECUDA    -3   /* CUDA runtime error */
+#define MHAPB_ENOMEM   -4
+#define MHAPB_EDUPID   -5   /* "Sequence ID already exists in the hash table." impl/MinHashSearch.java:112-117 */
+#define MHAPB_ESTATE   -6   /* call out of order (e.g. search before any sequence was added) */
+
+typedef struct mhapb_ctx mhapb_ctx;
+
+/* Sketch parameters: the constructor arguments of impl/SequenceSketch.java:106-116
+ * (kmerSize, numHashes, orderedKmerSize, orderedSketchSize, repeatWeight) plus the streamer's
+ * minOlapLength read filter (impl/SequenceSketchStreamer.java:129-133).  No -f filter file. */
+typedef struct {
+    int32_t kmer_size;            /* -k, 16 */
+    int32_t num_hashes;           /* --num-hashes, 512 (1..2048) */
+    int32_t ordered_kmer_size;    /* --ordered-kmer-size, 12 */
+    int32_t ordered_sketch_size;  /* --ordered-sketch-size, 1536 */
+    int32_t unweighted;           /* 1 <=> --repeat-weight < 0 (classic MinHash, weight 1) */
+    int32_t min_olap_length;      /* --min-olap-length, 116: shorter reads are skipped */
+} mhapb_sketch_params;
+
+/* Search parameters: impl/MinHashSearch.java:63-76 constructor arguments. */
+typedef struct {
+    int32_t num_min_matches;      /* --num-min-matches, 3 */
+    int32_t min_store_length;     /* --min-store-length, 0 */
+    double  max_shift;            /* --max-shift, 0.2 */
+    double  accept_score;         /* --threshold, 0.78 */
+    int32_t keep_all;             /* 1: also return fully-compared candidates that fail the threshold */
+    int32_t reserved;
+    int64_t query_first;          /* self search: restrict queries to stored sketches            */
+    int64_t query_count;          /*   [query_first, query_first+query_count); count<0 => all    */
+} mhapb_search_params;
+
+/* One overlap = the integers behind impl/MatchResult.java:46-65 + impl/OverlapInfo.java:40-50.
+ * a1..b2 are in ordered-k-mer units before MatchResult's strand flip; score is
+ * BottomOverlapSketch.jaccardToIdentity(intersect/kmin) (sketch/BottomOverlapSketch.java:391-395)
+ * evaluated on the host in double precision. */
+typedef struct {
+    int64_t from_id, to_id;        /* header ids */
+    int32_t from_fwd, to_fwd;
+    int32_t hit_count;             /* shared min-hashes (HitCounter.count, MinHashSearch.java:176) */
+    int32_t a1, a2, b1, b2;
+    int32_t valid_count;           /* rawScore */
+    int32_t intersect, kmin;       /* bottom-k jaccard numerator / k */
+    int32_t from_len, to_len;      /* bases */
+    double  score;
+    int32_t accepted;              /* score >= accept_score (MinHashSearch.java:229) */
+    int32_t pad_;
+} mhapb_hit;
+
+/* The order-independent counters MhapMain.outputFinalStat prints (main/MhapMain.java:572-590). */
+typedef struct {
+    int64_t elements_processed;    /* getNumberElementsProcessed   MinHashSearch.java:188 */
+    int64_t sequences_hit;         /* getNumberSequencesHit        MinHashSearch.java:189 */
+    int64_t fully_compared;        /* getNumberSequencesFullyCompared MinHashSearch.java:232 */
+    int64_t matches_processed;     /* getMatchesProcessed          AbstractMatchSearch.java:161 */
+    int64_t sequences_searched;    /* getNumberSequencesSearched   AbstractMatchSearch.java:152 */
+} mhapb_stats;
+
+/* Device-time breakdown of the last sketch / search call (CUDA events, milliseconds). */
+typedef struct {
+    float h2d_ms, d2h_ms;
+    float hash_dedup_ms, minhash_ms, ordered_ms;      /* K1a, K1b, K1c */
+    float index_ms, probe_ms, filter_ms;              /* K2a, K2b, K2c */
+    int64_t kernel_launches;                          /* launches of this library's own kernels */
+    int64_t xorshift_steps;                           /* algorithmic XORShift-min steps of the last sketch call */
+} mhapb_timing;
+
+/* ---- housekeeping ------------------------------------------------------------------------ */
+const char *mhapb_version(void);
+/* device_id: CUDA ordinal.  Replaces nothing in the reference (single JVM); one per rank. */
+int  mhapb_create(int device_id, mhapb_ctx **out);
+void mhapb_destroy(mhapb_ctx *ctx);
+const char *mhapb_last_error(const mhapb_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
+void mhapb_free(void *p);
+int  mhapb_get_timing(mhapb_ctx *ctx, mhapb_timing *out);
+/* cudaHostAlloc / cudaFreeHost, so callers (JNI direct buffers, the benchmark) can stage reads
+ * in pinned memory. */
+int  mhapb_host_alloc(size_t bytes, void **out);
+void mhapb_host_free(void *p);
+
+/* ---- K1: sketching ------------------------------------------------------------------------
+ * Replaces SequenceSketchStreamer.getSketch (impl/SequenceSketchStreamer.java:262-266) applied
+ * to a batch of reads, i.e. new SequenceSketch(seq, k, H, ok, os, filter=null, true, repeatWeight)
+ * (impl/SequenceSketch.java:106-116) for the read and, when both_strands, its reverse complement
+ * (SequenceSketchStreamer.java:147-155, utils/Utils.java:496-507).
+ *
+ * bases: the reads' characters concatenated (ASCII; lower case is upper-cased like
+ * impl/FastaData.java:194; any letter is hashed as its UTF-16 code unit exactly as
+ * sketch/HashUtils.java:213-258 does, so N / IUPAC need no special handling);
+ * offsets[n_reads+1] delimit them.  Sketch slot j = read*(both_strands?2:1) + (0 fwd | 1 rc).
+ *
+ * out_minhash    [n_slots][H]      MinHashSketch.minHashes           (sketch/MinHashSketch.java:51-179)
+ * out_ord        [n_slots][S][2]   BottomOverlapSketch.orderedHashes (hash,pos) (sketch/BottomOverlapSketch.java:525-559)
+ * out_ord_n      [n_slots]         orderedHashes.length = min(S, L-ok+1)
+ * out_status     [n_reads]         0 ok; 1 = ZeroNGramsFoundException (read shorter than a k-mer,
+ *                                  MinHashSketch.java:55-56 / BottomOverlapSketch.java:530-531);
+ *                                  2 = skipped, shorter than min_olap_length.
+ * Slots of reads with status != 0 are zero-filled.  Any out pointer may be NULL. */
+int mhapb_sketch(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases,
+                 const uint64_t *offsets, uint32_t n_reads, int both_strands,
+                 int32_t *out_minhash, int32_t *out_ord, int32_t *out_ord_n, int32_t *out_status);
+
+/* Same computation with the bases already resident in HBM and the sketches left there
+ * (d_* are device pointers of the sizes above; h_offsets stays on the host).  This is what
+ * bench.py times for the device-resident figure and what the multi-GPU path calls per shard
+ * before the NCCL all-gather. */
+int mhapb_sketch_device(mhapb_ctx *ctx, const mhapb_sketch_params *p, const void *d_bases,
+                        const uint64_t *h_offsets, uint32_t n_reads, int both_strands,
+                        void *d_minhash, void *d_ord, void *d_ord_n, void *d_status);
+
+/* K1 + big-endian .dat records, the byte format SequenceSketch.fromByteStream reads
+ * (impl/SequenceSketch.java:61-96,123-148; framing impl/SequenceSketchStreamer.java:349-360):
+ * this is how sketches are handed to Java, whose MinHashSketch(int[]) /
+ * BottomOverlapSketch(int,int,int[][]) constructors are private.  ids[i] is the SequenceId
+ * number (1-based file position, impl/FastaData.java:181); the header string written is its
+ * decimal form (SequenceId.getHeader without --store-full-id).  *out is malloc'd (mhapb_free). */
+int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases,
+                        const uint64_t *offsets, const int64_t *ids, uint32_t n_reads,
+                        int both_strands, uint8_t **out, uint64_t *out_len, uint32_t *n_records);
+
+/* ---- .dat codec (host only) ---------------------------------------------------------------
+ * Encode one record (returns bytes; buf==NULL sizes it).  header==NULL => decimal id. */
+int64_t mhapb_dat_encode(int64_t id, int is_fwd, const char *header, int32_t seq_len,
+                         const int32_t *minhash, int32_t num_hashes, int32_t seq_len_kmers,
+                         int32_t ordered_kmer_size, const int32_t *ord_hash_pos, int32_t ord_n,
+                         uint8_t *buf);
+/* Decode a .dat byte stream (SequenceSketchStreamer.java:278-320 + SequenceSketch.fromByteStream)
+ * into flat arrays sized for n records with H hashes and at most S ordered entries each; first
+ * call with all outputs NULL to get *n_records, *num_hashes, *max_ord.  id_offset is added to the
+ * ids like fromByteStream(input, offset). */
+int mhapb_dat_decode(const uint8_t *buf, uint64_t len, int64_t id_offset, uint32_t *n_records,
+                     int32_t *num_hashes, int32_t *max_ord, int32_t *ordered_kmer_size,
+                     int64_t *ids, uint8_t *is_fwd, int32_t *seq_len, int32_t *seq_len_kmers,
+                     int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n);
+
+/* ---- K2a: the sketch store and its inverted index -------------------------------------------
+ * Replaces MinHashSearch's constructor + addSequence (impl/MinHashSearch.java:63-147): every
+ * stored sketch (forward and reverse) is posted under each of its H min-hashes in an
+ * open-addressed (word,value) -> posting-list table in HBM. */
+int mhapb_store_reset(mhapb_ctx *ctx, const mhapb_sketch_params *p);
+/* Sketch reads on the GPU and append them to the store without leaving HBM
+ * (enqueueFullFile + addData, MinHashSearch.java:80,95).  ids[i] = SequenceId number of read i. */
+int mhapb_store_add_reads(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
+                          const int64_t *ids, uint32_t n_reads, int both_strands,
+                          int64_t *n_added);
+/* Append pre-computed sketches from host arrays (the .dat path, addSequence per record). */
+int mhapb_store_add_sketches(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd,
+                             const int32_t *seq_len, const int32_t *seq_len_kmers,
+                             const int32_t *minhash, const int32_t *ord_hash_pos,
+                             const int32_t *ord_n, int32_t ord_stride, uint32_t n);
+/* Same with the two big blocks (minhash [n][H], ord [n][S][2]) already on this GPU -- the
+ * landing buffers of the NCCL all-gather of sketch blocks; the small per-sketch columns stay on
+ * the host. */
+int mhapb_store_add_sketches_device(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd,
+                                    const int32_t *seq_len, const int32_t *seq_len_kmers,
+                                    const void *d_minhash, const void *d_ord, const int32_t *ord_n,
+                                    uint32_t n);
+int64_t mhapb_store_size(mhapb_ctx *ctx);                          /* AbstractMatchSearch.size() */
+/* Copy stored sketch idx back to the host (getStoredSequenceHash, AbstractMatchSearch.java:314). */
+int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, int32_t *seq_len,
+                    int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n);
+/* Device views of the store's blocks (for the all-gather): minhash [n][H] and ord [n][S][2]. */
+int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, int64_t *n,
+                            int32_t *num_hashes, int32_t *ord_stride);
+int mhapb_index_build(mhapb_ctx *ctx);
+
+/* ---- K2b + K2c: search --------------------------------------------------------------------
+ * findMatches() to self (impl/AbstractMatchSearch.java:121-199 driving
+ * MinHashSearch.findMatches(sketch,true), impl/MinHashSearch.java:150-251): every stored forward
+ * sketch queries the index; hit counting, the id / length filters, then
+ * BottomOverlapSketch.getOverlapInfo (sketch/BottomOverlapSketch.java:592-630) per candidate.
+ * *out is malloc'd (mhapb_free); order of hits is unspecified, as in the reference. */
+int mhapb_search_self(mhapb_ctx *ctx, const mhapb_search_params *sp, mhapb_hit **out,
+                      uint64_t *n_out, mhapb_stats *stats);
+/* findMatches(SequenceSketchStreamer) (AbstractMatchSearch.java:203-285,
+ * MinHashSearch.findMatches(sketch,false)): query reads are sketched forward only (:225). */
+int mhapb_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, const char *bases,
+                             const uint64_t *offsets, const int64_t *ids, uint32_t n_reads,
+                             mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
+/* Same with query sketches from host arrays (a .dat query file). */
+int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, const int64_t *ids,
+                                const uint8_t *is_fwd, const int32_t *seq_len,
+                                const int32_t *seq_len_kmers, const int32_t *minhash,
+                                const int32_t *ord_hash_pos, const int32_t *ord_n,
+                                int32_t ord_stride, uint32_t n, mhapb_hit **out, uint64_t *n_out,
+                                mhapb_stats *stats);
+/* impl/MatchResult.java:46-65,98-113: one output line, no newline; returns its length. */
+int mhapb_format_match(const mhapb_hit *h, char *buf, size_t buflen);
+
+/* a10: MinHashSketch.jaccard (sketch/MinHashSketch.java:237-263) between stored sketches i and j:
+ * positional equality count; *out_equal / H is the reference's double. */
+int mhapb_minhash_equal_count(mhapb_ctx *ctx, int64_t i, int64_t j, int32_t *out_equal);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,986 @@
+// api.cu -- the C ABI of include/mhap_b200.h: context, device memory, batching, and the host-side
+// halves of the reference interfaces (status per read, id filters' inputs, score, MatchResult).
+// No CPU fallback: every compute entry point launches the kernels in sketch.cu / search.cu.
+#include "../../include/mhap_b200.h"
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+using namespace mhapb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    // grow keeping the first keep_bytes
+    cudaError_t grow(size_t bytes, size_t keep_bytes, cudaStream_t st)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = std::max(bytes, cap * 2);
+        void *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&np, want); }
+        if (e != cudaSuccess) return e;
+        if (p && keep_bytes) { e = cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; e = cudaStreamSynchronize(st); }
+        if (p) cudaFree(p);
+        p = np; cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Store {
+    mhapb_sketch_params p{};
+    bool configured = false;
+    int64_t n = 0;
+    int ord_stride = 0;
+    DevBuf minhash, ord, ord_n, lenk, len, id;
+    std::vector<int64_t> h_id; std::vector<uint8_t> h_fwd; std::vector<int32_t> h_len, h_lenk, h_ordn;
+    std::unordered_set<uint64_t> seen;
+    // index
+    bool indexed = false;
+    DevBuf slots, postings;
+    int log2capw = 0;
+};
+
+} // namespace
+
+struct mhapb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    mhapb_timing timing{};
+    // sketch scratch
+    DevBuf bases, desc, keys, wts, nlight, nheavy, dupcnt, gtable, ohash, counters;
+    DevBuf out_minhash, out_ord, out_ordn;
+    // search scratch
+    DevBuf qlist, cand, ovl, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
+    Store store;
+    cudaEvent_t ev[8]{};
+};
+
+namespace {
+
+int fail(mhapb_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(ctx, e__ == cudaErrorMemoryAllocation ? MHAPB_ENOMEM : MHAPB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+int check_sketch_params(mhapb_ctx *ctx, const mhapb_sketch_params *p)
+{
+    if (!p) return fail(ctx, MHAPB_EINVAL, "null sketch params");
+    if (p->kmer_size < 1 || p->kmer_size > 4096) return fail(ctx, MHAPB_EINVAL, "kmer_size %d out of range", p->kmer_size);
+    if (p->num_hashes < 1 || p->num_hashes > kMaxNumHashes) return fail(ctx, MHAPB_EINVAL, "num_hashes %d out of range 1..%d", p->num_hashes, kMaxNumHashes);
+    if (p->ordered_kmer_size < 1 || p->ordered_kmer_size > 4096) return fail(ctx, MHAPB_EINVAL, "ordered_kmer_size %d out of range", p->ordered_kmer_size);
+    if (p->ordered_sketch_size < 1 || p->ordered_sketch_size > kMaxOrderedSketch) return fail(ctx, MHAPB_EINVAL, "ordered_sketch_size %d out of range 1..%d", p->ordered_sketch_size, kMaxOrderedSketch);
+    return MHAPB_OK;
+}
+
+// Per-read status from lengths alone (SequenceSketchStreamer.java:129-133, MinHashSketch.java:55-56,
+// BottomOverlapSketch.java:530-531).
+inline int read_status(const mhapb_sketch_params &p, uint64_t len)
+{
+    if ((int64_t)len < (int64_t)p.min_olap_length) return 2;
+    if ((int64_t)len - p.kmer_size + 1 < 1) return 1;
+    if ((int64_t)len - p.ordered_kmer_size + 1 < 1) return 1;
+    return 0;
+}
+
+struct Elapsed { float hash = 0, minhash = 0, ordered = 0; };
+
+// Sketch reads whose characters are at d_bases (device).  row_of_slot[slot] (slot = read*per+strand)
+// gives the output row or -1 to skip.  Outputs are device arrays.
+int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_bases, const uint64_t *h_offsets,
+                uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
+                int32_t *d_ord, int ord_stride, int32_t *d_ord_n)
+{
+    const int per = both ? 2 : 1;
+    const int k = p.kmer_size, ok = p.ordered_kmer_size, H = p.num_hashes, S = p.ordered_sketch_size;
+    std::vector<StrandDesc> all;
+    all.reserve((size_t)n_reads * per);
+    for (uint32_t r = 0; r < n_reads; r++) {
+        uint64_t len = h_offsets[r + 1] - h_offsets[r];
+        if (len > 0x7fffff00ull) return fail(ctx, MHAPB_EINVAL, "read %u longer than 2^31 bases", r);
+        if (read_status(p, len)) continue;
+        for (int s = 0; s < per; s++) {
+            int64_t row = row_of_slot[(size_t)r * per + s];
+            if (row < 0) continue;
+            StrandDesc d; d.base_off = h_offsets[r]; d.koff = 0; d.len = (uint32_t)len; d.row = (uint32_t)row; d.rc = (uint32_t)s; d.pad = 0;
+            all.push_back(d);
+        }
+    }
+    ctx->timing.xorshift_steps = 0;
+    if (all.empty()) return MHAPB_OK;
+
+    const uint64_t chunk_cap = 256ull << 20;   // k-mers of key scratch per chunk (2 GB keys + 1 GB weights)
+    const int max_chunk_strands = 1 << 20;
+    int launches = 0;
+    std::vector<cudaEvent_t> evs;
+    auto ev_new = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e); };
+
+    size_t pos = 0;
+    std::vector<StrandDesc> chunk;
+    while (pos < all.size()) {
+        uint64_t tot = 0;
+        chunk.clear();
+        while (pos < all.size() && (int)chunk.size() < max_chunk_strands) {
+            uint64_t nk = all[pos].len - k + 1;
+            if (!chunk.empty() && tot + nk > chunk_cap) break;
+            chunk.push_back(all[pos]); tot += nk; pos++;
+        }
+        // short strands first, long (global-table) strands after
+        auto is_short = [&](const StrandDesc &d) { return (int64_t)d.len - k + 1 <= kShortMaxKmers && (int64_t)d.len - ok + 1 <= kShortMaxKmers + 64; };
+        std::stable_partition(chunk.begin(), chunk.end(), is_short);
+        int n = (int)chunk.size(), first_long = n;
+        int max_k_short = 1, max_k_long = 1, max_len_short = 1, max_len_long = 1;
+        uint64_t koff = 0;
+        for (int i = 0; i < n; i++) {
+            StrandDesc &d = chunk[i];
+            d.koff = koff; koff += d.len - k + 1;
+            int nk = (int)d.len - k + 1;
+            if (is_short(d)) { max_k_short = std::max(max_k_short, nk); max_len_short = std::max(max_len_short, (int)d.len); }
+            else { if (first_long == n) first_long = i; max_k_long = std::max(max_k_long, nk); max_len_long = std::max(max_len_long, (int)d.len); }
+            ctx->timing.xorshift_steps += (int64_t)nk * H;
+        }
+        const int n_long = n - first_long;
+        CU(ctx, ctx->desc.ensure((size_t)n * sizeof(StrandDesc)));
+        CU(ctx, ctx->keys.ensure((size_t)koff * 8));
+        CU(ctx, ctx->wts.ensure((size_t)koff * 4));
+        CU(ctx, ctx->nlight.ensure((size_t)n * 4));
+        CU(ctx, ctx->nheavy.ensure((size_t)n * 4));
+        CU(ctx, ctx->counters.ensure(64));
+        const size_t cap_short = (size_t)max_k_short + max_k_short / 2 + 8, cap_long = (size_t)max_k_long + max_k_long / 2 + 8;
+        const int g1 = hash_dedup_grid() * 2, g2 = ordered_grid();
+        size_t dup_need = first_long > 0 ? (size_t)g1 * cap_short * 4 : 0;
+        if (n_long) dup_need = std::max(dup_need, (size_t)g1 * cap_long * 4);
+        if (dup_need > ctx->dupcnt.cap) {
+            CU(ctx, ctx->dupcnt.ensure(dup_need));
+            CU(ctx, cudaMemsetAsync(ctx->dupcnt.p, 0, ctx->dupcnt.cap, ctx->stream));   // invariant: zero between uses
+        }
+        if (n_long) {
+            CU(ctx, ctx->gtable.ensure((size_t)g1 * cap_long * 8));
+            CU(ctx, ctx->ohash.ensure((size_t)g2 * ((size_t)max_len_long + 32) * 4));
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->desc.p, chunk.data(), (size_t)n * sizeof(StrandDesc), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+        SketchScratch sc;
+        sc.keys = ctx->keys.as<uint64_t>(); sc.wts = ctx->wts.as<uint32_t>();
+        sc.nlight = ctx->nlight.as<int32_t>(); sc.nheavy = ctx->nheavy.as<int32_t>();
+        sc.dupcnt = ctx->dupcnt.as<uint32_t>(); sc.gtable = ctx->gtable.as<uint64_t>();
+        sc.ohash = ctx->ohash.as<uint32_t>(); sc.counters = ctx->counters.as<uint32_t>();
+        const StrandDesc *dd = ctx->desc.as<StrandDesc>();
+        ev_new();
+        CU(ctx, launch_hash_dedup(ctx->stream, d_bases, dd, n, first_long, max_k_short, max_k_long, k, p.unweighted, sc, &launches));
+        ev_new();
+        if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n, k, H, sc, d_minhash, &launches));
+        ev_new();
+        if (d_ord) CU(ctx, launch_ordered(ctx->stream, d_bases, dd, n, first_long, max_len_short, max_len_long, ok, S, ord_stride, sc, d_ord, d_ord_n, &launches));
+        ev_new();
+        // the next chunk reuses desc/keys: the stream orders it, but the pageable host vector is copied synchronously above
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i + 3 < evs.size(); i += 4) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, evs[i], evs[i + 1]); cudaEventElapsedTime(&b, evs[i + 1], evs[i + 2]); cudaEventElapsedTime(&c, evs[i + 2], evs[i + 3]);
+        ctx->timing.hash_dedup_ms += a; ctx->timing.minhash_ms += b; ctx->timing.ordered_ms += c;
+    }
+    for (auto e : evs) cudaEventDestroy(e);
+    ctx->timing.kernel_launches += launches;
+    return MHAPB_OK;
+}
+
+void reset_sketch_timing(mhapb_ctx *ctx)
+{
+    ctx->timing.h2d_ms = ctx->timing.d2h_ms = 0;
+    ctx->timing.hash_dedup_ms = ctx->timing.minhash_ms = ctx->timing.ordered_ms = 0;
+    ctx->timing.kernel_launches = 0;
+}
+
+double jaccard_to_identity(double score, int kmer_size)
+{
+    // sketch/BottomOverlapSketch.java:391-395
+    double d = -1.0 / (double)kmer_size * std::log(2.0 * score / (1.0 + score));
+    return std::exp(-d);
+}
+
+int store_configure(mhapb_ctx *ctx, const mhapb_sketch_params *p)
+{
+    int rc = check_sketch_params(ctx, p);
+    if (rc) return rc;
+    Store &s = ctx->store;
+    s.p = *p; s.configured = true; s.n = 0; s.ord_stride = p->ordered_sketch_size; s.indexed = false;
+    s.h_id.clear(); s.h_fwd.clear(); s.h_len.clear(); s.h_lenk.clear(); s.h_ordn.clear(); s.seen.clear();
+    return MHAPB_OK;
+}
+
+int store_reserve(mhapb_ctx *ctx, int64_t extra)
+{
+    Store &s = ctx->store;
+    const size_t n = (size_t)s.n, want = (size_t)(s.n + extra);
+    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
+    CU(ctx, s.minhash.grow(want * H * 4, n * H * 4, ctx->stream));
+    CU(ctx, s.ord.grow(want * S * 8, n * S * 8, ctx->stream));
+    CU(ctx, s.ord_n.grow(want * 4, n * 4, ctx->stream));
+    CU(ctx, s.lenk.grow(want * 4, n * 4, ctx->stream));
+    CU(ctx, s.len.grow(want * 4, n * 4, ctx->stream));
+    CU(ctx, s.id.grow(want * 8, n * 8, ctx->stream));
+    return MHAPB_OK;
+}
+
+// push the per-sketch host columns of rows [from, n) to the device
+int store_sync_columns(mhapb_ctx *ctx, int64_t from)
+{
+    Store &s = ctx->store;
+    const size_t cnt = (size_t)(s.n - from);
+    if (!cnt) return MHAPB_OK;
+    CU(ctx, cudaMemcpyAsync(s.lenk.as<int32_t>() + from, s.h_lenk.data() + from, cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(s.len.as<int32_t>() + from, s.h_len.data() + from, cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(s.id.as<int64_t>() + from, s.h_id.data() + from, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return MHAPB_OK;
+}
+
+int store_push_meta(mhapb_ctx *ctx, int64_t id, int fwd, int32_t len, int32_t lenk, int32_t ordn)
+{
+    Store &s = ctx->store;
+    uint64_t key = ((uint64_t)id << 1) | (uint64_t)(fwd ? 1 : 0);
+    if (!s.seen.insert(key).second) return fail(ctx, MHAPB_EDUPID, "Sequence ID already exists in the hash table.");
+    s.h_id.push_back(id); s.h_fwd.push_back((uint8_t)(fwd ? 1 : 0)); s.h_len.push_back(len); s.h_lenk.push_back(lenk); s.h_ordn.push_back(ordn);
+    return MHAPB_OK;
+}
+
+int index_build(mhapb_ctx *ctx)
+{
+    Store &s = ctx->store;
+    if (!s.configured || s.n == 0) return fail(ctx, MHAPB_ESTATE, "index build on an empty store");
+    if (s.indexed) return MHAPB_OK;
+    const int H = s.p.num_hashes;
+    if ((uint64_t)s.n * (uint64_t)H >= 0xfffffff0ull || s.n >= 0x7fffffff) return fail(ctx, MHAPB_EINVAL, "store too large for 32-bit postings (%lld sketches x %d)", (long long)s.n, H);
+    int lg = 4; while ((1ll << lg) < 2 * s.n) lg++;
+    s.log2capw = lg;
+    const size_t nslots = (size_t)H << lg;
+    CU(ctx, s.slots.ensure(nslots * 8));
+    CU(ctx, s.postings.ensure((size_t)s.n * H * 4));
+    CU(ctx, ctx->tmp_start.ensure(nslots * 4));
+    CU(ctx, ctx->block_sums.ensure(((nslots + 4095) / 4096 + 1) * 4));
+    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), lg, H, s.n};
+    int launches = 0;
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    CU(ctx, launch_index_build(ctx->stream, s.minhash.as<int32_t>(), s.n, H, iv, ctx->tmp_start.as<uint32_t>(), ctx->block_sums.as<uint32_t>(), &launches));
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.index_ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timing.kernel_launches += launches;
+    s.indexed = true;
+    return MHAPB_OK;
+}
+
+struct QuerySet {
+    const int32_t *d_minhash, *d_ord, *d_ordn, *d_lenk, *d_len; const int64_t *d_id; int ord_stride;
+    const int64_t *h_id; const uint8_t *h_fwd; const int32_t *h_len;
+    std::vector<uint32_t> list;   // indices into the query arrays
+};
+
+int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q, int to_self,
+                mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+{
+    Store &s = ctx->store;
+    int rc = index_build(ctx);
+    if (rc) return rc;
+    const int H = s.p.num_hashes;
+    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.log2capw, H, s.n};
+    const int64_t nq = (int64_t)q.list.size();
+    mhapb_stats st{};
+    st.sequences_searched = nq;
+    std::vector<mhapb_hit> hits;
+    int launches = 0;
+    ctx->timing.probe_ms = ctx->timing.filter_ms = 0;
+    if (nq > 0) {
+        CU(ctx, ctx->qlist.ensure((size_t)nq * 4));
+        CU(ctx, cudaMemcpyAsync(ctx->qlist.p, q.list.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, ctx->scounters.ensure(64));
+        uint64_t cand_cap = std::max<uint64_t>(1 << 16, (uint64_t)nq * 16);
+        unsigned long long cnt[3] = {0, 0, 0};
+        for (int attempt = 0; attempt < 2; attempt++) {
+            CU(ctx, ctx->cand.ensure(cand_cap * sizeof(Candidate)));
+            CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 64, ctx->stream));
+            ProbeArgs a{};
+            a.q_minhash = q.d_minhash; a.q_id = q.d_id; a.q_len = q.d_len; a.q_list = ctx->qlist.as<uint32_t>(); a.nq_list = nq;
+            a.t_id = s.id.as<int64_t>(); a.t_len = s.len.as<int32_t>();
+            a.to_self = to_self; a.num_min_matches = sp->num_min_matches; a.min_store_length = sp->min_store_length;
+            a.cand = ctx->cand.as<Candidate>(); a.cand_cap = cand_cap; a.counters = ctx->scounters.as<unsigned long long>();
+            cudaEventRecord(ctx->ev[0], ctx->stream);
+            CU(ctx, launch_probe(ctx->stream, iv, a, &launches));
+            cudaEventRecord(ctx->ev[1], ctx->stream);
+            CU(ctx, cudaMemcpyAsync(cnt, ctx->scounters.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.probe_ms += ms;
+            if (cnt[0] <= cand_cap) break;
+            cand_cap = cnt[0];   // rare: more candidates than guessed; rerun with the exact size
+        }
+        st.elements_processed = (int64_t)cnt[1];
+        st.sequences_hit = (int64_t)cnt[2];
+        const uint64_t nc = cnt[0];
+        st.fully_compared = (int64_t)nc;
+        if (nc > 0) {
+            const uint32_t entries = 2u * (uint32_t)std::max(q.ord_stride, s.ord_stride) + 2u;
+            uint64_t budget = 4ull << 30;
+            uint64_t max_threads = std::max<uint64_t>(128, budget / (12ull * entries));
+            uint32_t nth = (uint32_t)std::min<uint64_t>(nc, max_threads);
+            nth = (nth + 127u) & ~127u;
+            CU(ctx, ctx->fscratch.ensure((size_t)3 * entries * nth * 4));
+            CU(ctx, ctx->ovl.ensure((size_t)nc * sizeof(OverlapOut)));
+            FilterArgs f{};
+            f.cand = ctx->cand.as<Candidate>(); f.n_cand = nc;
+            f.q_ord = q.d_ord; f.q_ord_n = q.d_ordn; f.q_lenk = q.d_lenk; f.q_stride = q.ord_stride;
+            f.t_ord = s.ord.as<int32_t>(); f.t_ord_n = s.ord_n.as<int32_t>(); f.t_lenk = s.lenk.as<int32_t>(); f.t_stride = s.ord_stride;
+            f.max_shift = sp->max_shift;
+            f.scratch = ctx->fscratch.as<int32_t>(); f.scratch_entries = entries; f.n_threads = nth;
+            f.out = ctx->ovl.as<OverlapOut>();
+            cudaEventRecord(ctx->ev[2], ctx->stream);
+            CU(ctx, launch_filter(ctx->stream, f, &launches));
+            cudaEventRecord(ctx->ev[3], ctx->stream);
+            std::vector<Candidate> hc(nc);
+            std::vector<OverlapOut> ho(nc);
+            CU(ctx, cudaMemcpyAsync(hc.data(), ctx->cand.p, nc * sizeof(Candidate), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(ho.data(), ctx->ovl.p, nc * sizeof(OverlapOut), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaEventElapsedTime(&ctx->timing.filter_ms, ctx->ev[2], ctx->ev[3]);
+            const int ok = s.p.ordered_kmer_size;
+            hits.reserve(nc / 2 + 16);
+            for (uint64_t i = 0; i < nc; i++) {
+                const OverlapOut &o = ho[i];
+                double score = 0.0;   // OverlapInfo.EMPTY
+                if (!o.empty) {
+                    double jac = o.kmin ? (double)o.inter / (double)o.kmin : 0.0;
+                    score = jaccard_to_identity(jac, ok);
+                }
+                const bool accept = score >= sp->accept_score;   // MinHashSearch.java:229
+                if (accept) st.matches_processed++;
+                if (!accept && !sp->keep_all) continue;
+                mhapb_hit h{};
+                const uint32_t qi = hc[i].q, ti = hc[i].t;
+                h.from_id = q.h_id[qi]; h.to_id = s.h_id[ti];
+                h.from_fwd = q.h_fwd[qi]; h.to_fwd = s.h_fwd[ti];
+                h.hit_count = (int32_t)hc[i].count;
+                h.a1 = o.a1; h.a2 = o.a2; h.b1 = o.b1; h.b2 = o.b2;
+                h.valid_count = o.valid; h.intersect = o.inter; h.kmin = o.kmin;
+                h.from_len = q.h_len[qi]; h.to_len = s.h_len[ti];
+                h.score = score; h.accepted = accept ? 1 : 0;
+                hits.push_back(h);
+            }
+        }
+    }
+    ctx->timing.kernel_launches += launches;
+    if (stats) *stats = st;
+    if (n_out) *n_out = hits.size();
+    if (out) {
+        mhapb_hit *arr = (mhapb_hit *)malloc(sizeof(mhapb_hit) * std::max<size_t>(1, hits.size()));
+        if (!arr) return fail(ctx, MHAPB_ENOMEM, "malloc hits");
+        if (!hits.empty()) memcpy(arr, hits.data(), sizeof(mhapb_hit) * hits.size());
+        *out = arr;
+    }
+    return MHAPB_OK;
+}
+
+int h2d_bases(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n_reads)
+{
+    const uint64_t total = offsets[n_reads] - offsets[0];
+    CU(ctx, ctx->bases.ensure((size_t)offsets[n_reads] + 64));
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    if (total) CU(ctx, cudaMemcpyAsync(ctx->bases.as<uint8_t>() + offsets[0], bases + offsets[0], (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    return MHAPB_OK;
+}
+
+// sketch reads and append them to the store (shared by store_add_reads and the tests' store_get path)
+int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, const int64_t *ids, uint32_t n_reads, int both, int64_t *n_added)
+{
+    Store &s = ctx->store;
+    if (!s.configured) return fail(ctx, MHAPB_ESTATE, "mhapb_store_reset must be called first");
+    const int per = both ? 2 : 1;
+    std::vector<int64_t> rows((size_t)n_reads * per, -1);
+    const int64_t n0 = s.n;
+    int64_t next = n0;
+    for (uint32_t r = 0; r < n_reads; r++) {
+        uint64_t len = offsets[r + 1] - offsets[r];
+        if (read_status(s.p, len)) continue;
+        for (int st = 0; st < per; st++) rows[(size_t)r * per + st] = next++;
+    }
+    const int64_t added = next - n0;
+    if (n_added) *n_added = added;
+    if (!added) return MHAPB_OK;
+    // metadata first (duplicate ids abort before any device work)
+    const size_t meta0 = s.h_id.size();
+    for (uint32_t r = 0; r < n_reads; r++) {
+        uint64_t len = offsets[r + 1] - offsets[r];
+        if (read_status(s.p, len)) continue;
+        for (int st = 0; st < per; st++) {
+            int32_t no = (int32_t)len - s.p.ordered_kmer_size + 1;
+            int rc = store_push_meta(ctx, ids ? ids[r] : (int64_t)r + 1, st == 0, (int32_t)len, no, std::min(no, s.p.ordered_sketch_size));
+            if (rc) {
+                for (size_t i = meta0; i < s.h_id.size(); i++) s.seen.erase(((uint64_t)s.h_id[i] << 1) | s.h_fwd[i]);
+                s.h_id.resize(meta0); s.h_fwd.resize(meta0); s.h_len.resize(meta0); s.h_lenk.resize(meta0); s.h_ordn.resize(meta0);
+                return rc;
+            }
+        }
+    }
+    int rc = store_reserve(ctx, added);
+    if (rc) return rc;
+    rc = h2d_bases(ctx, bases, offsets, n_reads);
+    if (rc) return rc;
+    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
+    CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)added * S * 8, ctx->stream));
+    rc = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>());
+    (void)H;
+    if (rc) return rc;
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.h2d_ms += ms;
+    s.n = next;
+    s.indexed = false;
+    return store_sync_columns(ctx, n0);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *mhapb_version(void) { return "mhap-b200 0.1 (sm_100a; reference marbl/MHAP 2.1.3)"; }
+
+int mhapb_create(int device_id, mhapb_ctx **out)
+{
+    if (!out) return fail(nullptr, MHAPB_EINVAL, "null out");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(nullptr, MHAPB_ENODEV, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return fail(nullptr, MHAPB_ENODEV, "device %d out of range (%d visible)", device_id, n);
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return fail(nullptr, MHAPB_ENODEV, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return fail(nullptr, MHAPB_ENODEV, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, MHAPB_ENODEV, "device %d is sm_%d%d; this build carries sm_100a code only", device_id, prop.major, prop.minor);
+    mhapb_ctx *c = new mhapb_ctx();
+    c->device = device_id;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, MHAPB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    for (auto &ev : c->ev) cudaEventCreate(&ev);
+    *out = c;
+    return MHAPB_OK;
+}
+
+void mhapb_destroy(mhapb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->bases, &ctx->desc, &ctx->keys, &ctx->wts, &ctx->nlight, &ctx->nheavy, &ctx->dupcnt, &ctx->gtable, &ctx->ohash,
+                      &ctx->counters, &ctx->out_minhash, &ctx->out_ord, &ctx->out_ordn, &ctx->qlist, &ctx->cand, &ctx->ovl, &ctx->fscratch,
+                      &ctx->scounters, &ctx->tmp_start, &ctx->block_sums, &ctx->q_minhash, &ctx->q_ord, &ctx->q_ordn, &ctx->q_lenk, &ctx->q_len,
+                      &ctx->q_id, &ctx->eq, &ctx->store.minhash, &ctx->store.ord, &ctx->store.ord_n, &ctx->store.lenk, &ctx->store.len,
+                      &ctx->store.id, &ctx->store.slots, &ctx->store.postings};
+    for (auto b : bufs) b->release();
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *mhapb_last_error(const mhapb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void mhapb_free(void *p) { free(p); }
+
+int mhapb_get_timing(mhapb_ctx *ctx, mhapb_timing *out)
+{
+    if (!ctx || !out) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = ctx->timing;
+    return MHAPB_OK;
+}
+
+int mhapb_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return MHAPB_EINVAL;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? MHAPB_OK : MHAPB_ENOMEM;
+}
+void mhapb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int mhapb_sketch_device(mhapb_ctx *ctx, const mhapb_sketch_params *p, const void *d_bases, const uint64_t *h_offsets,
+                        uint32_t n_reads, int both_strands, void *d_minhash, void *d_ord, void *d_ord_n, void *d_status)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = check_sketch_params(ctx, p);
+    if (rc) return rc;
+    if (!h_offsets || (!d_bases && n_reads && h_offsets[n_reads] > h_offsets[0])) return fail(ctx, MHAPB_EINVAL, "null bases/offsets");
+    if (d_ord && !d_ord_n) return fail(ctx, MHAPB_EINVAL, "d_ord needs d_ord_n");
+    reset_sketch_timing(ctx);
+    const int per = both_strands ? 2 : 1;
+    const size_t slots = (size_t)n_reads * per, H = (size_t)p->num_hashes, S = (size_t)p->ordered_sketch_size;
+    std::vector<int64_t> rows(slots);
+    std::vector<int32_t> status(n_reads);
+    for (uint32_t r = 0; r < n_reads; r++) {
+        status[r] = read_status(*p, h_offsets[r + 1] - h_offsets[r]);
+        for (int s = 0; s < per; s++) rows[(size_t)r * per + s] = (int64_t)r * per + s;
+    }
+    if (d_minhash && slots) CU(ctx, cudaMemsetAsync(d_minhash, 0, slots * H * 4, ctx->stream));
+    if (d_ord && slots) CU(ctx, cudaMemsetAsync(d_ord, 0, slots * S * 8, ctx->stream));
+    if (d_ord_n && slots) CU(ctx, cudaMemsetAsync(d_ord_n, 0, slots * 4, ctx->stream));
+    if (d_status && n_reads) CU(ctx, cudaMemcpyAsync(d_status, status.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = sketch_core(ctx, *p, (const uint8_t *)d_bases, h_offsets, n_reads, both_strands, rows, (int32_t *)d_minhash, (int32_t *)d_ord, (int)S, (int32_t *)d_ord_n);
+    if (rc) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return MHAPB_OK;
+}
+
+int mhapb_sketch(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases, const uint64_t *offsets, uint32_t n_reads,
+                 int both_strands, int32_t *out_minhash, int32_t *out_ord, int32_t *out_ord_n, int32_t *out_status)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = check_sketch_params(ctx, p);
+    if (rc) return rc;
+    if (!offsets || (!bases && n_reads && offsets[n_reads] > offsets[0])) return fail(ctx, MHAPB_EINVAL, "null bases/offsets");
+    reset_sketch_timing(ctx);
+    const int per = both_strands ? 2 : 1;
+    const size_t slots = (size_t)n_reads * per, H = (size_t)p->num_hashes, S = (size_t)p->ordered_sketch_size;
+    std::vector<int64_t> rows(slots);
+    for (uint32_t r = 0; r < n_reads; r++) {
+        int stt = read_status(*p, offsets[r + 1] - offsets[r]);
+        if (out_status) out_status[r] = stt;
+        for (int s = 0; s < per; s++) rows[(size_t)r * per + s] = (int64_t)r * per + s;
+    }
+    if (!slots) return MHAPB_OK;
+    rc = h2d_bases(ctx, bases, offsets, n_reads);
+    if (rc) return rc;
+    const bool want_ord = out_ord || out_ord_n;
+    if (out_minhash) { CU(ctx, ctx->out_minhash.ensure(slots * H * 4)); CU(ctx, cudaMemsetAsync(ctx->out_minhash.p, 0, slots * H * 4, ctx->stream)); }
+    if (want_ord) {
+        CU(ctx, ctx->out_ord.ensure(slots * S * 8)); CU(ctx, cudaMemsetAsync(ctx->out_ord.p, 0, slots * S * 8, ctx->stream));
+        CU(ctx, ctx->out_ordn.ensure(slots * 4)); CU(ctx, cudaMemsetAsync(ctx->out_ordn.p, 0, slots * 4, ctx->stream));
+    }
+    rc = sketch_core(ctx, *p, ctx->bases.as<uint8_t>(), offsets, n_reads, both_strands, rows,
+                     out_minhash ? ctx->out_minhash.as<int32_t>() : nullptr, want_ord ? ctx->out_ord.as<int32_t>() : nullptr, (int)S,
+                     want_ord ? ctx->out_ordn.as<int32_t>() : nullptr);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[6], ctx->stream);
+    if (out_minhash) CU(ctx, cudaMemcpyAsync(out_minhash, ctx->out_minhash.p, slots * H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ord) CU(ctx, cudaMemcpyAsync(out_ord, ctx->out_ord.p, slots * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ord_n) CU(ctx, cudaMemcpyAsync(out_ord_n, ctx->out_ordn.p, slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev[7], ctx->stream);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[6], ctx->ev[7]);
+    return MHAPB_OK;
+}
+
+// ---- .dat ------------------------------------------------------------------------------------
+static inline uint8_t *put32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; return p + 4; }
+static inline uint32_t get32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+int64_t mhapb_dat_encode(int64_t id, int is_fwd, const char *header, int32_t seq_len, const int32_t *minhash, int32_t H,
+                         int32_t seq_len_kmers, int32_t ok, const int32_t *ord, int32_t ord_n, uint8_t *buf)
+{
+    char idbuf[32];
+    if (!header) { snprintf(idbuf, sizeof idbuf, "%lld", (long long)id); header = idbuf; }
+    const size_t hl = strlen(header);   // ASCII headers: modified UTF-8 == the bytes
+    if (hl > 65535 || H < 0 || ord_n < 0) return MHAPB_EINVAL;
+    const int64_t payload = 1 + 8 + 2 + (int64_t)hl + 4 + 4 + 4 * (int64_t)H + 12 + 8 * (int64_t)ord_n;
+    const int64_t total = 1 + 4 + payload;
+    if (!buf) return total;
+    uint8_t *p = buf;
+    *p++ = is_fwd ? 1 : 0;                                  // SequenceSketchStreamer.java:352-356
+    p = put32(p, (uint32_t)payload);
+    *p++ = is_fwd ? 1 : 0;                                  // SequenceSketch.java:135 writeBoolean
+    p = put32(p, (uint32_t)((uint64_t)id >> 32)); p = put32(p, (uint32_t)(uint64_t)id);   // writeLong
+    *p++ = (uint8_t)(hl >> 8); *p++ = (uint8_t)hl; memcpy(p, header, hl); p += hl;        // writeUTF
+    p = put32(p, (uint32_t)seq_len);
+    p = put32(p, (uint32_t)H);                              // MinHashSketch.java:218-230
+    for (int i = 0; i < H; i++) p = put32(p, (uint32_t)minhash[i]);
+    p = put32(p, (uint32_t)seq_len_kmers);                  // BottomOverlapSketch.java:561-585
+    p = put32(p, (uint32_t)ok);
+    p = put32(p, (uint32_t)ord_n);
+    for (int i = 0; i < 2 * ord_n; i++) p = put32(p, (uint32_t)ord[i]);
+    return total;
+}
+
+int mhapb_dat_decode(const uint8_t *buf, uint64_t len, int64_t id_offset, uint32_t *n_records, int32_t *num_hashes,
+                     int32_t *max_ord, int32_t *ordered_kmer_size, int64_t *ids, uint8_t *is_fwd, int32_t *seq_len,
+                     int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n)
+{
+    if (!buf && len) return MHAPB_EINVAL;
+    // pass 1: shape
+    uint32_t n = 0; int32_t H = -1, mo = 0, okk = -1;
+    uint64_t off = 0;
+    while (off + 5 <= len) {
+        const uint32_t payload = get32(buf + off + 1);
+        if (off + 5 + payload > len || payload < 1 + 8 + 2 + 4 + 4 + 12) return MHAPB_EINVAL;   // truncated / corrupt
+        const uint8_t *p = buf + off + 5;
+        const uint32_t hl = ((uint32_t)p[9] << 8) | p[10];
+        if (11 + hl + 8 > payload) return MHAPB_EINVAL;
+        const int32_t h = (int32_t)get32(p + 11 + hl + 4);
+        if (h < 0 || 11ull + hl + 8 + 4ull * h + 12 > payload) return MHAPB_EINVAL;
+        if (H < 0) H = h; else if (H != h) return MHAPB_EINVAL;   // MinHashSearch.java:105
+        const uint8_t *o = p + 11 + hl + 8 + 4ull * h;
+        const int32_t kk = (int32_t)get32(o + 4), on = (int32_t)get32(o + 8);
+        if (on < 0 || 11ull + hl + 8 + 4ull * h + 12 + 8ull * on != payload) return MHAPB_EINVAL;
+        if (okk < 0) okk = kk; else if (okk != kk) return MHAPB_EINVAL;   // BottomOverlapSketch.java:594
+        mo = std::max(mo, on);
+        n++; off += 5 + payload;
+    }
+    if (off != len) return MHAPB_EINVAL;
+    const bool sizing = !ids && !is_fwd && !seq_len && !seq_len_kmers && !minhash && !ord_hash_pos && !ord_n;
+    const int32_t stride = (max_ord && !sizing && *max_ord > 0) ? *max_ord : mo;
+    if (!sizing && stride < mo) return MHAPB_EINVAL;
+    if (n_records) *n_records = n;
+    if (num_hashes) *num_hashes = H < 0 ? 0 : H;
+    if (ordered_kmer_size) *ordered_kmer_size = okk < 0 ? 0 : okk;
+    if (sizing) { if (max_ord) *max_ord = mo; return MHAPB_OK; }
+    off = 0;
+    for (uint32_t r = 0; r < n; r++) {
+        const uint32_t payload = get32(buf + off + 1);
+        const uint8_t *p = buf + off + 5;
+        if (is_fwd) is_fwd[r] = p[0] ? 1 : 0;
+        if (ids) ids[r] = (int64_t)(((uint64_t)get32(p + 1) << 32) | get32(p + 5)) + id_offset;
+        const uint32_t hl = ((uint32_t)p[9] << 8) | p[10];
+        const uint8_t *q = p + 11 + hl;
+        if (seq_len) seq_len[r] = (int32_t)get32(q);
+        const int32_t h = (int32_t)get32(q + 4);
+        if (minhash) for (int i = 0; i < h; i++) minhash[(size_t)r * h + i] = (int32_t)get32(q + 8 + 4ull * i);
+        const uint8_t *o = q + 8 + 4ull * h;
+        if (seq_len_kmers) seq_len_kmers[r] = (int32_t)get32(o);
+        const int32_t on = (int32_t)get32(o + 8);
+        if (ord_n) ord_n[r] = on;
+        if (ord_hash_pos) {
+            int32_t *dst = ord_hash_pos + (size_t)r * stride * 2;
+            for (int i = 0; i < 2 * on; i++) dst[i] = (int32_t)get32(o + 12 + 4ull * i);
+            for (int i = 2 * on; i < 2 * stride; i++) dst[i] = 0;
+        }
+        off += 5 + payload;
+    }
+    return MHAPB_OK;
+}
+
+int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases, const uint64_t *offsets,
+                        const int64_t *ids, uint32_t n_reads, int both_strands, uint8_t **out, uint64_t *out_len, uint32_t *n_records)
+{
+    if (!ctx || !out || !out_len) return MHAPB_EINVAL;
+    int rc = check_sketch_params(ctx, p);
+    if (rc) return rc;
+    const int per = both_strands ? 2 : 1;
+    const size_t slots = (size_t)n_reads * per, H = (size_t)p->num_hashes, S = (size_t)p->ordered_sketch_size;
+    std::vector<int32_t> mh(slots * H), ord(slots * S * 2), on(slots), status(n_reads);
+    rc = mhapb_sketch(ctx, p, bases, offsets, n_reads, both_strands, mh.data(), ord.data(), on.data(), status.data());
+    if (rc) return rc;
+    uint64_t total = 0; uint32_t nrec = 0;
+    for (uint32_t r = 0; r < n_reads; r++) {
+        if (status[r]) continue;
+        for (int s = 0; s < per; s++) {
+            size_t j = (size_t)r * per + s;
+            int64_t id = ids ? ids[r] : (int64_t)r + 1;
+            total += (uint64_t)mhapb_dat_encode(id, s == 0, nullptr, 0, nullptr, (int32_t)H, 0, 0, nullptr, on[j], nullptr);
+            nrec++;
+        }
+    }
+    uint8_t *buf = (uint8_t *)malloc(total ? total : 1);
+    if (!buf) return fail(ctx, MHAPB_ENOMEM, "malloc .dat buffer");
+    uint8_t *w = buf;
+    for (uint32_t r = 0; r < n_reads; r++) {
+        if (status[r]) continue;
+        const int32_t len = (int32_t)(offsets[r + 1] - offsets[r]);
+        for (int s = 0; s < per; s++) {
+            size_t j = (size_t)r * per + s;
+            int64_t id = ids ? ids[r] : (int64_t)r + 1;
+            w += mhapb_dat_encode(id, s == 0, nullptr, len, mh.data() + j * H, (int32_t)H, len - p->ordered_kmer_size + 1,
+                                  p->ordered_kmer_size, ord.data() + j * S * 2, on[j], w);
+        }
+    }
+    *out = buf; *out_len = total;
+    if (n_records) *n_records = nrec;
+    return MHAPB_OK;
+}
+
+// ---- store -------------------------------------------------------------------------------------
+int mhapb_store_reset(mhapb_ctx *ctx, const mhapb_sketch_params *p)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return store_configure(ctx, p);
+}
+
+int mhapb_store_add_reads(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, const int64_t *ids, uint32_t n_reads,
+                          int both_strands, int64_t *n_added)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!offsets || (!bases && n_reads && offsets[n_reads] > offsets[0])) return fail(ctx, MHAPB_EINVAL, "null bases/offsets");
+    reset_sketch_timing(ctx);
+    return add_reads_locked(ctx, bases, offsets, ids, n_reads, both_strands, n_added);
+}
+
+static int add_sketches_common(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd, const int32_t *seq_len,
+                               const int32_t *seq_len_kmers, const void *minhash, const void *ord, const int32_t *ord_n,
+                               int32_t ord_stride, uint32_t n, cudaMemcpyKind kind)
+{
+    Store &s = ctx->store;
+    if (!s.configured) return fail(ctx, MHAPB_ESTATE, "mhapb_store_reset must be called first");
+    if (!ids || !is_fwd || !seq_len || !seq_len_kmers || !minhash || !ord || !ord_n) return fail(ctx, MHAPB_EINVAL, "null sketch column");
+    if (ord_stride < 1) return fail(ctx, MHAPB_EINVAL, "ord_stride %d", ord_stride);
+    if (!n) return MHAPB_OK;
+    int32_t max_on = 0;
+    for (uint32_t i = 0; i < n; i++) { if (ord_n[i] < 0 || ord_n[i] > ord_stride) return fail(ctx, MHAPB_EINVAL, "ord_n[%u]=%d exceeds stride %d", i, ord_n[i], ord_stride); max_on = std::max(max_on, ord_n[i]); }
+    if (max_on > s.ord_stride) {
+        if (s.n) return fail(ctx, MHAPB_EINVAL, "ordered sketch of %d entries exceeds the store's stride %d", max_on, s.ord_stride);
+        s.ord_stride = max_on;
+    }
+    const size_t meta0 = s.h_id.size();
+    for (uint32_t i = 0; i < n; i++) {
+        int rc = store_push_meta(ctx, ids[i], is_fwd[i] != 0, seq_len[i], seq_len_kmers[i], ord_n[i]);
+        if (rc) {
+            for (size_t j = meta0; j < s.h_id.size(); j++) s.seen.erase(((uint64_t)s.h_id[j] << 1) | s.h_fwd[j]);
+            s.h_id.resize(meta0); s.h_fwd.resize(meta0); s.h_len.resize(meta0); s.h_lenk.resize(meta0); s.h_ordn.resize(meta0);
+            return rc;
+        }
+    }
+    int rc = store_reserve(ctx, n);
+    if (rc) return rc;
+    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
+    const int64_t n0 = s.n;
+    CU(ctx, cudaMemcpyAsync(s.minhash.as<int32_t>() + (size_t)n0 * H, minhash, (size_t)n * H * 4, kind, ctx->stream));
+    if ((size_t)ord_stride == S) CU(ctx, cudaMemcpyAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, ord, (size_t)n * S * 8, kind, ctx->stream));
+    else {
+        CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)n * S * 8, ctx->stream));
+        CU(ctx, cudaMemcpy2DAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, S * 8, ord, (size_t)ord_stride * 8, std::min(S, (size_t)ord_stride) * 8, n, kind, ctx->stream));
+    }
+    CU(ctx, cudaMemcpyAsync(s.ord_n.as<int32_t>() + n0, ord_n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    s.n += n;
+    s.indexed = false;
+    return store_sync_columns(ctx, n0);
+}
+
+int mhapb_store_add_sketches(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd, const int32_t *seq_len,
+                             const int32_t *seq_len_kmers, const int32_t *minhash, const int32_t *ord_hash_pos,
+                             const int32_t *ord_n, int32_t ord_stride, uint32_t n)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return add_sketches_common(ctx, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hash_pos, ord_n, ord_stride, n, cudaMemcpyHostToDevice);
+}
+
+int mhapb_store_add_sketches_device(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd, const int32_t *seq_len,
+                                    const int32_t *seq_len_kmers, const void *d_minhash, const void *d_ord, const int32_t *ord_n, uint32_t n)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return add_sketches_common(ctx, ids, is_fwd, seq_len, seq_len_kmers, d_minhash, d_ord, ord_n, ctx->store.p.ordered_sketch_size, n, cudaMemcpyDeviceToDevice);
+}
+
+int64_t mhapb_store_size(mhapb_ctx *ctx)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->store.n;
+}
+
+int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, int32_t *seq_len, int32_t *seq_len_kmers,
+                    int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (idx < 0 || idx >= s.n) return fail(ctx, MHAPB_EINVAL, "store index %lld out of range", (long long)idx);
+    if (id) *id = s.h_id[idx];
+    if (is_fwd) *is_fwd = s.h_fwd[idx];
+    if (seq_len) *seq_len = s.h_len[idx];
+    if (seq_len_kmers) *seq_len_kmers = s.h_lenk[idx];
+    if (ord_n) *ord_n = s.h_ordn[idx];
+    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
+    if (minhash) CU(ctx, cudaMemcpyAsync(minhash, s.minhash.as<int32_t>() + (size_t)idx * H, H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ord_hash_pos) CU(ctx, cudaMemcpyAsync(ord_hash_pos, s.ord.as<int32_t>() + (size_t)idx * S * 2, (size_t)s.h_ordn[idx] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return MHAPB_OK;
+}
+
+int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, int64_t *n, int32_t *num_hashes, int32_t *ord_stride)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Store &s = ctx->store;
+    if (d_minhash) *d_minhash = s.minhash.p;
+    if (d_ord) *d_ord = s.ord.p;
+    if (n) *n = s.n;
+    if (num_hashes) *num_hashes = s.p.num_hashes;
+    if (ord_stride) *ord_stride = s.ord_stride;
+    return MHAPB_OK;
+}
+
+int mhapb_index_build(mhapb_ctx *ctx)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    return index_build(ctx);
+}
+
+// ---- search ------------------------------------------------------------------------------------
+int mhapb_search_self(mhapb_ctx *ctx, const mhapb_search_params *sp, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+{
+    if (!ctx || !sp) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (!s.configured || s.n == 0) return fail(ctx, MHAPB_ESTATE, "search on an empty store");
+    ctx->store.ord_n.as<int32_t>();
+    // ord_n column may have been produced on the device (add_reads): the host mirror is exact by construction
+    QuerySet q{};
+    q.d_minhash = s.minhash.as<int32_t>(); q.d_ord = s.ord.as<int32_t>(); q.d_ordn = s.ord_n.as<int32_t>();
+    q.d_lenk = s.lenk.as<int32_t>(); q.d_len = s.len.as<int32_t>(); q.d_id = s.id.as<int64_t>(); q.ord_stride = s.ord_stride;
+    q.h_id = s.h_id.data(); q.h_fwd = s.h_fwd.data(); q.h_len = s.h_len.data();
+    int64_t first = std::max<int64_t>(0, sp->query_first);
+    int64_t last = sp->query_count < 0 ? s.n : std::min<int64_t>(s.n, first + sp->query_count);
+    for (int64_t i = first; i < last; i++) if (s.h_fwd[i]) q.list.push_back((uint32_t)i);   // AbstractMatchSearch.java:128-129
+    return search_core(ctx, sp, q, 1, out, n_out, stats);
+}
+
+static int search_query_sketches_locked(mhapb_ctx *ctx, const mhapb_search_params *sp, const int64_t *ids, const uint8_t *is_fwd,
+                                        const int32_t *seq_len, const int32_t *seq_len_kmers, const int32_t *d_minhash,
+                                        const int32_t *d_ord, const int32_t *d_ordn, int32_t ord_stride, uint32_t n,
+                                        mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+{
+    CU(ctx, ctx->q_lenk.ensure((size_t)n * 4 + 4));
+    CU(ctx, ctx->q_len.ensure((size_t)n * 4 + 4));
+    CU(ctx, ctx->q_id.ensure((size_t)n * 8 + 8));
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(ctx->q_lenk.p, seq_len_kmers, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->q_len.p, seq_len, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->q_id.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    QuerySet q{};
+    q.d_minhash = d_minhash; q.d_ord = d_ord; q.d_ordn = d_ordn;
+    q.d_lenk = ctx->q_lenk.as<int32_t>(); q.d_len = ctx->q_len.as<int32_t>(); q.d_id = ctx->q_id.as<int64_t>(); q.ord_stride = ord_stride;
+    q.h_id = ids; q.h_fwd = is_fwd; q.h_len = seq_len;
+    for (uint32_t i = 0; i < n; i++) if (is_fwd[i]) q.list.push_back(i);   // AbstractMatchSearch.java:225 dequeue(true)
+    return search_core(ctx, sp, q, 0, out, n_out, stats);
+}
+
+int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, const int64_t *ids, const uint8_t *is_fwd,
+                                const int32_t *seq_len, const int32_t *seq_len_kmers, const int32_t *minhash,
+                                const int32_t *ord_hash_pos, const int32_t *ord_n, int32_t ord_stride, uint32_t n,
+                                mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+{
+    if (!ctx || !sp) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (!s.configured || s.n == 0) return fail(ctx, MHAPB_ESTATE, "search on an empty store");
+    if (n && (!ids || !is_fwd || !seq_len || !seq_len_kmers || !minhash || !ord_hash_pos || !ord_n)) return fail(ctx, MHAPB_EINVAL, "null query column");
+    const size_t H = (size_t)s.p.num_hashes;
+    CU(ctx, ctx->q_minhash.ensure((size_t)n * H * 4 + 4));
+    CU(ctx, ctx->q_ord.ensure((size_t)n * ord_stride * 8 + 8));
+    CU(ctx, ctx->q_ordn.ensure((size_t)n * 4 + 4));
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(ctx->q_minhash.p, minhash, (size_t)n * H * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->q_ord.p, ord_hash_pos, (size_t)n * ord_stride * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->q_ordn.p, ord_n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return search_query_sketches_locked(ctx, sp, ids, is_fwd, seq_len, seq_len_kmers, ctx->q_minhash.as<int32_t>(),
+                                        ctx->q_ord.as<int32_t>(), ctx->q_ordn.as<int32_t>(), ord_stride, n, out, n_out, stats);
+}
+
+int mhapb_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, const char *bases, const uint64_t *offsets,
+                             const int64_t *ids, uint32_t n_reads, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+{
+    if (!ctx || !sp) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (!s.configured || s.n == 0) return fail(ctx, MHAPB_ESTATE, "search on an empty store");
+    if (!offsets || (!bases && n_reads && offsets[n_reads] > offsets[0])) return fail(ctx, MHAPB_EINVAL, "null bases/offsets");
+    reset_sketch_timing(ctx);
+    // forward-only sketches of the valid query reads, compacted
+    std::vector<int64_t> rows(n_reads, -1), qid; std::vector<uint8_t> qfwd; std::vector<int32_t> qlen, qlenk;
+    int64_t nq = 0;
+    for (uint32_t r = 0; r < n_reads; r++) {
+        uint64_t len = offsets[r + 1] - offsets[r];
+        if (read_status(s.p, len)) continue;
+        rows[r] = nq++;
+        qid.push_back(ids ? ids[r] : (int64_t)r + 1); qfwd.push_back(1); qlen.push_back((int32_t)len);
+        qlenk.push_back((int32_t)len - s.p.ordered_kmer_size + 1);
+    }
+    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.p.ordered_sketch_size;
+    CU(ctx, ctx->q_minhash.ensure((size_t)nq * H * 4 + 4));
+    CU(ctx, ctx->q_ord.ensure((size_t)nq * S * 8 + 8));
+    CU(ctx, ctx->q_ordn.ensure((size_t)nq * 4 + 4));
+    if (nq) {
+        int rc = h2d_bases(ctx, bases, offsets, n_reads);
+        if (rc) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->q_ord.p, 0, (size_t)nq * S * 8, ctx->stream));
+        rc = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, 0, rows, ctx->q_minhash.as<int32_t>(), ctx->q_ord.as<int32_t>(), (int)S, ctx->q_ordn.as<int32_t>());
+        if (rc) return rc;
+    }
+    return search_query_sketches_locked(ctx, sp, qid.data(), qfwd.data(), qlen.data(), qlenk.data(), ctx->q_minhash.as<int32_t>(),
+                                        ctx->q_ord.as<int32_t>(), ctx->q_ordn.as<int32_t>(), (int32_t)S, (uint32_t)nq, out, n_out, stats);
+}
+
+int mhapb_format_match(const mhapb_hit *h, char *buf, size_t buflen)
+{
+    if (!h || !buf) return MHAPB_EINVAL;
+    // impl/MatchResult.java:54-57 strand flip, :61-64 clamp, :98-113 format
+    const int32_t a1 = h->from_fwd ? h->a1 : h->from_len - h->a2 - 1;
+    const int32_t a2 = h->from_fwd ? h->a2 : h->from_len - h->a1 - 1;
+    const int32_t b1 = h->to_fwd ? h->b1 : h->to_len - h->b2 - 1;
+    const int32_t b2 = h->to_fwd ? h->b2 : h->to_len - h->b1 - 1;
+    const double score = h->score > 1.0 ? 1.0 : h->score;
+    return snprintf(buf, buflen, "%lld %lld %.6f %.6f %d %d %d %d %d %d %d %d", (long long)h->from_id, (long long)h->to_id,
+                    1.0 - score, (double)h->valid_count, h->from_fwd ? 0 : 1, a1, a2, h->from_len, h->to_fwd ? 0 : 1, b1, b2, h->to_len);
+}
+
+int mhapb_minhash_equal_count(mhapb_ctx *ctx, int64_t i, int64_t j, int32_t *out_equal)
+{
+    if (!ctx || !out_equal) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (i < 0 || j < 0 || i >= s.n || j >= s.n) return fail(ctx, MHAPB_EINVAL, "store index out of range");
+    CU(ctx, ctx->eq.ensure(16));
+    const size_t H = (size_t)s.p.num_hashes;
+    int launches = 0;
+    CU(ctx, launch_equal_count(ctx->stream, s.minhash.as<int32_t>() + (size_t)i * H, s.minhash.as<int32_t>() + (size_t)j * H, (int)H, ctx->eq.as<int32_t>(), &launches));
+    CU(ctx, cudaMemcpyAsync(out_equal, ctx->eq.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.kernel_launches += launches;
+    return MHAPB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,93 @@
+// engine.h -- internal interface between the C-ABI layer (api.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mhapb {
+
+// One strand of one read to be sketched.  `row` is the output row (sketch slot / store index).
+struct StrandDesc {
+    uint64_t base_off;   // offset of the read's first char in the bases buffer
+    uint64_t koff;       // offset of this strand's region in the k-mer key scratch
+    uint32_t len;        // read length in bases
+    uint32_t row;        // output row
+    uint32_t rc;         // 1: sketch the reverse complement (Sequence.getReverseCompliment)
+    uint32_t pad;
+};
+
+// ---- K1 ------------------------------------------------------------------------------------
+// Strands with nk = len-k+1 <= kShortMaxKmers use the shared-memory dedup table; longer ones the
+// global-memory table.
+constexpr int kShortMaxKmers = 16384;
+constexpr int kMaxNumHashes = 2048;
+constexpr int kMaxOrderedSketch = 4096;
+
+struct SketchScratch {
+    uint64_t *keys;      // [cap_kmers] distinct k-mer hashes per strand: light from the front, heavy from the back
+    uint32_t *wts;       // [cap_kmers] weights of the heavy keys (same index as keys)
+    int32_t  *nlight;    // [n_strands]
+    int32_t  *nheavy;    // [n_strands]
+    uint32_t *dupcnt;    // [grid][table_cap] zero between uses
+    uint64_t *gtable;    // [grid_long][long_cap] global dedup tables (long strands only)
+    uint32_t *ohash;     // [grid][ohash_cap] ordered-hash staging for long strands
+    uint32_t *counters;  // work-queue counters
+};
+
+// K1a: hash every k-mer (MurmurHash3_x64_128 h1), de-duplicate with counts.
+cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
+                              int first_long /* descs [first_long, n) are long strands */, int max_kmers_short,
+                              int max_kmers_long, int k, int unweighted, const SketchScratch &sc, int *launches);
+// K1b: H-step XORShift chain per distinct k-mer, per-word signed minimum -> minhash rows.
+cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
+                           const SketchScratch &sc, int32_t *d_minhash, int *launches);
+// K1c: MurmurHash3_x86_32 of every ordered k-mer, bottom-S by (signed hash, position), sorted.
+cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
+                           int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,
+                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int *launches);
+int hash_dedup_grid();
+int ordered_grid();
+size_t dedup_table_cap_short();   // slots per block in SketchScratch.dupcnt
+
+// ---- K2 ------------------------------------------------------------------------------------
+struct IndexView {
+    uint64_t *slots;      // [H][capw]  (value | begin<<32), empty = ~0
+    uint32_t *postings;   // [n_store*H] sketch index, MSB set on the last entry of a bucket
+    int       log2capw;
+    int       H;
+    int64_t   n_store;
+};
+
+cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_t n_store, int H, IndexView iv,
+                               uint32_t *d_tmp_start /*[H*capw]*/, uint32_t *d_block_sums, int *launches);
+
+struct Candidate { uint32_t q; uint32_t t; uint32_t count; };
+
+struct ProbeArgs {
+    const int32_t *q_minhash;  // [nq][H]
+    const int64_t *q_id;       // [nq]
+    const int32_t *q_len;      // [nq] bases
+    const uint32_t *q_list;    // [nq_list] indices into the query arrays (NULL: 0..nq-1)
+    int64_t nq_list;
+    const int64_t *t_id;       // [n_store]
+    const int32_t *t_len;      // [n_store]
+    int to_self, num_min_matches, min_store_length;
+    Candidate *cand; uint64_t cand_cap;
+    unsigned long long *counters;  // [0]=n_cand [1]=elements_processed [2]=sequences_hit
+};
+cudaError_t launch_probe(cudaStream_t st, IndexView iv, ProbeArgs a, int *launches);
+
+struct OverlapOut { int32_t a1, a2, b1, b2, valid, inter, kmin, empty; };
+
+struct FilterArgs {
+    const Candidate *cand; uint64_t n_cand;
+    const int32_t *q_ord; const int32_t *q_ord_n; const int32_t *q_lenk; int q_stride;   // [nq][stride][2]
+    const int32_t *t_ord; const int32_t *t_ord_n; const int32_t *t_lenk; int t_stride;
+    double max_shift;
+    int32_t *scratch; uint32_t scratch_entries; uint32_t n_threads;   // 3 arrays [entries][n_threads]
+    OverlapOut *out;
+};
+cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches);
+
+cudaError_t launch_equal_count(cudaStream_t st, const int32_t *a, const int32_t *b, int H, int32_t *d_out, int *launches);
+
+} // namespace mhapb

@@ -1,0 +1,525 @@
+// search.cu -- K2: MinHashSearch on sm_100a: inverted-index build, probe + hit counting, and the
+// second-stage ordered-sketch filter.
+//
+// Replaces (paths relative to /root/reference/src/main/java/edu/umd/marbl/mhap/):
+//   K2a k_index_*   : impl/MinHashSearch.java:101-147 (addSequence: H maps value -> list of ids)
+//   K2b k_probe     : impl/MinHashSearch.java:150-225 (findMatches: bucket walk, hit counts, filters)
+//   K2c k_filter    : sketch/BottomOverlapSketch.java:592-630 (getOverlapInfo) with MatchData :64-298,
+//                     recordMatchingKmers :397-516, computeKBottomSketchJaccard :304-364 and
+//                     utils/Utils.java:445-494 (quickSelect)
+// HBM / L2 random-access bound integer work; no tensor cores.
+#include "engine.h"
+
+namespace mhapb {
+
+static constexpr uint64_t kEmptySlot = ~0ull;
+static constexpr unsigned kFull = 0xffffffffu;
+static constexpr uint32_t kLastFlag = 0x80000000u;
+
+__device__ __forceinline__ uint32_t slot_hash(uint32_t value, int log2capw)
+{
+    return (value * 0x9E3779B1u) >> (32 - log2capw);   // Fibonacci hashing into one word's sub-table
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: index build (count -> scan -> fill -> pack)
+// ---------------------------------------------------------------------------------------------
+// Sub-table w (capw slots, capw = pow2 >= 2*n_store) holds the distinct values of min-hash word w,
+// i.e. it is the reference's hashes.get(w) map.  During the count pass a slot is (value | cnt<<32).
+__global__ void k_index_count(const int32_t *__restrict__ minhash, int64_t n_store, int H, uint64_t *slots, int log2capw)
+{
+    const int64_t total = n_store * H;
+    const uint32_t capmask = (1u << log2capw) - 1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % H);
+        const uint32_t v = (uint32_t)minhash[i];
+        uint64_t *sub = slots + ((size_t)w << log2capw);
+        uint32_t p = slot_hash(v, log2capw);
+        for (;;) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&sub[p]);
+            if (cur == kEmptySlot) {
+                cur = atomicCAS(reinterpret_cast<unsigned long long *>(&sub[p]), (unsigned long long)kEmptySlot, (unsigned long long)v);
+                if (cur == kEmptySlot) cur = v;
+            }
+            if ((uint32_t)cur == v) {
+                atomicAdd(reinterpret_cast<unsigned int *>(&sub[p]) + 1, 1u);   // cnt lives in the high word
+                break;
+            }
+            p = (p + 1) & capmask;
+        }
+    }
+}
+
+// three-kernel exclusive scan of the slot counts (empty slots count 0)
+constexpr int kScanThreads = 512, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t slot_cnt(uint64_t s) { return s == kEmptySlot ? 0u : (uint32_t)(s >> 32); }
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
+{
+    __shared__ uint32_t s_w[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = lane < kScanThreads / 32 ? s_w[lane] : 0, xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(kFull, xi, o); if (lane >= o) xi += t; }
+        if (lane < kScanThreads / 32) s_w[lane] = xi - x;
+        if (lane == 31 && total) *total = xi;
+    }
+    __syncthreads();
+    uint32_t r = incl - v + s_w[w];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const uint64_t *__restrict__ slots, size_t n, uint32_t *block_sums)
+{
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++) if (base + q < n) sum += slot_cnt(slots[base + q]);
+    __shared__ uint32_t s_total;
+    block_exclusive_scan(sum, &s_total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s_total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(uint32_t *block_sums, size_t nb)
+{
+    __shared__ uint32_t s_carry, s_total;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (size_t b0 = 0; b0 < nb; b0 += kScanThreads) {
+        size_t i = b0 + threadIdx.x;
+        uint32_t v = i < nb ? block_sums[i] : 0;
+        uint32_t ex = block_exclusive_scan(v, &s_total);
+        if (i < nb) block_sums[i] = ex + s_carry;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint64_t *__restrict__ slots, size_t n, const uint32_t *__restrict__ block_sums, uint32_t *start)
+{
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t c[kScanItems], sum = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++) { c[q] = base + q < n ? slot_cnt(slots[base + q]) : 0; sum += c[q]; }
+    uint32_t run = block_exclusive_scan(sum, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < kScanItems; q++) { if (base + q < n) start[base + q] = run; run += c[q]; }
+}
+
+__global__ void k_index_fill(const int32_t *__restrict__ minhash, int64_t n_store, int H, const uint64_t *__restrict__ slots,
+                             int log2capw, uint32_t *start, uint32_t *postings)
+{
+    const int64_t total = n_store * H;
+    const uint32_t capmask = (1u << log2capw) - 1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % H);
+        const uint32_t v = (uint32_t)minhash[i];
+        const size_t sub = (size_t)w << log2capw;
+        uint32_t p = slot_hash(v, log2capw);
+        while ((uint32_t)slots[sub + p] != v || slots[sub + p] == kEmptySlot) p = (p + 1) & capmask;
+        uint32_t pos = atomicAdd(&start[sub + p], 1u);
+        postings[pos] = (uint32_t)(i / H);
+    }
+}
+
+// after the fill start[] holds each bucket's end: flag the last posting, rewrite slot as (value | begin<<32)
+__global__ void k_index_pack(uint64_t *slots, size_t n, const uint32_t *__restrict__ start, uint32_t *postings)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t s = slots[i];
+        if (s == kEmptySlot) continue;
+        uint32_t cnt = (uint32_t)(s >> 32), end = start[i];
+        postings[end - 1] |= kLastFlag;
+        slots[i] = (uint64_t)(uint32_t)s | ((uint64_t)(end - cnt) << 32);
+    }
+}
+
+cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_t n_store, int H, IndexView iv,
+                               uint32_t *d_tmp_start, uint32_t *d_block_sums, int *launches)
+{
+    const size_t nslots = (size_t)H << iv.log2capw;
+    cudaError_t e = cudaMemsetAsync(iv.slots, 0xff, nslots * 8, st);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 8;
+    k_index_count<<<grid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw);
+    const size_t nb = (nslots + kScanTile - 1) / kScanTile;
+    k_scan_tiles<<<(unsigned)nb, kScanThreads, 0, st>>>(iv.slots, nslots, d_block_sums);
+    k_scan_sums<<<1, kScanThreads, 0, st>>>(d_block_sums, nb);
+    k_scan_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(iv.slots, nslots, d_block_sums, d_tmp_start);
+    k_index_fill<<<grid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw, d_tmp_start, iv.postings);
+    k_index_pack<<<grid, 256, 0, st>>>(iv.slots, nslots, d_tmp_start, iv.postings);
+    *launches += 6;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b: probe + hit counting
+// ---------------------------------------------------------------------------------------------
+// One CTA per query.  The H buckets are walked by the CTA's threads and the per-target hit counts
+// (the reference's bestSequenceHit map) live in a shared-memory open-addressed table.  A query
+// that touches more distinct targets than the table holds is recounted with dense per-range
+// counters (exact, a few extra bucket walks; only repeat-rich queries get there).
+constexpr int kProbeThreads = 128;
+constexpr int kHitCap = 4096;          // slots in the shared table (32 KB)
+constexpr int kHitMaxDistinct = 3072;  // switch to the dense path above this many distinct targets
+constexpr int kDenseRange = 2 * kHitCap * 2;   // u16 counters in the same 32 KB
+
+struct HitSlot { uint32_t t; uint32_t c; };
+
+__device__ __forceinline__ bool find_bucket(const IndexView &iv, int w, uint32_t v, uint32_t *begin)
+{
+    const uint64_t *sub = iv.slots + ((size_t)w << iv.log2capw);
+    const uint32_t capmask = (1u << iv.log2capw) - 1;
+    uint32_t p = slot_hash(v, iv.log2capw);
+    for (;;) {
+        uint64_t s = __ldg(&sub[p]);
+        if (s == kEmptySlot) return false;
+        if ((uint32_t)s == v) { *begin = (uint32_t)(s >> 32); return true; }
+        p = (p + 1) & capmask;
+    }
+}
+
+__device__ __forceinline__ bool pass_filters(const ProbeArgs &a, int64_t qid, int32_t qlen, uint32_t t, uint32_t count)
+{
+    const int64_t tid = a.t_id[t];
+    if (a.to_self && tid == qid) return false;                                   // MinHashSearch.java:200
+    if ((int)count < a.num_min_matches) return false;                            // :204
+    const int32_t tlen = a.t_len[t];
+    const int ms = a.min_store_length;
+    if (tlen < ms && qlen < ms) return false;                                    // :211
+    if (a.to_self && tid > qid && tlen >= ms && qlen >= ms) return false;        // :215-219
+    if (a.to_self && tlen < ms && qlen >= ms) return false;                      // :222-225
+    return true;
+}
+
+__device__ __forceinline__ void emit_candidate(const ProbeArgs &a, uint32_t q, uint32_t t, uint32_t count)
+{
+    unsigned long long p = atomicAdd(&a.counters[0], 1ull);
+    if (p < a.cand_cap) { Candidate c; c.q = q; c.t = t; c.count = count; a.cand[p] = c; }
+}
+
+__global__ void __launch_bounds__(kProbeThreads)
+k_probe(IndexView iv, ProbeArgs a)
+{
+    __shared__ HitSlot s_tab[kHitCap];
+    __shared__ int s_distinct, s_overflow;
+    __shared__ unsigned long long s_elements;
+
+    for (int64_t qi = blockIdx.x; qi < a.nq_list; qi += gridDim.x) {
+        const uint32_t q = a.q_list ? a.q_list[qi] : (uint32_t)qi;
+        const int32_t *qmh = a.q_minhash + (size_t)q * iv.H;
+        const int64_t qid = a.q_id[q];
+        const int32_t qlen = a.q_len[q];
+
+        for (int i = threadIdx.x; i < kHitCap; i += blockDim.x) { s_tab[i].t = 0xffffffffu; s_tab[i].c = 0; }
+        if (threadIdx.x == 0) { s_distinct = 0; s_overflow = 0; s_elements = 0; }
+        __syncthreads();
+
+        unsigned long long elements = 0;
+        for (int w = threadIdx.x; w < iv.H; w += blockDim.x) {
+            uint32_t begin;
+            if (!find_bucket(iv, w, (uint32_t)qmh[w], &begin)) continue;
+            for (uint32_t p = begin;; p++) {
+                const uint32_t raw = __ldg(&iv.postings[p]);
+                const uint32_t t = raw & ~kLastFlag;
+                elements++;
+                if (!s_overflow) {
+                    uint32_t hs = (t * 0x9E3779B1u) >> 20;   // 12 bits
+                    for (;;) {
+                        uint32_t old = atomicCAS(&s_tab[hs].t, 0xffffffffu, t);
+                        if (old == 0xffffffffu) {
+                            if (atomicAdd(&s_distinct, 1) + 1 > kHitMaxDistinct) s_overflow = 1;
+                            old = t;
+                        }
+                        if (old == t) { atomicAdd(&s_tab[hs].c, 1u); break; }
+                        hs = (hs + 1) & (kHitCap - 1);
+                    }
+                }
+                if (raw & kLastFlag) break;
+            }
+        }
+        atomicAdd(&s_elements, elements);
+        __syncthreads();
+
+        if (!s_overflow) {
+            for (int i = threadIdx.x; i < kHitCap; i += blockDim.x) {
+                const uint32_t t = s_tab[i].t;
+                if (t == 0xffffffffu) continue;
+                if (pass_filters(a, qid, qlen, t, s_tab[i].c)) emit_candidate(a, q, t, s_tab[i].c);
+            }
+            if (threadIdx.x == 0) { atomicAdd(&a.counters[1], s_elements); atomicAdd(&a.counters[2], (unsigned long long)s_distinct); }
+        } else {
+            // dense recount: targets [r0, r0+kDenseRange) per pass, u16 counters (count <= H <= 2048)
+            uint16_t *cnt = reinterpret_cast<uint16_t *>(s_tab);
+            unsigned long long distinct = 0;
+            __syncthreads();
+            for (int64_t r0 = 0; r0 < iv.n_store; r0 += kDenseRange) {
+                for (int i = threadIdx.x; i < kDenseRange / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(cnt)[i] = 0;
+                __syncthreads();
+                for (int w = threadIdx.x; w < iv.H; w += blockDim.x) {
+                    uint32_t begin;
+                    if (!find_bucket(iv, w, (uint32_t)qmh[w], &begin)) continue;
+                    for (uint32_t p = begin;; p++) {
+                        const uint32_t raw = __ldg(&iv.postings[p]);
+                        const int64_t rel = (int64_t)(raw & ~kLastFlag) - r0;
+                        if (rel >= 0 && rel < kDenseRange) {
+                            // 16-bit increment through a 32-bit atomic on the containing word
+                            atomicAdd(reinterpret_cast<uint32_t *>(cnt) + (rel >> 1), (rel & 1) ? 0x10000u : 1u);
+                        }
+                        if (raw & kLastFlag) break;
+                    }
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < kDenseRange; i += blockDim.x) {
+                    const uint32_t c = cnt[i];
+                    if (!c) continue;
+                    distinct++;
+                    const uint32_t t = (uint32_t)(r0 + i);
+                    if (pass_filters(a, qid, qlen, t, c)) emit_candidate(a, q, t, c);
+                }
+                __syncthreads();
+            }
+            atomicAdd(&a.counters[2], distinct);
+            if (threadIdx.x == 0) atomicAdd(&a.counters[1], s_elements);
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_probe(cudaStream_t st, IndexView iv, ProbeArgs a, int *launches)
+{
+    if (a.nq_list <= 0) return cudaSuccess;
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (int64_t)sms * 6;
+    if (grid > a.nq_list) grid = a.nq_list;
+    k_probe<<<(unsigned)grid, kProbeThreads, 0, st>>>(iv, a);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2c: second-stage ordered-sketch filter
+// ---------------------------------------------------------------------------------------------
+// One thread per candidate pair; the merge is inherently serial (window tests interleaved with the
+// hash compare, "first and last match" handling of duplicate hashes).  Matches are recorded in an
+// HBM scratch laid out [entry][thread] so a warp's records coalesce.
+struct Scratch {
+    int32_t *p1, *p2, *tmp; uint32_t stride;
+    __device__ __forceinline__ int32_t &P1(int i) const { return p1[(size_t)i * stride]; }
+    __device__ __forceinline__ int32_t &P2(int i) const { return p2[(size_t)i * stride]; }
+    __device__ __forceinline__ int32_t &T(int i) const { return tmp[(size_t)i * stride]; }
+};
+
+// utils/Utils.java:445-494 on the scratch copy
+__device__ int32_t quick_select(const Scratch &sc, int k, int length)
+{
+    int from = 0, to = length - 1;
+    while (from < to) {
+        int r = from, w = to;
+        const int32_t mid = sc.T((r + w) / 2);
+        while (r < w) {
+            if (sc.T(r) >= mid) { int32_t tmp = sc.T(w); sc.T(w) = sc.T(r); sc.T(r) = tmp; w--; }
+            else r++;
+        }
+        if (sc.T(r) > mid) r--;
+        if (k <= r) to = r; else from = r + 1;
+    }
+    return sc.T(k);
+}
+
+struct MatchState { int32_t count, median, absmax, len1, len2; double max_shift; };
+
+// MatchData.performUpdate, sketch/BottomOverlapSketch.java:191-215
+__device__ void perform_update(MatchState &m, const Scratch &sc)
+{
+    if (m.count > 0) {
+        for (int i = 0; i < m.count; i++) sc.T(i) = sc.P2(i) - sc.P1(i);
+        m.median = quick_select(sc, m.count / 2, m.count);
+        const int32_t left = max(0, -m.median);
+        const int32_t right = min(m.len1, m.len2 - m.median);
+        const int32_t overlap = max(10, right - left);
+        m.absmax = min(max(m.len1, m.len2), (int32_t)((double)overlap * m.max_shift));
+    } else {
+        m.median = 0;
+        m.absmax = max(m.len1, m.len2) + 1;
+    }
+}
+
+// recordMatchingKmers, sketch/BottomOverlapSketch.java:397-516
+__device__ void record_matching(MatchState &m, const Scratch &sc, const int2 *__restrict__ s1, int n1, const int2 *__restrict__ s2, int n2)
+{
+    const int32_t median = m.median, absmax = m.absmax;
+    const int32_t v1lo = max(0, -median - absmax);
+    const int32_t v2lo = max(0, median - absmax);
+    const int32_t v1hi = min(m.len1, m.len2 - median + absmax);
+    const int32_t v2hi = min(m.len2, m.len1 + median + absmax);
+    int i1 = 0, i2 = 0, count = 0;
+    if (n1 > 0 && n2 > 0) {
+        int2 e1 = __ldg(&s1[0]), e2 = __ldg(&s2[0]);
+        for (;;) {
+            const int32_t hash1 = e1.x, pos1 = e1.y, hash2 = e2.x, pos2 = e2.y;
+            if (hash1 < hash2 || pos1 < v1lo || pos1 >= v1hi) { if (++i1 >= n1) break; e1 = __ldg(&s1[i1]); }
+            else if (hash2 < hash1 || pos2 < v2lo || pos2 >= v2hi) { if (++i2 >= n2) break; e2 = __ldg(&s2[i2]); }
+            else {
+                const int32_t diff = (pos2 - pos1) - median;
+                if (diff > absmax) { if (++i1 >= n1) break; e1 = __ldg(&s1[i1]); }
+                else if (diff < -absmax) { if (++i2 >= n2) break; e2 = __ldg(&s2[i2]); }
+                else {
+                    sc.P1(count) = pos1; sc.P2(count) = pos2; count++;
+                    int i1last = i1, i1try = i1 + 1;
+                    int32_t p1last = pos1;
+                    while (i1try < n1) {
+                        int2 t = __ldg(&s1[i1try]);
+                        if (!(t.x == hash1 && t.y >= v1lo && t.y < v1hi)) break;
+                        i1last = i1try; p1last = t.y; i1try++;
+                    }
+                    int i2last = i2, i2try = i2 + 1;
+                    int32_t p2last = pos2;
+                    while (i2try < n2) {
+                        int2 t = __ldg(&s2[i2try]);
+                        if (!(t.x == hash2 && t.y >= v2lo && t.y < v2hi)) break;
+                        i2last = i2try; p2last = t.y; i2try++;
+                    }
+                    if (i1 != i1last || i2 != i2last) {
+                        sc.P1(count) = p1last; sc.P2(count) = p2last; count++;
+                        i1 = i1last + 1; i2 = i2last + 1;
+                    } else { i1++; i2++; }
+                    if (i1 >= n1 || i2 >= n2) break;
+                    e1 = __ldg(&s1[i1]); e2 = __ldg(&s2[i2]);
+                }
+            }
+        }
+    }
+    m.count = count;
+}
+
+__device__ __forceinline__ int32_t java_round_div(int32_t num, int32_t den)
+{
+    // (int) Math.round((double) num / (double) den): round half up (floor(x + 0.5) semantics)
+    double x = (double)num / (double)den;
+    double f = floor(x);
+    return (int32_t)((long long)f + ((x - f) >= 0.5 ? 1 : 0));
+}
+
+__global__ void __launch_bounds__(128) k_filter(FilterArgs a)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= a.n_threads) return;
+    Scratch sc;
+    sc.stride = a.n_threads;
+    sc.p1 = a.scratch + tid;
+    sc.p2 = a.scratch + (size_t)a.scratch_entries * a.n_threads + tid;
+    sc.tmp = a.scratch + 2 * (size_t)a.scratch_entries * a.n_threads + tid;
+
+    for (uint64_t ci = tid; ci < a.n_cand; ci += a.n_threads) {
+        const Candidate c = a.cand[ci];
+        const int2 *A = reinterpret_cast<const int2 *>(a.q_ord) + (size_t)c.q * a.q_stride;
+        const int2 *Bs = reinterpret_cast<const int2 *>(a.t_ord) + (size_t)c.t * a.t_stride;
+        const int nA = a.q_ord_n[c.q], nB = a.t_ord_n[c.t];
+        OverlapOut o; o.a1 = o.a2 = o.b1 = o.b2 = o.valid = o.inter = o.kmin = 0; o.empty = 1;
+        MatchState m; m.count = 0; m.len1 = a.q_lenk[c.q]; m.len2 = a.t_lenk[c.t]; m.max_shift = a.max_shift;
+
+        perform_update(m, sc);                       // count == 0: median 0, absmax = max(len)+1
+        record_matching(m, sc, A, nA, Bs, nB);       // getOverlapInfo :601
+        if (m.count > 0) {
+            perform_update(m, sc);
+            record_matching(m, sc, A, nA, Bs, nB);   // :607
+        }
+        if (m.count > 0) {
+            // optimizeShifts :156-189
+            perform_update(m, sc);
+            int reduced = -1;
+            for (int it = 0; it < m.count; it++) {
+                const int32_t p1 = sc.P1(it), p2 = sc.P2(it);
+                if (reduced >= 0 && sc.P1(reduced) == p1) {
+                    const int32_t sr = sc.P2(reduced) - sc.P1(reduced);
+                    if (abs(sr - m.median) > abs((p2 - p1) - m.median)) { sc.P1(reduced) = p1; sc.P2(reduced) = p2; }
+                } else { reduced++; sc.P1(reduced) = p1; sc.P2(reduced) = p2; }
+            }
+            m.count = reduced + 1;
+            perform_update(m, sc);
+            // computeEdges :90-137
+            int32_t le1 = INT32_MAX, le2 = INT32_MAX, re1 = INT32_MIN, re2 = INT32_MIN, valid = 0;
+            for (int it = 0; it < m.count; it++) {
+                const int32_t p1 = sc.P1(it), p2 = sc.P2(it);
+                if (abs((p2 - p1) - m.median) > m.absmax) continue;
+                le1 = min(le1, p1); le2 = min(le2, p2); re1 = max(re1, p1); re2 = max(re2, p2);
+                valid++;
+            }
+            if (valid >= 3) {
+                const int32_t n = valid;
+                o.a1 = max(0, java_round_div(n * le1 - re1, n - 1));
+                o.a2 = min(m.len1, java_round_div(n * re1 - le1, n - 1));
+                o.b1 = max(0, java_round_div(n * le2 - re2, n - 1));
+                o.b2 = min(m.len2, java_round_div(n * re2 - le2, n - 1));
+                o.valid = valid;
+                // computeKBottomSketchJaccard :304-364, streamed: s1/s2 first, then the bottom-k merge
+                int s1 = 0, s2 = 0;
+                for (int i = 0; i < nA; i++) { int32_t p = __ldg(&A[i]).y; s1 += (p >= o.a1 && p <= o.a2); }
+                for (int j = 0; j < nB; j++) { int32_t p = __ldg(&Bs[j]).y; s2 += (p >= o.b1 && p <= o.b2); }
+                const int k = min(s1, s2);
+                int inter = 0;
+                if (k > 0) {
+                    int i = 0, j = 0, uni = 0;
+                    // advance to the first in-window entry of each side
+                    int2 ea = __ldg(&A[0]); while (!(ea.y >= o.a1 && ea.y <= o.a2)) ea = __ldg(&A[++i]);
+                    int2 eb = __ldg(&Bs[0]); while (!(eb.y >= o.b1 && eb.y <= o.b2)) eb = __ldg(&Bs[++j]);
+                    while (uni < k) {
+                        bool adv_a = false, adv_b = false;
+                        if (ea.x < eb.x) adv_a = true;
+                        else if (ea.x > eb.x) adv_b = true;
+                        else { inter++; adv_a = adv_b = true; }
+                        uni++;
+                        if (uni >= k) break;
+                        // the reference indexes the filtered arrays; entries past the k-th union element are never read
+                        if (adv_a) { do { ++i; if (i >= nA) break; ea = __ldg(&A[i]); } while (!(ea.y >= o.a1 && ea.y <= o.a2)); }
+                        if (adv_b) { do { ++j; if (j >= nB) break; eb = __ldg(&Bs[j]); } while (!(eb.y >= o.b1 && eb.y <= o.b2)); }
+                    }
+                }
+                o.inter = inter; o.kmin = k; o.empty = 0;
+            }
+        }
+        a.out[ci] = o;
+    }
+}
+
+cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches)
+{
+    if (a.n_cand == 0) return cudaSuccess;
+    unsigned grid = (a.n_threads + 127) / 128;
+    k_filter<<<grid, 128, 0, st>>>(a);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// a10: MinHashSketch.jaccard numerator (sketch/MinHashSketch.java:237-263)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_equal_count(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int H, int32_t *out)
+{
+    int c = 0;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) c += a[i] == b[i];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(kFull, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+cudaError_t launch_equal_count(cudaStream_t st, const int32_t *a, const int32_t *b, int H, int32_t *d_out, int *launches)
+{
+    cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    k_equal_count<<<1, 128, 0, st>>>(a, b, H, d_out);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+} // namespace mhapb

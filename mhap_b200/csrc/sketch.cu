@@ -1,0 +1,507 @@
+// sketch.cu -- K1: per-read MinHashSketch + BottomOverlapSketch construction on sm_100a.
+//
+// Replaces (paths relative to /root/reference/src/main/java/edu/umd/marbl/mhap/):
+//   K1a k_hash_dedup : sketch/HashUtils.java:237-258 + the multiset count of
+//                      sketch/MinHashSketch.java:66-81
+//   K1b k_minhash    : the weighted XORShift-min loop, sketch/MinHashSketch.java:95-154
+//   K1c k_ordered    : sketch/HashUtils.java:213-235 + sketch/BottomOverlapSketch.java:525-559
+//
+// Pure integer work, no tensor cores.  K1b dominates (nk*H XORShift steps per strand) and is
+// bound by integer issue, not HBM -- see DESIGN.md.
+#include "engine.h"
+#include "hash.cuh"
+
+namespace mhapb {
+
+static constexpr uint64_t kEmptyKey = ~0ull;
+static constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// character sources
+// ---------------------------------------------------------------------------------------------
+struct CharsSmem {
+    const uint8_t *s;
+    __device__ __forceinline__ uint8_t operator()(int i) const { return s[i]; }
+};
+// Direct from HBM with FastaData's upper-casing and Utils.rc applied on the fly (long reads).
+struct CharsGlobal {
+    const uint8_t *g; uint32_t len; uint32_t rc;
+    __device__ __forceinline__ uint8_t operator()(int i) const
+    {
+        uint8_t c = upper_char(rc ? __ldg(g + (len - 1 - (uint32_t)i)) : __ldg(g + i));
+        return rc ? complement_char(c) : c;
+    }
+};
+
+__device__ __forceinline__ void stage_chars(uint8_t *dst, const uint8_t *g, uint32_t len, uint32_t rc)
+{
+    // coalesced byte loads; a 10 kbp read is 10 KB, this is noise next to K1b
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+        uint8_t c = upper_char(__ldg(g + i));
+        if (rc) dst[len - 1 - i] = complement_char(c);
+        else dst[i] = c;
+    }
+}
+
+// warp-aggregated cursor bump on a shared-memory counter; every lane of the warp must call it
+__device__ __forceinline__ int warp_alloc(int *counter, bool want)
+{
+    unsigned m = __ballot_sync(kFull, want);
+    if (m == 0) return 0;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(kFull, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a: k-mer hashing + exact de-duplication with counts
+// ---------------------------------------------------------------------------------------------
+// One CTA per strand (persistent, work queue).  Distinct hashes go into an open-addressed table
+// (shared memory for strands up to kShortMaxKmers k-mers, HBM scratch beyond); a repeat occurrence
+// bumps a per-slot counter in HBM that is zero between uses (touched only for duplicated k-mers).
+// Output per strand: keys[koff .. koff+nlight) weight-1 hashes, keys[koff+nk-1 .. ] (downwards)
+// the hashes with weight > 1 and their weights.  Order is irrelevant: the XORShift map is a
+// bijection, so two distinct keys never tie in the min.
+template <bool LONG>
+__global__ void __launch_bounds__(1024)
+k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc, int s_begin, int s_end,
+             int k, int unweighted, uint32_t table_cap, uint32_t chars_cap, SketchScratch sc, uint32_t *queue)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int s_strand, s_nlight, s_nheavy, s_special;
+
+    uint64_t *table;
+    uint32_t *dupmask = nullptr;
+    uint8_t *chars = nullptr;
+    if (LONG) {
+        table = sc.gtable + (size_t)blockIdx.x * table_cap;
+    } else {
+        table = reinterpret_cast<uint64_t *>(smem_raw);
+        dupmask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)table_cap * 8);
+        chars = smem_raw + (size_t)table_cap * 8 + (size_t)((table_cap + 31) / 32) * 4;
+    }
+    uint32_t *dupcnt = sc.dupcnt + (size_t)blockIdx.x * table_cap;
+    (void)chars_cap;
+
+    for (;;) {
+        if (threadIdx.x == 0) {
+            s_strand = s_begin + (int)atomicAdd(queue, 1u);
+            s_nlight = 0; s_nheavy = 0; s_special = 0;
+        }
+        __syncthreads();
+        const int s = s_strand;
+        if (s >= s_end) break;
+        const StrandDesc d = desc[s];
+        const int nk = (int)d.len - k + 1;
+        // table sized for this strand: load factor <= 2/3
+        uint32_t C = (uint32_t)nk + (uint32_t)nk / 2 + 8;
+        if (C > table_cap) C = table_cap;
+
+        for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) table[i] = kEmptyKey;
+        if (!LONG) {
+            for (uint32_t i = threadIdx.x; i < (C + 31) / 32; i += blockDim.x) dupmask[i] = 0;
+            stage_chars(chars, bases + d.base_off, d.len, d.rc);
+        }
+        __syncthreads();
+
+        const CharsGlobal gsrc{bases + d.base_off, d.len, d.rc};
+        for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+            uint64_t h;
+            if (LONG) h = murmur3_128_h1_chars([&](int j) { return gsrc(i + j); }, k);
+            else      h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, k);
+            if (h == kEmptyKey) { atomicAdd(&s_special, 1); continue; }
+            uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * C) >> 32);
+            for (;;) {
+                unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&table[slot]),
+                                                   (unsigned long long)kEmptyKey, (unsigned long long)h);
+                if (old == kEmptyKey) break;
+                if (old == h) {
+                    if (!unweighted) {
+                        if (!LONG) atomicOr(&dupmask[slot >> 5], 1u << (slot & 31));
+                        atomicAdd(&dupcnt[slot], 1u);
+                    }
+                    break;
+                }
+                if (++slot == C) slot = 0;
+            }
+        }
+        __syncthreads();
+
+        uint64_t *keys = sc.keys + d.koff;
+        uint32_t *wts = sc.wts + d.koff;
+        const uint32_t Cr = (C + 31u) & ~31u;
+        for (uint32_t i = threadIdx.x; i < Cr; i += blockDim.x) {
+            uint64_t key = (i < C) ? table[i] : kEmptyKey;
+            bool occ = key != kEmptyKey;
+            uint32_t extra = 0;
+            if (occ && !unweighted) {
+                if (LONG) extra = dupcnt[i];
+                else if (dupmask[i >> 5] & (1u << (i & 31))) extra = dupcnt[i];
+                if (extra) dupcnt[i] = 0;   // leave the scratch zeroed for the next strand
+            }
+            int pl = warp_alloc(&s_nlight, occ && extra == 0);
+            int ph = warp_alloc(&s_nheavy, occ && extra != 0);
+            if (occ) {
+                if (extra == 0) keys[pl] = key;
+                else { keys[nk - 1 - ph] = key; wts[nk - 1 - ph] = extra + 1; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int nl = s_nlight, nh = s_nheavy;
+            if (s_special > 0) {   // a k-mer whose hash equals the table's empty marker (p = 2^-64)
+                if (s_special > 1 && !unweighted) { keys[nk - 1 - nh] = kEmptyKey; wts[nk - 1 - nh] = (uint32_t)s_special; nh++; }
+                else { keys[nl] = kEmptyKey; nl++; }
+            }
+            sc.nlight[s] = nl;
+            sc.nheavy[s] = nh;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b: XORShift-min
+// ---------------------------------------------------------------------------------------------
+// One warp per strand, systolic: lane l owns words [l*B, (l+1)*B) with their running minima in
+// registers; distinct k-mers enter at lane 0 and their chain state x is handed lane to lane by
+// shuffle, so every lane always advances a *different* k-mer through its own B words and the
+// chain (x_{j+1} = M x_j, MinHashSketch.java:140-143) is never recomputed.  The common case per
+// step is the 3-shift XORShift plus one signed compare of the high word against the lane's
+// register-resident minimum; the full 64-bit compare and the update run only on the rare path.
+__device__ __forceinline__ uint64_t xorshift_step(uint64_t x)
+{
+    x ^= x << 21;
+    x ^= x >> 35;
+    x ^= x << 4;
+    return x;
+}
+
+template <int B>
+struct LaneMins {
+    int32_t hi[B];
+    uint32_t lo[B];
+    int32_t out[B];
+};
+
+template <int B, bool WEIGHTED>
+__device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ wts,
+                                                 int n, int dir /* +1 light, -1 heavy */, uint64_t *kbuf, uint32_t *wbuf, int lane)
+{
+    uint64_t x = 0;
+    uint32_t w = 1;
+    const int total = n + 31;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        {
+            int e = t0 + lane;
+            uint64_t mk = 0; uint32_t mw = 1;
+            if (e < n) { mk = keys[(long long)dir * e]; if (WEIGHTED) mw = wts[(long long)dir * e]; }
+            kbuf[lane] = mk;
+            if (WEIGHTED) wbuf[lane] = mw;
+        }
+        __syncwarp();
+        const int jn = min(32, total - t0);
+#pragma unroll 1
+        for (int j = 0; j < jn; j++) {
+            uint64_t xin = __shfl_up_sync(kFull, x, 1);
+            x = lane == 0 ? kbuf[j] : xin;
+            if (WEIGHTED) {
+                uint32_t win = __shfl_up_sync(kFull, w, 1);
+                w = lane == 0 ? wbuf[j] : win;
+            }
+            const int e = t0 + j - lane;
+            if (e >= 0 && e < n) {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    uint32_t c = 0;
+                    do {
+                        x = xorshift_step(x);
+                        const int32_t xh = (int32_t)(x >> 32);
+                        if (xh <= m.hi[b]) {
+                            const uint32_t xl = (uint32_t)x;
+                            if (xh < m.hi[b] || xl < m.lo[b]) {      // signed 64-bit x < best[word]
+                                m.hi[b] = xh; m.lo[b] = xl;
+                                const uint64_t key = keys[(long long)dir * e];
+                                // MinHashSketch.java:146-149: even word -> (int)key, odd -> (int)(key>>>32)
+                                m.out[b] = ((lane * B + b) & 1) ? (int32_t)(key >> 32) : (int32_t)key;
+                            }
+                        }
+                    } while (WEIGHTED && ++c < w);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(256)
+k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
+          int32_t *__restrict__ minhash, uint32_t *queue)
+{
+    __shared__ uint64_t s_kbuf[8][32];
+    __shared__ uint32_t s_wbuf[8][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (;;) {
+        int s = 0;
+        if (lane == 0) s = (int)atomicAdd(queue, 1u);
+        s = __shfl_sync(kFull, s, 0);
+        if (s >= n_strands) break;
+        const StrandDesc d = desc[s];
+        const int nk = (int)d.len - k + 1;
+        LaneMins<B> m;
+#pragma unroll
+        for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
+        const uint64_t *keys = sc.keys + d.koff;
+        const int nl = sc.nlight[s], nh = sc.nheavy[s];
+        minhash_pipeline<B, false>(m, keys, nullptr, nl, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        if (nh > 0)
+            minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
+        int32_t *row = minhash + (size_t)d.row * H;
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            int word = lane * B + b;
+            if (word < H) row[word] = m.out[b];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1c: ordered bottom-S sketch
+// ---------------------------------------------------------------------------------------------
+// One CTA per strand.  Hash every ordered k-mer, radix-select the S smallest 64-bit keys
+// (hash biased to unsigned order << 32 | position) -- which is exactly "ascending signed hash,
+// ties by ascending position" of fastutil's stable radixSortIndirect -- then bitonic-sort the
+// S survivors in shared memory.
+template <bool LONG>
+__global__ void __launch_bounds__(512)
+k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc, int s_begin, int s_end, int ok, int S,
+          int ord_stride, uint32_t len_cap, uint32_t sel_cap, SketchScratch sc, int32_t *__restrict__ ord,
+          int32_t *__restrict__ ord_n, uint32_t *queue)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int s_strand, s_nsel;
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_digit, s_before, s_bin;
+
+    uint64_t *sel = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *oh;
+    uint8_t *chars = nullptr;
+    if (LONG) oh = sc.ohash + (size_t)blockIdx.x * len_cap;
+    else { oh = reinterpret_cast<uint32_t *>(smem_raw + (size_t)sel_cap * 8); chars = smem_raw + (size_t)sel_cap * 8 + (size_t)len_cap * 4; }
+
+    for (;;) {
+        if (threadIdx.x == 0) { s_strand = s_begin + (int)atomicAdd(queue, 1u); s_nsel = 0; }
+        __syncthreads();
+        const int s = s_strand;
+        if (s >= s_end) break;
+        const StrandDesc d = desc[s];
+        const int no = (int)d.len - ok + 1;
+        if (!LONG) { stage_chars(chars, bases + d.base_off, d.len, d.rc); __syncthreads(); }
+        const CharsGlobal gsrc{bases + d.base_off, d.len, d.rc};
+        for (int i = threadIdx.x; i < no; i += blockDim.x) {
+            uint32_t h;
+            if (LONG) h = murmur3_32_chars([&](int j) { return gsrc(i + j); }, ok);
+            else      h = murmur3_32_chars([&](int j) { return chars[i + j]; }, ok);
+            oh[i] = h ^ 0x80000000u;   // signed order -> unsigned order
+        }
+        __syncthreads();
+
+        const int nsel = min(S, no);
+        uint64_t T = ~0ull;   // select keys <= T
+        if (no > S) {
+            uint64_t prefix = 0, mask = 0;
+            uint32_t remaining = (uint32_t)S;
+            for (int pass = 7; pass >= 0; pass--) {
+                const int shift = pass * 8;
+                if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+                __syncthreads();
+                for (int i = threadIdx.x; i < no; i += blockDim.x) {
+                    uint64_t key = ((uint64_t)oh[i] << 32) | (uint32_t)i;
+                    if ((key & mask) == prefix) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    // lane l owns bins [8l, 8l+8): find the bin where the running count crosses `remaining`
+                    uint32_t c[8], sum = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { c[q] = s_hist[threadIdx.x * 8 + q]; sum += c[q]; }
+                    uint32_t incl = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(kFull, incl, o); if ((int)threadIdx.x >= o) incl += v; }
+                    uint32_t excl = incl - sum;
+                    if (excl < remaining && remaining <= incl) {
+                        uint32_t run = excl;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (run < remaining && remaining <= run + c[q]) { s_digit = threadIdx.x * 8 + q; s_before = run; s_bin = c[q]; }
+                            run += c[q];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= (uint64_t)s_digit << shift;
+                mask |= 0xffull << shift;
+                remaining -= s_before;
+                if (s_bin == remaining) {   // the whole bin is selected: no need to split it further
+                    T = prefix | ((shift == 0) ? 0ull : ((1ull << shift) - 1));
+                    break;
+                }
+                // (after pass 0 the bin holds exactly one key, so the branch above always fires)
+            }
+        }
+        __syncthreads();
+        const int nor = (no + 31) & ~31;
+        for (int i = threadIdx.x; i < nor; i += blockDim.x) {
+            uint64_t key = (i < no) ? (((uint64_t)oh[i] << 32) | (uint32_t)i) : ~0ull;
+            bool want = (i < no) && key <= T;
+            int p = warp_alloc(&s_nsel, want);
+            if (want) sel[p] = key;
+        }
+        uint32_t P = 1; while ((int)P < nsel) P <<= 1;
+        __syncthreads();
+        for (uint32_t i = nsel + threadIdx.x; i < P; i += blockDim.x) sel[i] = ~0ull;
+        __syncthreads();
+        for (uint32_t size = 2; size <= P; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                    uint32_t i = 2 * t - (t & (stride - 1));
+                    uint32_t j = i + stride;
+                    bool up = (i & size) == 0;
+                    uint64_t a = sel[i], b = sel[j];
+                    if ((a > b) == up) { sel[i] = b; sel[j] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        int2 *row = reinterpret_cast<int2 *>(ord) + (size_t)d.row * ord_stride;
+        for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
+            uint64_t key = sel[i];
+            row[i] = make_int2((int32_t)((uint32_t)(key >> 32) ^ 0x80000000u), (int32_t)(uint32_t)key);
+        }
+        if (threadIdx.x == 0) ord_n[d.row] = nsel;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count()
+{
+    if (!g_sm_count) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+static constexpr uint32_t kShortTableCap = kShortMaxKmers + kShortMaxKmers / 2 + 8;   // 24584 slots = 192 KB
+
+int hash_dedup_grid() { return sm_count(); }          // 1 CTA/SM (shared-memory table)
+int ordered_grid() { return sm_count() * 2; }
+size_t dedup_table_cap_short() { return kShortTableCap; }
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
+                              int first_long, int max_kmers_short, int max_kmers_long, int k, int unweighted,
+                              const SketchScratch &sc, int *launches)
+{
+    cudaError_t e;
+    if (first_long > 0) {
+        uint32_t cap = (uint32_t)max_kmers_short + (uint32_t)max_kmers_short / 2 + 8;
+        uint32_t chars_cap = (uint32_t)align16((size_t)max_kmers_short + k);
+        size_t smem = (size_t)cap * 8 + (size_t)((cap + 31) / 32) * 4 + chars_cap;
+        e = cudaFuncSetAttribute(k_hash_dedup<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int grid = hash_dedup_grid();
+        if (smem <= 100 * 1024) grid *= 2;
+        if (grid > first_long) grid = first_long;
+        // dupcnt rows are strided by the *launch's* cap so both variants can share the buffer
+        k_hash_dedup<false><<<grid, 1024, smem, st>>>(d_bases, d_desc, 0, first_long, k, unweighted, cap, chars_cap, sc, sc.counters + 0);
+        (*launches)++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (first_long < n_strands) {
+        uint32_t cap = (uint32_t)max_kmers_long + (uint32_t)max_kmers_long / 2 + 8;
+        int grid = hash_dedup_grid();
+        if (grid > n_strands - first_long) grid = n_strands - first_long;
+        k_hash_dedup<true><<<grid, 1024, 0, st>>>(d_bases, d_desc, first_long, n_strands, k, unweighted, cap, 0, sc, sc.counters + 1);
+        (*launches)++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+template <int B>
+static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
+                                    const SketchScratch &sc, int32_t *d_minhash)
+{
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash<B>, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count() * per_sm;
+    int need = (n_strands + 7) / 8;
+    if (grid > need) grid = need;
+    k_minhash<B><<<grid, 256, 0, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
+                           const SketchScratch &sc, int32_t *d_minhash, int *launches)
+{
+    if (n_strands <= 0) return cudaSuccess;
+    (*launches)++;
+    const int b = (H + 31) / 32;
+    if (b <= 1) return launch_minhash_b<1>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 2) return launch_minhash_b<2>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 4) return launch_minhash_b<4>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 8) return launch_minhash_b<8>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 12) return launch_minhash_b<12>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 16) return launch_minhash_b<16>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 24) return launch_minhash_b<24>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 32) return launch_minhash_b<32>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 48) return launch_minhash_b<48>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    return launch_minhash_b<64>(st, d_desc, n_strands, k, H, sc, d_minhash);
+}
+
+cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
+                           int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,
+                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int *launches)
+{
+    cudaError_t e;
+    uint32_t sel_cap = 1; while ((int)sel_cap < S) sel_cap <<= 1;
+    if (first_long > 0) {
+        uint32_t len_cap = (uint32_t)align16((size_t)max_len_short + 16);
+        // a short read may have fewer ordered k-mers than S, but never more than len_cap
+        size_t smem = (size_t)sel_cap * 8 + (size_t)len_cap * 4 + len_cap;
+        e = cudaFuncSetAttribute(k_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int grid = sm_count() * (smem <= 100 * 1024 ? 2 : 1);
+        if (grid > first_long) grid = first_long;
+        k_ordered<false><<<grid, 512, smem, st>>>(d_bases, d_desc, 0, first_long, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 3);
+        (*launches)++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (first_long < n_strands) {
+        uint32_t len_cap = (uint32_t)align16((size_t)max_len_long + 16);
+        size_t smem = (size_t)sel_cap * 8;
+        e = cudaFuncSetAttribute(k_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int grid = ordered_grid();
+        if (grid > n_strands - first_long) grid = n_strands - first_long;
+        k_ordered<true><<<grid, 512, smem, st>>>(d_bases, d_desc, first_long, n_strands, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 4);
+        (*launches)++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+} // namespace mhapb

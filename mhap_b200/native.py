@@ -1,0 +1,328 @@
+"""ctypes binding of libmhap_b200.so -- the C ABI declared in include/mhap_b200.h.
+
+This is the same binding a JNI shim would make; Python is only the harness
+language of this image (no JVM here).  There is no CPU fallback: loading fails loudly when the
+library is missing and `Engine()` fails when no sm_100 GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmhap_b200.so")
+
+# every symbol include/mhap_b200.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = [
+    "mhapb_version", "mhapb_create", "mhapb_destroy", "mhapb_last_error", "mhapb_free", "mhapb_get_timing",
+    "mhapb_host_alloc", "mhapb_host_free", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
+    "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads",
+    "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
+    "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
+    "mhapb_search_query_sketches", "mhapb_format_match", "mhapb_minhash_equal_count",
+]
+
+
+class MhapError(RuntimeError):
+    """Mirrors the reference's unchecked MhapRuntimeException / SketchRuntimeException."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class SketchParams(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("num_hashes", C.c_int32), ("ordered_kmer_size", C.c_int32),
+                ("ordered_sketch_size", C.c_int32), ("unweighted", C.c_int32), ("min_olap_length", C.c_int32)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("num_min_matches", C.c_int32), ("min_store_length", C.c_int32), ("max_shift", C.c_double),
+                ("accept_score", C.c_double), ("keep_all", C.c_int32), ("reserved", C.c_int32),
+                ("query_first", C.c_int64), ("query_count", C.c_int64)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("from_id", C.c_int64), ("to_id", C.c_int64), ("from_fwd", C.c_int32), ("to_fwd", C.c_int32),
+                ("hit_count", C.c_int32), ("a1", C.c_int32), ("a2", C.c_int32), ("b1", C.c_int32), ("b2", C.c_int32),
+                ("valid_count", C.c_int32), ("intersect", C.c_int32), ("kmin", C.c_int32), ("from_len", C.c_int32),
+                ("to_len", C.c_int32), ("score", C.c_double), ("accepted", C.c_int32), ("pad_", C.c_int32)]
+
+
+HIT_DTYPE = np.dtype([("from_id", "<i8"), ("to_id", "<i8"), ("from_fwd", "<i4"), ("to_fwd", "<i4"),
+                      ("hit_count", "<i4"), ("a1", "<i4"), ("a2", "<i4"), ("b1", "<i4"), ("b2", "<i4"),
+                      ("valid_count", "<i4"), ("intersect", "<i4"), ("kmin", "<i4"), ("from_len", "<i4"),
+                      ("to_len", "<i4"), ("score", "<f8"), ("accepted", "<i4"), ("pad_", "<i4")])
+assert HIT_DTYPE.itemsize == C.sizeof(Hit)
+
+
+class Stats(C.Structure):
+    _fields_ = [("elements_processed", C.c_int64), ("sequences_hit", C.c_int64), ("fully_compared", C.c_int64),
+                ("matches_processed", C.c_int64), ("sequences_searched", C.c_int64)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("hash_dedup_ms", C.c_float), ("minhash_ms", C.c_float),
+                ("ordered_ms", C.c_float), ("index_ms", C.c_float), ("probe_ms", C.c_float), ("filter_ms", C.c_float),
+                ("kernel_launches", C.c_int64), ("xorshift_steps", C.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libmhap_b200.so; raises if it has not been built (python __graft_entry__.py / make)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MhapError(-2, f"{LIB_PATH} not built: run `make -C mhap_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+    P = C.POINTER
+    L.mhapb_version.restype = C.c_char_p
+    L.mhapb_create.argtypes = [C.c_int, P(vp)]
+    L.mhapb_destroy.argtypes = [vp]; L.mhapb_destroy.restype = None
+    L.mhapb_last_error.argtypes = [vp]; L.mhapb_last_error.restype = C.c_char_p
+    L.mhapb_free.argtypes = [vp]; L.mhapb_free.restype = None
+    L.mhapb_get_timing.argtypes = [vp, P(Timing)]
+    L.mhapb_host_alloc.argtypes = [C.c_size_t, P(vp)]
+    L.mhapb_host_free.argtypes = [vp]; L.mhapb_host_free.restype = None
+    L.mhapb_sketch.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
+    L.mhapb_sketch_device.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
+    L.mhapb_sketch_to_dat.argtypes = [vp, P(SketchParams), vp, vp, vp, u32, C.c_int, P(vp), P(u64), P(u32)]
+    L.mhapb_dat_encode.argtypes = [i64, C.c_int, C.c_char_p, i32, vp, i32, i32, i32, vp, i32, vp]
+    L.mhapb_dat_encode.restype = i64
+    L.mhapb_dat_decode.argtypes = [vp, u64, i64, P(u32), P(i32), P(i32), P(i32), vp, vp, vp, vp, vp, vp, vp]
+    L.mhapb_store_reset.argtypes = [vp, P(SketchParams)]
+    L.mhapb_store_add_reads.argtypes = [vp, vp, vp, vp, u32, C.c_int, P(i64)]
+    L.mhapb_store_add_sketches.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, u32]
+    L.mhapb_store_add_sketches_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32]
+    L.mhapb_store_size.argtypes = [vp]; L.mhapb_store_size.restype = i64
+    L.mhapb_store_get.argtypes = [vp, i64, P(i64), P(i32), P(i32), P(i32), vp, vp, P(i32)]
+    L.mhapb_store_device_ptrs.argtypes = [vp, P(vp), P(vp), P(i64), P(i32), P(i32)]
+    L.mhapb_index_build.argtypes = [vp]
+    L.mhapb_search_self.argtypes = [vp, P(SearchParams), P(vp), P(u64), P(Stats)]
+    L.mhapb_search_query_reads.argtypes = [vp, P(SearchParams), vp, vp, vp, u32, P(vp), P(u64), P(Stats)]
+    L.mhapb_search_query_sketches.argtypes = [vp, P(SearchParams), vp, vp, vp, vp, vp, vp, vp, i32, u32, P(vp), P(u64), P(Stats)]
+    L.mhapb_format_match.argtypes = [P(Hit), C.c_char_p, C.c_size_t]
+    L.mhapb_minhash_equal_count.argtypes = [vp, i64, i64, P(i32)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def pack_reads(reads):
+    """list[bytes|str] -> (uint8 bases, uint64 offsets[n+1])."""
+    bs = [r if isinstance(r, (bytes, bytearray)) else r.encode("latin-1") for r in reads]
+    offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offsets[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, dtype=np.uint8)
+    return bases, offsets
+
+
+class Engine:
+    """One mhapb_ctx = one GPU.  Thin, 1:1 over the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.mhapb_create(device, C.byref(h))
+        if rc:
+            raise MhapError(rc, (self.L.mhapb_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mhapb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise MhapError(rc, (self.L.mhapb_last_error(self.h) or b"").decode())
+        return rc
+
+    def timing(self) -> dict:
+        t = Timing()
+        self._ck(self.L.mhapb_get_timing(self.h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in Timing._fields_}
+
+    # ---- K1 ----
+    def sketch(self, bases, offsets, params: SketchParams, both_strands=True, want_ord=True):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.size - 1
+        per = 2 if both_strands else 1
+        H, S = params.num_hashes, params.ordered_sketch_size
+        mh = np.empty((n * per, H), dtype=np.int32)
+        od = np.empty((n * per, S, 2), dtype=np.int32) if want_ord else None
+        on = np.empty(n * per, dtype=np.int32) if want_ord else None
+        st = np.empty(n, dtype=np.int32)
+        b = bases if bases.size else np.zeros(1, dtype=np.uint8)
+        self._ck(self.L.mhapb_sketch(self.h, C.byref(params), _ptr(b), _ptr(offsets), n, int(both_strands),
+                                     _ptr(mh), _ptr(od), _ptr(on), _ptr(st)))
+        return mh, od, on, st
+
+    def sketch_device(self, d_bases: int, offsets, params: SketchParams, both_strands, d_minhash: int, d_ord: int,
+                      d_ord_n: int, d_status: int = 0):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.size - 1
+        self._ck(self.L.mhapb_sketch_device(self.h, C.byref(params), d_bases, _ptr(offsets), n, int(both_strands),
+                                            d_minhash or None, d_ord or None, d_ord_n or None, d_status or None))
+
+    def sketch_to_dat(self, bases, offsets, ids, params: SketchParams, both_strands=True) -> tuple[bytes, int]:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        out = C.c_void_p(); ln = C.c_uint64(); nrec = C.c_uint32()
+        b = bases if bases.size else np.zeros(1, dtype=np.uint8)
+        self._ck(self.L.mhapb_sketch_to_dat(self.h, C.byref(params), _ptr(b), _ptr(offsets), _ptr(ids), offsets.size - 1,
+                                            int(both_strands), C.byref(out), C.byref(ln), C.byref(nrec)))
+        data = C.string_at(out.value, ln.value)
+        self.L.mhapb_free(out)
+        return data, nrec.value
+
+    # ---- store / index ----
+    def store_reset(self, params: SketchParams):
+        self._ck(self.L.mhapb_store_reset(self.h, C.byref(params)))
+
+    def store_add_reads(self, bases, offsets, ids=None, both_strands=True) -> int:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        added = C.c_int64()
+        b = bases if bases.size else np.zeros(1, dtype=np.uint8)
+        self._ck(self.L.mhapb_store_add_reads(self.h, _ptr(b), _ptr(offsets), _ptr(ids), offsets.size - 1,
+                                              int(both_strands), C.byref(added)))
+        return added.value
+
+    def store_add_sketches(self, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hp, ord_n):
+        ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
+        seq_len = np.ascontiguousarray(seq_len, dtype=np.int32); slk = np.ascontiguousarray(seq_len_kmers, dtype=np.int32)
+        minhash = np.ascontiguousarray(minhash, dtype=np.int32); ord_hp = np.ascontiguousarray(ord_hp, dtype=np.int32)
+        ord_n = np.ascontiguousarray(ord_n, dtype=np.int32)
+        self._ck(self.L.mhapb_store_add_sketches(self.h, _ptr(ids), _ptr(is_fwd), _ptr(seq_len), _ptr(slk), _ptr(minhash),
+                                                 _ptr(ord_hp), _ptr(ord_n), ord_hp.shape[1], ids.size))
+
+    def store_add_sketches_device(self, ids, is_fwd, seq_len, seq_len_kmers, d_minhash: int, d_ord: int, ord_n):
+        ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
+        seq_len = np.ascontiguousarray(seq_len, dtype=np.int32); slk = np.ascontiguousarray(seq_len_kmers, dtype=np.int32)
+        ord_n = np.ascontiguousarray(ord_n, dtype=np.int32)
+        self._ck(self.L.mhapb_store_add_sketches_device(self.h, _ptr(ids), _ptr(is_fwd), _ptr(seq_len), _ptr(slk),
+                                                        d_minhash, d_ord, _ptr(ord_n), ids.size))
+
+    def store_size(self) -> int:
+        return int(self.L.mhapb_store_size(self.h))
+
+    def store_get(self, idx: int, H: int, S: int) -> dict:
+        id_ = C.c_int64(); fwd = C.c_int32(); sl = C.c_int32(); slk = C.c_int32(); on = C.c_int32()
+        mh = np.zeros(H, dtype=np.int32); od = np.zeros((S, 2), dtype=np.int32)
+        self._ck(self.L.mhapb_store_get(self.h, idx, C.byref(id_), C.byref(fwd), C.byref(sl), C.byref(slk), _ptr(mh), _ptr(od), C.byref(on)))
+        return dict(id=id_.value, is_fwd=bool(fwd.value), seq_len=sl.value, seq_len_kmers=slk.value, minhash=mh, ord=od[:on.value].copy())
+
+    def store_device_ptrs(self):
+        a = C.c_void_p(); b = C.c_void_p(); n = C.c_int64(); H = C.c_int32(); S = C.c_int32()
+        self._ck(self.L.mhapb_store_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(n), C.byref(H), C.byref(S)))
+        return a.value, b.value, n.value, H.value, S.value
+
+    def index_build(self):
+        self._ck(self.L.mhapb_index_build(self.h))
+
+    # ---- search ----
+    def _collect(self, out, n, st):
+        if n.value:
+            hits = np.frombuffer(C.string_at(out.value, n.value * C.sizeof(Hit)), dtype=HIT_DTYPE).copy()
+        else:
+            hits = np.zeros(0, dtype=HIT_DTYPE)
+        self.L.mhapb_free(out)
+        return hits, {f: int(getattr(st, f)) for f, _ in Stats._fields_}
+
+    def search_self(self, sp: SearchParams):
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        self._ck(self.L.mhapb_search_self(self.h, C.byref(sp), C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
+    def search_query_reads(self, sp: SearchParams, bases, offsets, ids=None):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        b = bases if bases.size else np.zeros(1, dtype=np.uint8)
+        self._ck(self.L.mhapb_search_query_reads(self.h, C.byref(sp), _ptr(b), _ptr(offsets), _ptr(ids), offsets.size - 1,
+                                                 C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
+    def search_query_sketches(self, sp: SearchParams, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hp, ord_n):
+        ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
+        seq_len = np.ascontiguousarray(seq_len, dtype=np.int32); slk = np.ascontiguousarray(seq_len_kmers, dtype=np.int32)
+        minhash = np.ascontiguousarray(minhash, dtype=np.int32); ord_hp = np.ascontiguousarray(ord_hp, dtype=np.int32)
+        ord_n = np.ascontiguousarray(ord_n, dtype=np.int32)
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        self._ck(self.L.mhapb_search_query_sketches(self.h, C.byref(sp), _ptr(ids), _ptr(is_fwd), _ptr(seq_len), _ptr(slk),
+                                                    _ptr(minhash), _ptr(ord_hp), _ptr(ord_n), ord_hp.shape[1], ids.size,
+                                                    C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
+    def minhash_equal_count(self, i: int, j: int) -> int:
+        out = C.c_int32()
+        self._ck(self.L.mhapb_minhash_equal_count(self.h, i, j, C.byref(out)))
+        return out.value
+
+
+def format_match(hit_row) -> str:
+    """impl/MatchResult.java:98-113 through the library (one line, no newline)."""
+    h = Hit()
+    for f, _ in Hit._fields_:
+        v = hit_row[f]
+        setattr(h, f, v.item() if hasattr(v, "item") else v)
+    buf = C.create_string_buffer(256)
+    load().mhapb_format_match(C.byref(h), buf, 256)
+    return buf.value.decode()
+
+
+def dat_encode(id_, is_fwd, seq_len, minhash, seq_len_kmers, ordered_k, ord_hp, header=None) -> bytes:
+    mh = np.ascontiguousarray(minhash, dtype=np.int32)
+    oh = np.ascontiguousarray(ord_hp, dtype=np.int32).reshape(-1, 2)
+    hdr = None if header is None else (header if isinstance(header, bytes) else header.encode())
+    L = load()
+    n = L.mhapb_dat_encode(id_, int(is_fwd), hdr, seq_len, _ptr(mh), mh.size, seq_len_kmers, ordered_k, _ptr(oh), oh.shape[0], None)
+    if n < 0:
+        raise MhapError(n, "dat_encode")
+    buf = C.create_string_buffer(n)
+    L.mhapb_dat_encode(id_, int(is_fwd), hdr, seq_len, _ptr(mh), mh.size, seq_len_kmers, ordered_k, _ptr(oh), oh.shape[0], buf)
+    return buf.raw
+
+
+def dat_decode(data: bytes, id_offset: int = 0) -> dict:
+    """SequenceSketchStreamer.java:278-320 + SequenceSketch.fromByteStream: .dat bytes -> flat arrays."""
+    L = load()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    n = C.c_uint32(); H = C.c_int32(); mo = C.c_int32(); ok = C.c_int32()
+    rc = L.mhapb_dat_decode(_ptr(buf) if buf.size else None, buf.size, id_offset, C.byref(n), C.byref(H), C.byref(mo), C.byref(ok),
+                            None, None, None, None, None, None, None)
+    if rc:
+        raise MhapError(rc, "corrupt .dat stream")
+    nr, h, s = n.value, H.value, max(mo.value, 1)
+    out = dict(ids=np.zeros(nr, np.int64), is_fwd=np.zeros(nr, np.uint8), seq_len=np.zeros(nr, np.int32),
+               seq_len_kmers=np.zeros(nr, np.int32), minhash=np.zeros((nr, h), np.int32), ord=np.zeros((nr, s, 2), np.int32),
+               ord_n=np.zeros(nr, np.int32), ordered_kmer_size=ok.value, num_hashes=h)
+    mo2 = C.c_int32(s)
+    rc = L.mhapb_dat_decode(_ptr(buf) if buf.size else None, buf.size, id_offset, C.byref(n), C.byref(H), C.byref(mo2), C.byref(ok),
+                            _ptr(out["ids"]), _ptr(out["is_fwd"]), _ptr(out["seq_len"]), _ptr(out["seq_len_kmers"]),
+                            _ptr(out["minhash"]), _ptr(out["ord"]), _ptr(out["ord_n"]))
+    if rc:
+        raise MhapError(rc, "corrupt .dat stream")
+    return out

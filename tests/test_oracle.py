@@ -1,0 +1,231 @@
+"""CPU suite, part 1: pin the oracle.
+
+The reference (marbl/MHAP, Java) ships no tests, no golden vectors and cannot run here (no JVM), and
+its hash / sort arithmetic lives in un-vendored Guava 19.0 / fastutil 7.0.12 -- so parity is UNPINNED
+by the reference itself.  What pins the restatement:
+  * the public MurmurHash3 known-answer vectors (Guava's own Murmur3Hash128Test vectors for x64_128,
+    SMHasher's verification constants for both functions),
+  * agreement between two independently written restatements (oracle/mhap_oracle.c and
+    oracle/pyref.py) on random inputs with N's, IUPAC letters, repeats and duplicate hashes,
+  * the path-level vectors recorded in SURVEY.md 8c (tests/golden/path_vectors.json).
+"""
+import json
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import pyref
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    with open(os.path.join(golden_dir, "murmur3_kat.json")) as f:
+        return json.load(f)
+
+
+def test_murmur3_x64_128_known_answers(kat):
+    for row in kat["x64_128"]:
+        data = row["ascii"].encode()
+        h1, h2 = orc.murmur3_x64_128(data, row["seed"])
+        assert (f"{h1:016x}", f"{h2:016x}") == (row["h1"], row["h2"]), row
+        assert pyref.murmur3_x64_128(data, row["seed"]) == (h1, h2)
+
+
+def test_murmur3_x86_32_known_answers(kat):
+    for row in kat["x86_32"]:
+        data = bytes.fromhex(row["hex"])
+        seed = int(row["seed"], 16)
+        assert f"{orc.murmur3_x86_32(data, seed):08x}" == row["h"], row
+        assert pyref.murmur3_x86_32(data, seed) == orc.murmur3_x86_32(data, seed)
+
+
+def test_smhasher_verification(kat):
+    # Appleby's VerificationTest: hash keys {0}, {0,1}, ... with seed 256-i, then hash the hashes with seed 0.
+    def verify(fn, nbytes):
+        acc = b""
+        for i in range(256):
+            acc += fn(bytes(range(i)), 256 - i)
+        return fn(acc, 0)[:4][::-1].hex()
+
+    f32 = lambda d, s: struct.pack("<I", orc.murmur3_x86_32(d, s))
+    f128 = lambda d, s: struct.pack("<QQ", *orc.murmur3_x64_128(d, s))
+    assert verify(f32, 4) == kat["smhasher_verification"]["x86_32"]
+    assert verify(f128, 16) == kat["smhasher_verification"]["x64_128"]
+
+
+def _rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(alphabet) for _ in range(n))
+
+
+def _nasty_seq(rng, n):
+    """ACGT with N's, IUPAC, lower case free (callers upper-case), tandem repeats and homopolymers."""
+    s = []
+    while len(s) < n:
+        r = rng.random()
+        if r < 0.15:
+            unit = _rand_seq(rng, rng.randint(1, 6))
+            s.extend(unit * rng.randint(3, 15))
+        elif r < 0.25:
+            s.extend(rng.choice("ACGT") * rng.randint(5, 40))
+        elif r < 0.30:
+            s.extend(_rand_seq(rng, rng.randint(1, 5), "NRYKMSWBDHV"))
+        else:
+            s.extend(_rand_seq(rng, rng.randint(5, 60)))
+    return "".join(s[:n])
+
+
+def test_path_vectors(golden_dir):
+    with open(os.path.join(golden_dir, "path_vectors.json")) as f:
+        pv = json.load(f)
+    assert f"{int(orc.kmer_hashes_long('ACGTACGTACGTACGT', 16)[0]) & 0xFFFFFFFFFFFFFFFF:016x}" == pv["h1_ACGTx4"]
+    assert int(orc.kmer_hashes_int("ACGTACGTACGT", 12)[0]) == pv["m32_ACGTx3"]
+    s = pv["minhash"]["seq"]
+    assert orc.minhash_sketch(s, 16, 8).tolist() == pv["minhash"]["weighted"]
+    assert orc.minhash_sketch(s, 16, 8, unweighted=True).tolist() == pv["minhash"]["unweighted"]
+    assert pyref.minhash_sketch(s, 16, 8) == pv["minhash"]["weighted"]
+    b = pv["bottom"]
+    got, slk = orc.bottom_sketch(b["seq"], 12, 5)
+    assert got.tolist() == b["expected"] and slk == len(b["seq"]) - 11
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_c_oracle_matches_python_restatement_sketch(seed):
+    rng = random.Random(seed)
+    for _ in range(6):
+        n = rng.choice([16, 17, 40, 130, 300, 700])
+        s = _nasty_seq(rng, n) if rng.random() < 0.6 else _rand_seq(rng, n)
+        k = rng.choice([16, 16, 12, 7, 21, 8])
+        H = rng.choice([8, 32, 64])
+        for unweighted in (False, True):
+            a = orc.minhash_sketch(s, k, H, unweighted)
+            if len(s) - k + 1 < 1:
+                assert a is None and pyref.minhash_sketch(s, k, H, unweighted) is None
+                continue
+            assert a.tolist() == pyref.minhash_sketch(s, k, H, unweighted)
+        ok = rng.choice([12, 12, 5, 14, 13])
+        S = rng.choice([5, 50, 1536])
+        got, slk = orc.bottom_sketch(s, ok, S)
+        if len(s) - ok + 1 <= 0:
+            assert got is None
+        else:
+            assert [tuple(x) for x in got.tolist()] == [tuple(x) for x in pyref.bottom_sketch(s, ok, S)[0]]
+        assert orc.rc(s).decode() == pyref.rc(s)
+        assert orc.rc(orc.rc(s)).decode() == s.upper()
+
+
+def test_quick_select_is_exact_median():
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        n = int(rng.integers(1, 200))
+        a = rng.integers(-20, 20, size=n).astype(np.int32) if rng.random() < 0.5 else rng.integers(-10**6, 10**6, size=n).astype(np.int32)
+        for k in {0, n // 2, n - 1}:
+            assert orc.quick_select(a, k) == int(np.sort(a)[k])
+
+
+def _overlapping_reads(rng, n_reads, L, glen, err, with_n=False):
+    g = _rand_seq(rng, glen)
+    reads = []
+    for _ in range(n_reads):
+        st = rng.randrange(0, glen - L)
+        r = list(g[st:st + L])
+        for i in range(L):
+            if rng.random() < err:
+                r[i] = rng.choice("ACGT")
+        if with_n and rng.random() < 0.3:
+            r[rng.randrange(L)] = "N"
+        s = "".join(r)
+        if rng.random() < 0.5:
+            s = pyref.rc(s)
+        reads.append(s)
+    return reads
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_c_oracle_matches_python_restatement_search(seed):
+    rng = random.Random(100 + seed)
+    reads = _overlapping_reads(rng, 14, 400, 1500, 0.04, with_n=True)
+    reads.append("ACGT" * 20)          # shorter than min-olap: skipped
+    reads.append(_rand_seq(rng, 130))
+    H, S = 64, 60
+    st = orc.Store(k=16, num_hashes=H, ordered_k=12, ordered_size=S)
+    bases, offs = orc.pack_reads(reads)
+    st.add_reads(bases, offs)
+    res = st.search_self(num_min_matches=2, accept_score=0.5, keep_all=True)
+    pstore = pyref.sketch_reads(reads, k=16, H=H, ok=12, S=S)
+    phits, pstats = pyref.search(pstore, pstore, True, m=2, accept=0.5, ok=12)
+    assert len(st) == len(pstore)
+    assert res.stats["elements_processed"] == pstats["elements_processed"]
+    assert res.stats["sequences_hit"] == pstats["sequences_hit"]
+    assert res.stats["fully_compared"] == pstats["fully_compared"]
+    got = sorted((int(h["from_id"]), int(h["to_id"]), int(h["to_fwd"]), int(h["hit_count"]), int(h["a1"]), int(h["a2"]),
+                  int(h["b1"]), int(h["b2"]), int(h["valid_count"]), int(h["intersect"]), int(h["kmin"])) for h in res.hits)
+    def ovt(o):
+        return (0,) * 7 if o is None else (o["a1"], o["a2"], o["b1"], o["b2"], o["valid_count"], o["intersect"], o["kmin"])
+    exp = sorted((h["from_id"], h["to_id"], int(h["to_fwd"]), h["hit_count"]) + ovt(h["ov"]) for h in phits)
+    assert got == exp
+    assert len(got) > 0 and any(h["accepted"] for h in phits)
+    pscore = {(h["from_id"], h["to_id"], int(h["to_fwd"])): h["score"] for h in phits}
+    for h in res.hits:
+        assert abs(h["score"] - pscore[(int(h["from_id"]), int(h["to_id"]), int(h["to_fwd"]))]) < 1e-15
+        assert bool(h["accepted"]) == (h["score"] >= 0.5)
+
+
+def test_overlap_info_on_duplicate_hash_runs():
+    # hand-built ordered sketches with runs of equal hashes exercise the first/last-match branch
+    rng = random.Random(7)
+    for _ in range(200):
+        def mk(n, L):
+            hs = sorted(rng.randrange(-40, 40) for _ in range(n))
+            out, last_h, last_p = [], None, -1
+            for h in hs:
+                p = rng.randrange(0, L) if h != last_h else min(L - 1, last_p + rng.randrange(1, 5))
+                out.append((h, p)); last_h, last_p = h, p
+            return out
+        L1, L2 = rng.randrange(50, 300), rng.randrange(50, 300)
+        A, B = mk(rng.randrange(1, 80), L1), mk(rng.randrange(1, 80), L2)
+        o = orc.overlap_info(np.array(A, np.int32).reshape(-1, 2), L1, np.array(B, np.int32).reshape(-1, 2), L2, 12, 0.3)
+        p = pyref.overlap_info(A, L1, B, L2, 12, 0.3)
+        if p is None:
+            assert o.empty == 1
+        else:
+            assert o.empty == 0
+            assert (o.a1, o.a2, o.b1, o.b2, o.valid_count, o.intersect, o.kmin) == (p["a1"], p["a2"], p["b1"], p["b2"], p["valid_count"], p["intersect"], p["kmin"])
+
+
+def test_match_result_format_and_docs_fixture(golden_dir):
+    # docs/source/quickstart.rst:66-68 shows three output lines (input not shipped): format check only
+    with open(os.path.join(golden_dir, "quickstart_lines.txt")) as f:
+        lines = [l.strip() for l in f if l.strip()]
+    for ln in lines:
+        tok = ln.split()
+        assert len(tok) == 12
+        float(tok[2]); float(tok[3])
+        assert all(t.lstrip("-").isdigit() for t in tok[:2] + tok[4:])
+    hit = np.zeros(1, dtype=orc.HIT_DTYPE)[0]
+    hit["from_id"], hit["to_id"], hit["from_fwd"], hit["to_fwd"] = 155, 11, 1, 0
+    hit["a1"], hit["a2"], hit["b1"], hit["b2"], hit["from_len"], hit["to_len"] = 16, 1166, 2, 1153, 1180, 1201
+    hit["valid_count"], hit["score"] = 20, 1.0 - 0.185
+    s = orc.format_match(hit)
+    # reverse strand flips to len - b2 - 1, len - b1 - 1
+    assert s == "155 11 0.185000 20.000000 0 16 1166 1180 1 47 1198 1201"
+
+
+def test_dat_record_layout():
+    mh = np.array([1, -2, 3, 4], np.int32)
+    od = np.array([[-5, 7], [6, 0]], np.int32)
+    rec = orc.dat_encode(258, False, 100, mh, 89, 12, od)
+    assert rec[0] == 0 and struct.unpack(">i", rec[1:5])[0] == len(rec) - 5
+    p = rec[5:]
+    assert p[0] == 0 and struct.unpack(">q", p[1:9])[0] == 258
+    hl = struct.unpack(">H", p[9:11])[0]
+    assert p[11:11 + hl] == b"258"
+    q = p[11 + hl:]
+    assert struct.unpack(">ii", q[:8]) == (100, 4)
+    assert struct.unpack(">4i", q[8:24]) == (1, -2, 3, 4)
+    assert struct.unpack(">iii", q[24:36]) == (89, 12, 2)
+    assert struct.unpack(">4i", q[36:52]) == (-5, 7, 6, 0)
+    assert len(q) == 52
