@@ -70,9 +70,9 @@ def test_repeat_rich_queries_overflow_to_dense_counting():
     # every read shares a long tandem repeat, so each query hits every stored sketch (> 3072 distinct targets)
     rng = random.Random(4)
     rep = "ACGGTCATTG" * 40
-    reads = [rand_seq(rng, 150) + rep + rand_seq(rng, 150) for _ in range(1700)]
+    reads = [rand_seq(rng, 150) + rep + rand_seq(rng, 150) for _ in range(3200)]
     hits, stats, _ = _run_self(reads, H=32, S=64, m=3, thr=0.9, keep_all=False)
-    assert stats["sequences_hit"] > 3072 * 1700
+    assert stats["sequences_hit"] > 3072 * 3200
 
 
 def test_nasty_reads_with_duplicate_ordered_hashes():
