@@ -94,6 +94,9 @@ typedef struct {
     float index_ms, probe_ms, filter_ms;              /* K2a, K2b, K2c */
     int64_t kernel_launches;                          /* launches of this library's own kernels */
     int64_t xorshift_steps;                           /* algorithmic XORShift-min steps of the last sketch call */
+    float sketch_total_ms;                            /* first K1 launch -> last K1 kernel end, all chunks */
+    float search_total_ms;                            /* K2b start -> K2c end (device work only) */
+    int64_t kmers_hashed;                             /* k-mers (MinHash k) of the last sketch call */
 } mhapb_timing;
 
 /* ---- housekeeping ------------------------------------------------------------------------ */
@@ -108,6 +111,10 @@ int  mhapb_get_timing(mhapb_ctx *ctx, mhapb_timing *out);
  * in pinned memory. */
 int  mhapb_host_alloc(size_t bytes, void **out);
 void mhapb_host_free(void *p);
+/* Micro-benchmark for the roofline denominator of K1b: independent 64-bit XORShift chains
+ * (x ^= x<<21; x ^= x>>>35; x ^= x<<4) at full occupancy, no compare, no memory.  Returns the
+ * sustained steps/s of this GPU at its current clocks. */
+int  mhapb_xorshift_peak(mhapb_ctx *ctx, double *steps_per_s);
 
 /* ---- K1: sketching ------------------------------------------------------------------------
  * Replaces SequenceSketchStreamer.getSketch (impl/SequenceSketchStreamer.java:262-266) applied

@@ -138,6 +138,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         }
     }
     ctx->timing.xorshift_steps = 0;
+    ctx->timing.kmers_hashed = 0;
     if (all.empty()) return MHAPB_OK;
 
     const uint64_t chunk_cap = 256ull << 20;   // k-mers of key scratch per chunk (2 GB keys + 1 GB weights)
@@ -169,6 +170,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
             if (is_short(d)) { max_k_short = std::max(max_k_short, nk); max_len_short = std::max(max_len_short, (int)d.len); }
             else { if (first_long == n) first_long = i; max_k_long = std::max(max_k_long, nk); max_len_long = std::max(max_len_long, (int)d.len); }
             ctx->timing.xorshift_steps += (int64_t)nk * H;
+            ctx->timing.kmers_hashed += nk;
         }
         const int n_long = n - first_long;
         CU(ctx, ctx->desc.ensure((size_t)n * sizeof(StrandDesc)));
@@ -212,6 +214,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         cudaEventElapsedTime(&a, evs[i], evs[i + 1]); cudaEventElapsedTime(&b, evs[i + 1], evs[i + 2]); cudaEventElapsedTime(&c, evs[i + 2], evs[i + 3]);
         ctx->timing.hash_dedup_ms += a; ctx->timing.minhash_ms += b; ctx->timing.ordered_ms += c;
     }
+    if (evs.size() >= 2) { float t = 0; cudaEventElapsedTime(&t, evs.front(), evs.back()); ctx->timing.sketch_total_ms += t; }
     for (auto e : evs) cudaEventDestroy(e);
     ctx->timing.kernel_launches += launches;
     return MHAPB_OK;
@@ -221,6 +224,7 @@ void reset_sketch_timing(mhapb_ctx *ctx)
 {
     ctx->timing.h2d_ms = ctx->timing.d2h_ms = 0;
     ctx->timing.hash_dedup_ms = ctx->timing.minhash_ms = ctx->timing.ordered_ms = 0;
+    ctx->timing.sketch_total_ms = 0;
     ctx->timing.kernel_launches = 0;
 }
 
@@ -400,6 +404,7 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
         }
     }
     ctx->timing.kernel_launches += launches;
+    ctx->timing.search_total_ms = ctx->timing.probe_ms + ctx->timing.filter_ms;
     if (stats) *stats = st;
     if (n_out) *n_out = hits.size();
     if (out) {
@@ -528,6 +533,25 @@ int mhapb_host_alloc(size_t bytes, void **out)
     return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? MHAPB_OK : MHAPB_ENOMEM;
 }
 void mhapb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int mhapb_xorshift_peak(mhapb_ctx *ctx, double *steps_per_s)
+{
+    if (!ctx || !steps_per_s) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, ctx->eq.ensure(16));
+    float best = 1e30f; double steps = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(ctx->ev[0], ctx->stream);
+        CU(ctx, launch_xorshift_peak(ctx->stream, ctx->eq.as<unsigned long long>(), &steps));
+        cudaEventRecord(ctx->ev[1], ctx->stream);
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *steps_per_s = steps / (best * 1e-3);
+    return MHAPB_OK;
+}
 
 int mhapb_sketch_device(mhapb_ctx *ctx, const mhapb_sketch_params *p, const void *d_bases, const uint64_t *h_offsets,
                         uint32_t n_reads, int both_strands, void *d_minhash, void *d_ord, void *d_ord_n, void *d_status)

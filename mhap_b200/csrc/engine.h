@@ -44,6 +44,8 @@ cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_stra
 cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
                            int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,
                            const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int *launches);
+// independent XORShift chains at full occupancy: the integer-issue ceiling K1b is measured against
+cudaError_t launch_xorshift_peak(cudaStream_t st, unsigned long long *d_sink, double *steps);
 int hash_dedup_grid();
 int ordered_grid();
 size_t dedup_table_cap_short();   // slots per block in SketchScratch.dupcnt

@@ -388,6 +388,28 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
 }
 
 // ---------------------------------------------------------------------------------------------
+// roofline denominator for K1b: the same recurrence with nothing else (4 independent chains/thread)
+// ---------------------------------------------------------------------------------------------
+constexpr int kPeakIters = 4096, kPeakIlp = 4;
+__global__ void __launch_bounds__(256) k_xorshift_peak(unsigned long long *sink)
+{
+    uint64_t x[kPeakIlp];
+#pragma unroll
+    for (int i = 0; i < kPeakIlp; i++) x[i] = 0x9E3779B97F4A7C15ull * (blockIdx.x * 256ull + threadIdx.x + 1) + i;
+    for (int it = 0; it < kPeakIters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < kPeakIlp; i++) x[i] = xorshift_step(x[i]);
+        }
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < kPeakIlp; i++) acc ^= x[i];
+    if (acc == 0x1234567) atomicAdd(sink, 1ull);   // keeps the chains live
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 static int g_sm_count = 0;
@@ -402,6 +424,14 @@ static int sm_count()
 }
 
 static constexpr uint32_t kShortTableCap = kShortMaxKmers + kShortMaxKmers / 2 + 8;   // 24584 slots = 192 KB
+
+cudaError_t launch_xorshift_peak(cudaStream_t st, unsigned long long *d_sink, double *steps)
+{
+    const int grid = sm_count() * 8;
+    k_xorshift_peak<<<grid, 256, 0, st>>>(d_sink);
+    *steps = (double)grid * 256.0 * kPeakIters * 8.0 * kPeakIlp;
+    return cudaGetLastError();
+}
 
 int hash_dedup_grid() { return sm_count(); }          // 1 CTA/SM (shared-memory table)
 int ordered_grid() { return sm_count() * 2; }

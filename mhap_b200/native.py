@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libmhap_b200.so")
 # every symbol include/mhap_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "mhapb_version", "mhapb_create", "mhapb_destroy", "mhapb_last_error", "mhapb_free", "mhapb_get_timing",
-    "mhapb_host_alloc", "mhapb_host_free", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
+    "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
     "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads",
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
@@ -66,7 +66,8 @@ class Stats(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("hash_dedup_ms", C.c_float), ("minhash_ms", C.c_float),
                 ("ordered_ms", C.c_float), ("index_ms", C.c_float), ("probe_ms", C.c_float), ("filter_ms", C.c_float),
-                ("kernel_launches", C.c_int64), ("xorshift_steps", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("xorshift_steps", C.c_int64), ("sketch_total_ms", C.c_float),
+                ("search_total_ms", C.c_float), ("kmers_hashed", C.c_int64)]
 
 
 _lib = None
@@ -90,6 +91,7 @@ def load():
     L.mhapb_get_timing.argtypes = [vp, P(Timing)]
     L.mhapb_host_alloc.argtypes = [C.c_size_t, P(vp)]
     L.mhapb_host_free.argtypes = [vp]; L.mhapb_host_free.restype = None
+    L.mhapb_xorshift_peak.argtypes = [vp, P(C.c_double)]
     L.mhapb_sketch.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
     L.mhapb_sketch_device.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
     L.mhapb_sketch_to_dat.argtypes = [vp, P(SketchParams), vp, vp, vp, u32, C.c_int, P(vp), P(u64), P(u32)]
@@ -159,6 +161,11 @@ class Engine:
         t = Timing()
         self._ck(self.L.mhapb_get_timing(self.h, C.byref(t)))
         return {f: getattr(t, f) for f, _ in Timing._fields_}
+
+    def xorshift_peak(self) -> float:
+        v = C.c_double()
+        self._ck(self.L.mhapb_xorshift_peak(self.h, C.byref(v)))
+        return v.value
 
     # ---- K1 ----
     def sketch(self, bases, offsets, params: SketchParams, both_strands=True, want_ord=True):
