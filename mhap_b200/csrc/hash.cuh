@@ -41,6 +41,7 @@ __host__ __device__ __forceinline__ uint64_t murmur3_128_h1_chars(const C &ch, i
     uint64_t h1 = 0, h2 = 0;
     const int nblocks = k >> 3;            // 16-byte blocks = 8 chars
     int p = 0;
+#pragma unroll 4
     for (int b = 0; b < nblocks; b++, p += 8) {
         uint64_t k1 = (uint64_t)ch(p) | ((uint64_t)ch(p + 1) << 16) | ((uint64_t)ch(p + 2) << 32) | ((uint64_t)ch(p + 3) << 48);
         uint64_t k2 = (uint64_t)ch(p + 4) | ((uint64_t)ch(p + 5) << 16) | ((uint64_t)ch(p + 6) << 32) | ((uint64_t)ch(p + 7) << 48);
@@ -73,6 +74,7 @@ __host__ __device__ __forceinline__ uint32_t murmur3_32_chars(const C &ch, int k
     uint32_t h = 0;
     const int nblocks = k >> 1;            // 4-byte blocks = 2 chars
     int p = 0;
+#pragma unroll 8
     for (int b = 0; b < nblocks; b++, p += 2) {
         uint32_t kk = (uint32_t)ch(p) | ((uint32_t)ch(p + 1) << 16);
         kk *= c1; kk = rotl32(kk, 15); kk *= c2;

@@ -65,7 +65,7 @@ __device__ __forceinline__ int warp_alloc(int *counter, bool want)
 // Output per strand: keys[koff .. koff+nlight) weight-1 hashes, keys[koff+nk-1 .. ] (downwards)
 // the hashes with weight > 1 and their weights.  Order is irrelevant: the XORShift map is a
 // bijection, so two distinct keys never tie in the min.
-template <bool LONG>
+template <bool LONG, int KC /* compile-time k, 0 = runtime */>
 __global__ void __launch_bounds__(1024)
 k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc, int s_begin, int s_end,
              int k, int unweighted, uint32_t table_cap, uint32_t chars_cap, SketchScratch sc, uint32_t *queue)
@@ -108,25 +108,33 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
         __syncthreads();
 
         const CharsGlobal gsrc{bases + d.base_off, d.len, d.rc};
-        for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-            uint64_t h;
-            if (LONG) h = murmur3_128_h1_chars([&](int j) { return gsrc(i + j); }, k);
-            else      h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, k);
-            if (h == kEmptyKey) { atomicAdd(&s_special, 1); continue; }
-            uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * C) >> 32);
-            for (;;) {
-                unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&table[slot]),
-                                                   (unsigned long long)kEmptyKey, (unsigned long long)h);
-                if (old == kEmptyKey) break;
-                if (old == h) {
-                    if (!unweighted) {
-                        if (!LONG) atomicOr(&dupmask[slot >> 5], 1u << (slot & 31));
-                        atomicAdd(&dupcnt[slot], 1u);
+        // uniform trip count + __syncwarp: the CAS probe below is a data-dependent loop and without an
+        // explicit reconvergence point the lanes of a warp stay split for the rest of the strand
+        for (int base = 0; base < nk; base += blockDim.x) {
+            const int i = base + (int)threadIdx.x;
+            if (i < nk) {
+                uint64_t h;
+                if (LONG) h = murmur3_128_h1_chars([&](int j) { return gsrc(i + j); }, KC ? KC : k);
+                else      h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, KC ? KC : k);
+                if (h == kEmptyKey) atomicAdd(&s_special, 1);
+                else {
+                    uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * C) >> 32);
+                    for (;;) {
+                        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&table[slot]),
+                                                           (unsigned long long)kEmptyKey, (unsigned long long)h);
+                        if (old == kEmptyKey) break;
+                        if (old == h) {
+                            if (!unweighted) {
+                                if (!LONG) atomicOr(&dupmask[slot >> 5], 1u << (slot & 31));
+                                atomicAdd(&dupcnt[slot], 1u);
+                            }
+                            break;
+                        }
+                        if (++slot == C) slot = 0;
                     }
-                    break;
                 }
-                if (++slot == C) slot = 0;
             }
+            __syncwarp();
         }
         __syncthreads();
 
@@ -187,11 +195,25 @@ struct LaneMins {
     int32_t out[B];
 };
 
+// The step on 32-bit halves.  tools/ubench_xorshift.cu measured eight instruction mixes for this
+// recurrence on B200 (shifts as SHF on the alu pipe vs as IMAD / IMAD.WIDE / IMAD.HI on the fma pipe):
+// the plain form below -- ptxas emits 3 SHF + 4 LOP3 (alu) + 2 IMAD.SHL (fma) -- is the fastest at
+// 14.1 cycles per warp-step (alu-pipe bound, 7 x 2 cycles); every multiply-based rewrite was slower
+// (14.2-17.7), wide/high multiplies being far below the alu rate (profiles/ubench_xorshift_r1.txt).
+__device__ __forceinline__ void xorshift_step32(uint32_t &lo, uint32_t &hi)
+{
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    x = xorshift_step(x);
+    lo = (uint32_t)x; hi = (uint32_t)(x >> 32);
+}
+
 template <int B, bool WEIGHTED>
 __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ wts,
                                                  int n, int dir /* +1 light, -1 heavy */, uint64_t *kbuf, uint32_t *wbuf, int lane)
 {
-    uint64_t x = 0;
+    constexpr int G = B < 4 ? B : 4;   // steps per rare-path check
+    static_assert(B % G == 0, "B must be a multiple of the check group");
+    uint32_t xl = 0, xh = 0;
     uint32_t w = 1;
     const int total = n + 31;
     for (int t0 = 0; t0 < total; t0 += 32) {
@@ -206,30 +228,62 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
         const int jn = min(32, total - t0);
 #pragma unroll 1
         for (int j = 0; j < jn; j++) {
-            uint64_t xin = __shfl_up_sync(kFull, x, 1);
-            x = lane == 0 ? kbuf[j] : xin;
+            const uint32_t il = __shfl_up_sync(kFull, xl, 1), ih = __shfl_up_sync(kFull, xh, 1);
+            const uint64_t kin = kbuf[j];
+            xl = lane == 0 ? (uint32_t)kin : il;
+            xh = lane == 0 ? (uint32_t)(kin >> 32) : ih;
             if (WEIGHTED) {
                 uint32_t win = __shfl_up_sync(kFull, w, 1);
                 w = lane == 0 ? wbuf[j] : win;
             }
             const int e = t0 + j - lane;
             if (e >= 0 && e < n) {
+                if (!WEIGHTED) {
 #pragma unroll
-                for (int b = 0; b < B; b++) {
-                    uint32_t c = 0;
-                    do {
-                        x = xorshift_step(x);
-                        const int32_t xh = (int32_t)(x >> 32);
-                        if (xh <= m.hi[b]) {
-                            const uint32_t xl = (uint32_t)x;
-                            if (xh < m.hi[b] || xl < m.lo[b]) {      // signed 64-bit x < best[word]
-                                m.hi[b] = xh; m.lo[b] = xl;
-                                const uint64_t key = keys[(long long)dir * e];
-                                // MinHashSketch.java:146-149: even word -> (int)key, odd -> (int)(key>>>32)
-                                m.out[b] = ((lane * B + b) & 1) ? (int32_t)(key >> 32) : (int32_t)key;
+                    for (int b0 = 0; b0 < B; b0 += G) {
+                        uint32_t l[G], h[G];
+                        bool any = false;
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            xorshift_step32(xl, xh);
+                            l[g] = xl; h[g] = xh;
+                            any |= (int32_t)xh <= m.hi[b0 + g];
+                        }
+                        if (__builtin_expect(any, 0)) {   // rare: ~ln(n) times per word per strand
+                            const uint64_t key = keys[(long long)dir * e];
+#pragma unroll
+                            for (int g = 0; g < G; g++) {
+                                // signed 64-bit x < best[word]  (MinHashSketch.java:144)
+                                if ((int32_t)h[g] < m.hi[b0 + g] || ((int32_t)h[g] == m.hi[b0 + g] && l[g] < m.lo[b0 + g])) {
+                                    m.hi[b0 + g] = (int32_t)h[g]; m.lo[b0 + g] = l[g];
+                                    // :146-149 even word -> (int)key, odd word -> (int)(key>>>32)
+                                    m.out[b0 + g] = ((lane * B + b0 + g) & 1) ? (int32_t)(key >> 32) : (int32_t)key;
+                                }
                             }
                         }
-                    } while (WEIGHTED && ++c < w);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int b = 0; b < B; b++) {
+                        // register arrays need static indices: weighted k-mers (rare) go through a switch-free
+                        // unrolled select below instead of indexing m.hi[b] dynamically
+                        int32_t bh = 0x7fffffff; uint32_t bl = 0xffffffffu;
+                        bool hit = false;
+                        for (uint32_t c = 0; c < w; c++) {
+                            xorshift_step32(xl, xh);
+                            if ((int32_t)xh < bh || ((int32_t)xh == bh && xl < bl)) { bh = (int32_t)xh; bl = xl; hit = true; }
+                        }
+                        if (hit) {
+                            const uint64_t key = keys[(long long)dir * e];
+#pragma unroll
+                            for (int bb = 0; bb < B; bb++) {
+                                if (bb == b && (bh < m.hi[bb] || (bh == m.hi[bb] && bl < m.lo[bb]))) {
+                                    m.hi[bb] = bh; m.lo[bb] = bl;
+                                    m.out[bb] = ((lane * B + bb) & 1) ? (int32_t)(key >> 32) : (int32_t)key;
+                                }
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -276,7 +330,7 @@ k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, Sket
 // (hash biased to unsigned order << 32 | position) -- which is exactly "ascending signed hash,
 // ties by ascending position" of fastutil's stable radixSortIndirect -- then bitonic-sort the
 // S survivors in shared memory.
-template <bool LONG>
+template <bool LONG, int KC /* compile-time ordered k, 0 = runtime */>
 __global__ void __launch_bounds__(512)
 k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc, int s_begin, int s_end, int ok, int S,
           int ord_stride, uint32_t len_cap, uint32_t sel_cap, SketchScratch sc, int32_t *__restrict__ ord,
@@ -304,8 +358,8 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
         const CharsGlobal gsrc{bases + d.base_off, d.len, d.rc};
         for (int i = threadIdx.x; i < no; i += blockDim.x) {
             uint32_t h;
-            if (LONG) h = murmur3_32_chars([&](int j) { return gsrc(i + j); }, ok);
-            else      h = murmur3_32_chars([&](int j) { return chars[i + j]; }, ok);
+            if (LONG) h = murmur3_32_chars([&](int j) { return gsrc(i + j); }, KC ? KC : ok);
+            else      h = murmur3_32_chars([&](int j) { return chars[i + j]; }, KC ? KC : ok);
             oh[i] = h ^ 0x80000000u;   // signed order -> unsigned order
         }
         __syncthreads();
@@ -388,25 +442,29 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
 }
 
 // ---------------------------------------------------------------------------------------------
-// roofline denominator for K1b: the same recurrence with nothing else (4 independent chains/thread)
+// roofline denominator for K1b: the same pipe-balanced recurrence with nothing else (no compare,
+// no memory, 4 independent chains/thread)
 // ---------------------------------------------------------------------------------------------
 constexpr int kPeakIters = 4096, kPeakIlp = 4;
 __global__ void __launch_bounds__(256) k_xorshift_peak(unsigned long long *sink)
 {
-    uint64_t x[kPeakIlp];
+    uint32_t xl[kPeakIlp], xh[kPeakIlp];
 #pragma unroll
-    for (int i = 0; i < kPeakIlp; i++) x[i] = 0x9E3779B97F4A7C15ull * (blockIdx.x * 256ull + threadIdx.x + 1) + i;
+    for (int i = 0; i < kPeakIlp; i++) {
+        uint64_t x = 0x9E3779B97F4A7C15ull * (blockIdx.x * 256ull + threadIdx.x + 1) + i;
+        xl[i] = (uint32_t)x; xh[i] = (uint32_t)(x >> 32);
+    }
     for (int it = 0; it < kPeakIters; it++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
 #pragma unroll
-            for (int i = 0; i < kPeakIlp; i++) x[i] = xorshift_step(x[i]);
+            for (int i = 0; i < kPeakIlp; i++) xorshift_step32(xl[i], xh[i]);
         }
     }
-    uint64_t acc = 0;
+    uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < kPeakIlp; i++) acc ^= x[i];
-    if (acc == 0x1234567) atomicAdd(sink, 1ull);   // keeps the chains live
+    for (int i = 0; i < kPeakIlp; i++) acc ^= xl[i] ^ xh[i];
+    if (acc == 0x1234567u) atomicAdd(sink, 1ull);   // keeps the chains live
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,13 +506,14 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         uint32_t cap = (uint32_t)max_kmers_short + (uint32_t)max_kmers_short / 2 + 8;
         uint32_t chars_cap = (uint32_t)align16((size_t)max_kmers_short + k);
         size_t smem = (size_t)cap * 8 + (size_t)((cap + 31) / 32) * 4 + chars_cap;
-        e = cudaFuncSetAttribute(k_hash_dedup<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = k == 16 ? k_hash_dedup<false, 16> : k_hash_dedup<false, 0>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int grid = hash_dedup_grid();
         if (smem <= 100 * 1024) grid *= 2;
         if (grid > first_long) grid = first_long;
         // dupcnt rows are strided by the *launch's* cap so both variants can share the buffer
-        k_hash_dedup<false><<<grid, 1024, smem, st>>>(d_bases, d_desc, 0, first_long, k, unweighted, cap, chars_cap, sc, sc.counters + 0);
+        kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, 0, first_long, k, unweighted, cap, chars_cap, sc, sc.counters + 0);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -462,7 +521,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         uint32_t cap = (uint32_t)max_kmers_long + (uint32_t)max_kmers_long / 2 + 8;
         int grid = hash_dedup_grid();
         if (grid > n_strands - first_long) grid = n_strands - first_long;
-        k_hash_dedup<true><<<grid, 1024, 0, st>>>(d_bases, d_desc, first_long, n_strands, k, unweighted, cap, 0, sc, sc.counters + 1);
+        k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, first_long, n_strands, k, unweighted, cap, 0, sc, sc.counters + 1);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -512,22 +571,23 @@ cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const Strand
         uint32_t len_cap = (uint32_t)align16((size_t)max_len_short + 16);
         // a short read may have fewer ordered k-mers than S, but never more than len_cap
         size_t smem = (size_t)sel_cap * 8 + (size_t)len_cap * 4 + len_cap;
-        e = cudaFuncSetAttribute(k_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = ok == 12 ? k_ordered<false, 12> : k_ordered<false, 0>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int grid = sm_count() * (smem <= 100 * 1024 ? 2 : 1);
         if (grid > first_long) grid = first_long;
-        k_ordered<false><<<grid, 512, smem, st>>>(d_bases, d_desc, 0, first_long, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 3);
+        kern<<<grid, 512, smem, st>>>(d_bases, d_desc, 0, first_long, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 3);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (first_long < n_strands) {
         uint32_t len_cap = (uint32_t)align16((size_t)max_len_long + 16);
         size_t smem = (size_t)sel_cap * 8;
-        e = cudaFuncSetAttribute(k_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_ordered<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int grid = ordered_grid();
         if (grid > n_strands - first_long) grid = n_strands - first_long;
-        k_ordered<true><<<grid, 512, smem, st>>>(d_bases, d_desc, first_long, n_strands, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 4);
+        k_ordered<true, 0><<<grid, 512, smem, st>>>(d_bases, d_desc, first_long, n_strands, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 4);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
