@@ -209,10 +209,13 @@ __device__ __forceinline__ void xorshift_step32(uint32_t &lo, uint32_t &hi)
 
 template <int B, bool WEIGHTED>
 __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ wts,
-                                                 int n, int dir /* +1 light, -1 heavy */, uint64_t *kbuf, uint32_t *wbuf, int lane)
+                                                 int n, int dir /* +1 light, -1 heavy */, uint64_t *kring, uint32_t *wbuf, int lane)
 {
     constexpr int G = B < 4 ? B : 4;   // steps per rare-path check
     static_assert(B % G == 0, "B must be a multiple of the check group");
+    // kring: the last 64 keys that entered the pipeline (two batches), so the rare path can fetch the
+    // key of the k-mer a lane is working on (e = t - lane) with one LDS instead of keeping a global
+    // address live on the hot path.
     uint32_t xl = 0, xh = 0;
     uint32_t w = 1;
     const int total = n + 31;
@@ -221,7 +224,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
             int e = t0 + lane;
             uint64_t mk = 0; uint32_t mw = 1;
             if (e < n) { mk = keys[(long long)dir * e]; if (WEIGHTED) mw = wts[(long long)dir * e]; }
-            kbuf[lane] = mk;
+            kring[e & 63] = mk;
             if (WEIGHTED) wbuf[lane] = mw;
         }
         __syncwarp();
@@ -229,7 +232,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
 #pragma unroll 1
         for (int j = 0; j < jn; j++) {
             const uint32_t il = __shfl_up_sync(kFull, xl, 1), ih = __shfl_up_sync(kFull, xh, 1);
-            const uint64_t kin = kbuf[j];
+            const uint64_t kin = kring[(t0 + j) & 63];
             xl = lane == 0 ? (uint32_t)kin : il;
             xh = lane == 0 ? (uint32_t)(kin >> 32) : ih;
             if (WEIGHTED) {
@@ -250,7 +253,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
                             any |= (int32_t)xh <= m.hi[b0 + g];
                         }
                         if (__builtin_expect(any, 0)) {   // rare: ~ln(n) times per word per strand
-                            const uint64_t key = keys[(long long)dir * e];
+                            const uint64_t key = kring[e & 63];
 #pragma unroll
                             for (int g = 0; g < G; g++) {
                                 // signed 64-bit x < best[word]  (MinHashSketch.java:144)
@@ -274,7 +277,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
                             if ((int32_t)xh < bh || ((int32_t)xh == bh && xl < bl)) { bh = (int32_t)xh; bl = xl; hit = true; }
                         }
                         if (hit) {
-                            const uint64_t key = keys[(long long)dir * e];
+                            const uint64_t key = kring[e & 63];
 #pragma unroll
                             for (int bb = 0; bb < B; bb++) {
                                 if (bb == b && (bh < m.hi[bb] || (bh == m.hi[bb] && bl < m.lo[bb]))) {
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(256)
 k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
           int32_t *__restrict__ minhash, uint32_t *queue)
 {
-    __shared__ uint64_t s_kbuf[8][32];
+    __shared__ uint64_t s_kbuf[8][64];
     __shared__ uint32_t s_wbuf[8][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (;;) {
