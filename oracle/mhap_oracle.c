@@ -847,6 +847,17 @@ int mo_search_self(mo_store *s, const mo_search_params *sp, int threads, int kee
     return run_search(s, s->sk, s->n, 1, sp, threads, keep_all, out, n_out, stats);
 }
 
+/* Self search restricted to stored sketches [first, first+count) as queries: the sharding rule of
+ * the multi-GPU path (each rank queries its own shard against the full index). */
+int mo_search_self_range(mo_store *s, int64_t first, int64_t count, const mo_search_params *sp, int threads, int keep_all,
+                         mo_hit **out, int64_t *n_out, mo_stats *stats)
+{
+    if (first < 0) first = 0;
+    if (first > s->n) first = s->n;
+    if (count < 0 || first + count > s->n) count = s->n - first;
+    return run_search(s, s->sk + first, count, 1, sp, threads, keep_all, out, n_out, stats);
+}
+
 int mo_search_query(mo_store *s, const mo_store *q, const mo_search_params *sp, int threads, int keep_all,
                     mo_hit **out, int64_t *n_out, mo_stats *stats)
 {

@@ -123,6 +123,8 @@ void      mo_store_build_index(mo_store *s);
  * Result array is malloc'd; free with mo_free. */
 int       mo_search_self(mo_store *s, const mo_search_params *sp, int threads, int keep_all,
                          mo_hit **out, int64_t *n_out, mo_stats *stats);
+int       mo_search_self_range(mo_store *s, int64_t first, int64_t count, const mo_search_params *sp, int threads,
+                               int keep_all, mo_hit **out, int64_t *n_out, mo_stats *stats);
 /* findMatches(streamer) (AbstractMatchSearch.java:203-285): queries come from another store. */
 int       mo_search_query(mo_store *s, const mo_store *queries, const mo_search_params *sp, int threads,
                           int keep_all, mo_hit **out, int64_t *n_out, mo_stats *stats);

@@ -99,6 +99,8 @@ def lib():
         L.mo_store_build_index.restype = None
         L.mo_search_self.argtypes = [C.c_void_p, C.POINTER(SearchParams), C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_int64), C.POINTER(Stats)]
+        L.mo_search_self_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(SearchParams), C.c_int, C.c_int,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Stats)]
         L.mo_search_query.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SearchParams), C.c_int, C.c_int,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Stats)]
         L.mo_free.argtypes = [C.c_void_p]
@@ -271,6 +273,13 @@ class Store:
         sp = SearchParams(num_min_matches, min_store_length, max_shift, accept_score)
         out = C.c_void_p(); n = C.c_int64(); st = Stats()
         lib().mo_search_self(self._h, C.byref(sp), threads, int(keep_all), C.byref(out), C.byref(n), C.byref(st))
+        return self._collect(out, n, st)
+
+    def search_self_range(self, first, count, num_min_matches=3, min_store_length=0, max_shift=0.2, accept_score=0.78,
+                          threads=1, keep_all=False):
+        sp = SearchParams(num_min_matches, min_store_length, max_shift, accept_score)
+        out = C.c_void_p(); n = C.c_int64(); st = Stats()
+        lib().mo_search_self_range(self._h, first, count, C.byref(sp), threads, int(keep_all), C.byref(out), C.byref(n), C.byref(st))
         return self._collect(out, n, st)
 
     def search_query(self, queries: "Store", num_min_matches=3, min_store_length=0, max_shift=0.2, accept_score=0.78,
