@@ -116,7 +116,7 @@ def cpu_sample_size(args, cores):
     return max(cores, min(args.reads, n))
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -147,7 +147,7 @@ def run_reference(args):
                          "note": "C restatement of the Java path (oracle/); the JVM reference cannot run in this image"},
         "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=real_stdout, flush=True)
 
 
 def workload_config(args):
@@ -161,8 +161,19 @@ def workload_config(args):
 
 def main():
     args = parse()
+    # NCCL (and anything else) may print to fd 1; the contract is ONE JSON line on stdout, so route
+    # fd 1 to stderr for the duration of the run and keep the real stdout for the result line.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, real_stdout):
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, real_stdout)
         return
 
     import torch
@@ -318,7 +329,7 @@ def main():
         out["cpu_baseline"] = {"value": n * L / 1e9 / (ts + tq), "unit": "Gbases/s", "cores": cores, "kind": "port",
                                "sample": f"first {n} of {total_reads} reads x {L} bp, sketch+index+self-search, {cores} threads, {ts + tq:.1f} s",
                                "sketch_gbases_per_s": n * L / 1e9 / ts, "overlaps_per_s": cst["fully_compared"] / tq if tq > 0 else None}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
