@@ -1,0 +1,323 @@
+// mhap-b200 -- host driver above the C ABI, mirroring the reference's command line for the hot path.
+//
+// The reference's driver is Java (main/MhapMain.java); this image has no JVM, so the host side above
+// libmhap_b200.so is written in C++ with the same flags, the same stdout (MatchResult lines) and the
+// same stderr bookkeeping, for the modes on the hot path:
+//   -s <fasta|dat>                 self overlap                      (MhapMain.computeMain :452-477)
+//   -s <fasta|dat> -q <file|dir>   store vs query files              (:478-541), --no-self
+//   -p <fasta|dir> -q <outdir>     FASTA -> .dat sketch files        (:384-451)
+// Not supported (outside the path): -f filter files (and --filter-threshold, --supress-noise,
+// --no-tf, --repeat-idf-scale, which only act through a filter), --store-full-id, gz/bz2 input.
+// Paths cited are relative to /root/reference/src/main/java/edu/umd/marbl/mhap/.
+#include "../../include/mhap_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <fstream>
+#include <map>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+namespace {
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+[[noreturn]] void die(const std::string &msg)
+{
+    // the reference throws MhapRuntimeException; the JVM prints it and exits non-zero
+    fprintf(stderr, "MhapRuntimeException: %s\n", msg.c_str());
+    exit(1);
+}
+
+struct Options {
+    std::string s, q, p, f;
+    int k = 16, num_hashes = 512, num_min_matches = 3, num_threads = 1, ordered_kmer = 12, ordered_sketch = 1536;
+    int min_store_length = 0, min_olap_length = 116, settings = 0, device = 0;
+    double threshold = 0.78, max_shift = 0.2, repeat_weight = 0.9;
+    bool no_self = false, store_full_id = false, no_rc = false;
+    std::map<std::string, bool> set;
+};
+
+// utils/ParseOptions.java:327-368: flag and value are separate argv tokens, booleans are presence flags
+Options parse(int argc, char **argv)
+{
+    Options o;
+    auto need = [&](int &i) -> const char * { if (i + 1 >= argc) { printf("Missing value for option %s\n", argv[i]); exit(1); } return argv[++i]; };
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        o.set[a] = true;
+        if (a == "-s") o.s = need(i);
+        else if (a == "-q") o.q = need(i);
+        else if (a == "-p") o.p = need(i);
+        else if (a == "-f") o.f = need(i);
+        else if (a == "-k") o.k = atoi(need(i));
+        else if (a == "--num-hashes") o.num_hashes = atoi(need(i));
+        else if (a == "--threshold") o.threshold = atof(need(i));
+        else if (a == "--max-shift") o.max_shift = atof(need(i));
+        else if (a == "--num-min-matches") o.num_min_matches = atoi(need(i));
+        else if (a == "--num-threads") o.num_threads = atoi(need(i));
+        else if (a == "--repeat-weight") o.repeat_weight = atof(need(i));
+        else if (a == "--ordered-kmer-size") o.ordered_kmer = atoi(need(i));
+        else if (a == "--ordered-sketch-size") o.ordered_sketch = atoi(need(i));
+        else if (a == "--min-store-length") o.min_store_length = atoi(need(i));
+        else if (a == "--min-olap-length") o.min_olap_length = atoi(need(i));
+        else if (a == "--settings") o.settings = atoi(need(i));
+        else if (a == "--device") o.device = atoi(need(i));
+        else if (a == "--no-self") o.no_self = true;
+        else if (a == "--no-rc") o.no_rc = true;   // main/MhapMain.java: does not stop rc sketches being stored (MinHashSearch.java:80)
+        else if (a == "--store-full-id") o.store_full_id = true;
+        else if (a == "--filter-threshold" || a == "--repeat-idf-scale" || a == "--supress-noise") need(i);
+        else if (a == "--no-tf") {}
+        else if (a == "-h" || a == "--help" || a == "--version") { printf("%s\n", mhapb_version()); exit(0); }
+        else { printf("Unknown option %s\n", a.c_str()); exit(1); }
+    }
+    // main/MhapMain.java:130-198 presets fill only options the user did not set
+    if (o.settings < 0 || o.settings > 3) { printf("Please enter valid --settings flag.\n"); exit(1); }
+    auto unset = [&](const char *n) { return !o.set.count(n); };
+    if (o.settings >= 1) {
+        const int m[4] = {0, 3, 3, 2}, h[4] = {0, 512, 256, 768}, os[4] = {0, 1536, 1000, 1536}, ok[4] = {0, 12, 14, 12};
+        const double thr[4] = {0, .78, .80, .73};
+        if (unset("-k")) o.k = 16;
+        if (unset("--num-min-matches")) o.num_min_matches = m[o.settings];
+        if (unset("--num-hashes")) o.num_hashes = h[o.settings];
+        if (unset("--threshold")) o.threshold = thr[o.settings];
+        if (unset("--ordered-sketch-size")) o.ordered_sketch = os[o.settings];
+        if (unset("--ordered-kmer-size")) o.ordered_kmer = ok[o.settings];
+    }
+    // main/MhapMain.java:200-300 validation, same messages
+    struct stat st;
+    if (o.s.empty() && o.p.empty()) { printf("Please set the -s or the -p options.\n"); exit(1); }
+    if (!o.p.empty() && o.q.empty()) { printf("Please set the -q option.\n"); exit(1); }
+    for (const std::string *f : {&o.p, &o.s, &o.q, &o.f})
+        if (!f->empty() && stat(f->c_str(), &st) != 0) { printf("Could not find requested file/folder: %s\n", f->c_str()); exit(1); }
+    if (o.num_threads <= 0) { printf("Number of threads must be positive.\n"); exit(1); }
+    if (o.k <= 0) { printf("k-mer size must be positive.\n"); exit(1); }
+    if (o.num_min_matches <= 0) { printf("Minimum number of matches must be positive.\n"); exit(1); }
+    if (o.min_store_length < 0) { printf("The minimum read length stored must be >=0.\n"); exit(1); }
+    if (o.max_shift < -1.0) { printf("The minimum shift must be greater than -1.\n"); exit(1); }
+    if (o.threshold < 0.0 || o.threshold > 1.0) { printf("The second stage filter threshold must be 0<=threshold<=1.0.\n"); exit(1); }
+    if (!o.f.empty()) { printf("-f k-mer filter files are not supported by mhap-b200 (outside the accelerated path).\n"); exit(1); }
+    if (o.store_full_id) { printf("--store-full-id is not supported by mhap-b200 (numeric ids only).\n"); exit(1); }
+    return o;
+}
+
+bool ends_with(const std::string &s, const char *suf)
+{
+    size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+bool is_dir(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+
+// directory listing without dot files, sorted (main/MhapMain.java:408-425,495-512)
+std::vector<std::string> list_files(const std::string &path)
+{
+    std::vector<std::string> out;
+    if (!is_dir(path)) { out.push_back(path); return out; }
+    DIR *d = opendir(path.c_str());
+    if (!d) die("Cannot list directory " + path);
+    while (dirent *e = readdir(d)) if (e->d_name[0] != '.') out.push_back(path + "/" + e->d_name);
+    closedir(d);
+    std::sort(out.begin(), out.end());
+    return out;
+}
+
+struct Reads {
+    std::string bases; std::vector<uint64_t> offsets{0}; std::vector<int64_t> ids;
+};
+
+// impl/FastaData.java:125-204: records start with '>', sequence lines are concatenated, ids are 1-based
+// positions of the non-empty records (+offset); an empty record ends the file like the reference's
+// enqueueNextSequenceInFile returning false.  Upper-casing (:194) happens on the GPU.
+Reads read_fasta(const std::string &path, int64_t offset)
+{
+    if (ends_with(path, ".gz") || ends_with(path, ".bz2")) die("compressed FASTA is not supported by mhap-b200: " + path);
+    std::ifstream in(path, std::ios::binary);
+    if (!in) die("Could not open " + path);
+    Reads r;
+    std::string line;
+    int64_t n = 0;
+    bool have = (bool)std::getline(in, line);
+    while (have) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty() || line[0] != '>') die("Next sequence does not start with >. Invalid format.");
+        size_t start = r.bases.size();
+        while ((have = (bool)std::getline(in, line))) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (!line.empty() && line[0] == '>') break;
+            r.bases += line;
+        }
+        if (r.bases.size() == start) break;   // empty record: the reference stops reading here
+        r.offsets.push_back(r.bases.size());
+        r.ids.push_back(++n + offset);
+    }
+    return r;
+}
+
+std::vector<uint8_t> read_file(const std::string &path)
+{
+    std::ifstream in(path, std::ios::binary | std::ios::ate);
+    if (!in) die("Could not open " + path);
+    std::vector<uint8_t> buf((size_t)in.tellg());
+    in.seekg(0);
+    in.read((char *)buf.data(), (std::streamsize)buf.size());
+    return buf;
+}
+
+struct DatSketches {
+    uint32_t n = 0; int32_t H = 0, max_ord = 0, ok = 0;
+    std::vector<int64_t> ids; std::vector<uint8_t> fwd; std::vector<int32_t> len, lenk, mh, ord, ordn;
+};
+
+// impl/SequenceSketchStreamer.java:278-320 + impl/SequenceSketch.java:61-96 (ids get +offset)
+DatSketches read_dat(const std::string &path, int64_t offset)
+{
+    std::vector<uint8_t> buf = read_file(path);
+    DatSketches d;
+    if (mhapb_dat_decode(buf.data(), buf.size(), offset, &d.n, &d.H, &d.max_ord, &d.ok, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr))
+        die("Unexpected data read error.");
+    int32_t stride = std::max(1, d.max_ord);
+    d.ids.resize(d.n); d.fwd.resize(d.n); d.len.resize(d.n); d.lenk.resize(d.n); d.ordn.resize(d.n);
+    d.mh.resize((size_t)d.n * d.H); d.ord.resize((size_t)d.n * stride * 2);
+    d.max_ord = stride;
+    if (mhapb_dat_decode(buf.data(), buf.size(), offset, &d.n, &d.H, &d.max_ord, &d.ok, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(),
+                         d.mh.data(), d.ord.data(), d.ordn.data()))
+        die("Unexpected data read error.");
+    return d;
+}
+
+void ck(mhapb_ctx *ctx, int rc) { if (rc) die(mhapb_last_error(ctx)); }
+
+struct Totals { mhapb_stats st{}; };
+
+// from_sub: sketches read from a .dat file print the header string stored in the record, i.e. the
+// file-local id without the run's offset (impl/SequenceId.java:102-108, SequenceSketch.java:75)
+void emit(mhapb_hit *hits, uint64_t n, const mhapb_stats &st, Totals &tot, int64_t from_sub = 0)
+{
+    // AbstractMatchSearch.outputResults :316-338: one MatchResult.toString() per line on stdout
+    char line[256];
+    for (uint64_t i = 0; i < n; i++) { hits[i].from_id -= from_sub; mhapb_format_match(&hits[i], line, sizeof line); puts(line); }
+    fflush(stdout);
+    mhapb_free(hits);
+    tot.st.elements_processed += st.elements_processed; tot.st.sequences_hit += st.sequences_hit;
+    tot.st.fully_compared += st.fully_compared; tot.st.matches_processed += st.matches_processed;
+    tot.st.sequences_searched += st.sequences_searched;
+}
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+    Options o = parse(argc, argv);
+    const double t_total = now_s();
+    mhapb_ctx *ctx = nullptr;
+    if (mhapb_create(o.device, &ctx)) die(mhapb_last_error(nullptr));
+    mhapb_sketch_params p{o.k, o.num_hashes, o.ordered_kmer, o.ordered_sketch, o.repeat_weight < 0.0 ? 1 : 0, o.min_olap_length};
+
+    if (!o.p.empty()) {   // main/MhapMain.java:384-451
+        fprintf(stderr, "Processing FASTA files for binary compression...\n");
+        if (!is_dir(o.q)) die("Target directory doesn't exit.");
+        for (const std::string &pf : list_files(o.p)) {
+            const double t0 = now_s();
+            Reads r = read_fasta(pf, 0);
+            uint8_t *blob = nullptr; uint64_t len = 0; uint32_t nrec = 0;
+            ck(ctx, mhapb_sketch_to_dat(ctx, &p, r.bases.data(), r.offsets.data(), r.ids.data(), (uint32_t)r.ids.size(), 1, &blob, &len, &nrec));
+            std::string name = pf.substr(pf.find_last_of('/') == std::string::npos ? 0 : pf.find_last_of('/') + 1);
+            size_t dot = name.find_last_of('.');
+            if (dot != std::string::npos && dot > 0) name = name.substr(0, dot);
+            std::string outp = o.q + "/" + name + ".dat";
+            std::ofstream out(outp, std::ios::binary);
+            if (!out) die("Could not open " + outp);
+            out.write((const char *)blob, (std::streamsize)len);
+            mhapb_free(blob);
+            fprintf(stderr, "Processed %u sequences (fwd and rev).\n", nrec);
+            fprintf(stderr, "Read, hashed, and stored file %s to %s.\n", pf.c_str(), outp.c_str());
+            fprintf(stderr, "Time (s): %g\n", now_s() - t0);
+        }
+        fprintf(stderr, "Total time (s): %g\n", now_s() - t_total);
+        mhapb_destroy(ctx);
+        return 0;
+    }
+
+    fprintf(stderr, "Processing files for storage in reverse index...\n");
+    const double t_proc = now_s();
+    int64_t n_sketches = 0;
+    if (ends_with(o.s, ".dat")) {
+        DatSketches d = read_dat(o.s, 0);
+        if (d.n && d.H != o.num_hashes) die("Number of MinHashes of the sequence does not match current settings.");   // MinHashSearch.java:105
+        p.ordered_sketch_size = std::max(p.ordered_sketch_size, d.max_ord);
+        ck(ctx, mhapb_store_reset(ctx, &p));
+        ck(ctx, mhapb_store_add_sketches(ctx, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.ord.data(), d.ordn.data(), d.max_ord, d.n));
+        n_sketches = d.n;
+    } else {
+        Reads r = read_fasta(o.s, 0);
+        ck(ctx, mhapb_store_reset(ctx, &p));
+        ck(ctx, mhapb_store_add_reads(ctx, r.bases.data(), r.offsets.data(), r.ids.data(), (uint32_t)r.ids.size(), 1, &n_sketches));
+    }
+    if (n_sketches > 0) ck(ctx, mhapb_index_build(ctx));
+    fprintf(stderr, "Stored %lld sequences in the index.\n", (long long)n_sketches);
+    int64_t seq_number_processed = n_sketches / 2;   // main/MhapMain.java:462
+    fprintf(stderr, "Processed %lld unique sequences (fwd and rev).\n", (long long)n_sketches);
+    fprintf(stderr, "Time (s) to read and hash from file: %g\n", now_s() - t_proc);
+
+    const double t_score = now_s();
+    mhapb_search_params sp{o.num_min_matches, o.min_store_length, o.max_shift, o.threshold, 0, 0, 0, -1};
+    Totals tot;
+    auto self = [&]() {
+        const double t0 = now_s();
+        if (n_sketches > 0) {
+            mhapb_hit *hits = nullptr; uint64_t n = 0; mhapb_stats st{};
+            ck(ctx, mhapb_search_self(ctx, &sp, &hits, &n, &st));
+            emit(hits, n, st, tot);
+        }
+        fprintf(stderr, "Time (s) to score and output to self: %g\n", now_s() - t0);
+    };
+    if (o.q.empty()) self();
+    else {
+        if (!o.no_self) self();
+        for (const std::string &cf : list_files(o.q)) {   // :525-541
+            const double t0 = now_s();
+            fprintf(stderr, "Opened fasta file %s.\n", cf.c_str());
+            mhapb_hit *hits = nullptr; uint64_t n = 0; mhapb_stats st{};
+            int64_t processed = 0, from_sub = 0;
+            if (n_sketches == 0) { /* nothing stored: nothing can match */ }
+            else if (ends_with(cf, ".dat")) {
+                DatSketches d = read_dat(cf, seq_number_processed);
+                ck(ctx, mhapb_search_query_sketches(ctx, &sp, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.ord.data(),
+                                                    d.ordn.data(), d.max_ord, d.n, &hits, &n, &st));
+                processed = st.sequences_searched;
+                from_sub = seq_number_processed;
+            } else {
+                Reads r = read_fasta(cf, seq_number_processed);
+                ck(ctx, mhapb_search_query_reads(ctx, &sp, r.bases.data(), r.offsets.data(), r.ids.data(), (uint32_t)r.ids.size(), &hits, &n, &st));
+                processed = st.sequences_searched;
+            }
+            if (hits) emit(hits, n, st, tot, from_sub);
+            seq_number_processed += processed;   // :537 counts the sketched (forward) query sequences
+            fprintf(stderr, "Processed %lld to sequences.\n", (long long)processed);
+            fprintf(stderr, "Time (s) to score, hash to-file, and output: %g\n", now_s() - t0);
+        }
+    }
+    fprintf(stderr, "Total scoring time (s): %g\n", now_s() - t_score);
+    fprintf(stderr, "Total time (s): %g\n", now_s() - t_total);
+    // main/MhapMain.java:572-590
+    const mhapb_stats &s = tot.st;
+    const double size = (double)mhapb_store_size(ctx);
+    fprintf(stderr, "Total matches found: %lld\n", (long long)s.matches_processed);
+    fprintf(stderr, "Average number of matches per lookup: %g\n", (double)s.matches_processed / (double)s.sequences_searched);
+    fprintf(stderr, "Average number of table elements processed per lookup: %g\n", (double)s.elements_processed / (double)s.sequences_searched);
+    fprintf(stderr, "Average number of table elements processed per match: %g\n", (double)s.elements_processed / (double)s.matches_processed);
+    fprintf(stderr, "Average %% of hashed sequences hit per lookup: %g\n", (double)s.sequences_hit / (size * (double)s.sequences_searched) * 100.0);
+    fprintf(stderr, "Average %% of hashed sequences hit that are matches: %g\n", (double)s.matches_processed / (double)s.sequences_hit * 100.0);
+    fprintf(stderr, "Average %% of hashed sequences fully compared that are matches: %g\n", (double)s.matches_processed / (double)s.fully_compared * 100.0);
+    mhapb_destroy(ctx);
+    return 0;
+}
