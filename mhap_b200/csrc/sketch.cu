@@ -11,6 +11,8 @@
 #include "engine.h"
 #include "hash.cuh"
 
+#include <cstdlib>
+
 namespace mhapb {
 
 static constexpr uint64_t kEmptyKey = ~0ull;
@@ -327,6 +329,210 @@ k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, Sket
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1b, bit-sliced variant (the default): 32 k-mers per thread
+// ---------------------------------------------------------------------------------------------
+// The scalar pipeline above is bound by the alu pipe at 7 LOP3/SHF per XORShift step (3 of them shifts).
+// Bit-slicing removes the shifts: a thread keeps 64 registers R[i] = bit i of the chain states of 32
+// different k-mers (a "bundle"), so x ^= x << 21 is R[i] ^= R[i-21] -- a register rename -- and one step
+// of 32 chains is 132 two-input XORs (4.1 LOP3 per chain step; tools/ubench_bitslice.cu measures
+// 5.1e12 steps/s bare against 2.6e12 for the scalar form).
+//
+// Structure (one warp per strand, still systolic): lane l owns words [l*B,(l+1)*B); bundles enter at
+// lane 0 and move lane to lane each hop (64 shuffles per B*32 chain steps).  The running minima are exact
+// 64-bit values in shared memory; per word-step a lane only asks "does any of my 32 chains have its top
+// F bits (of the sign-biased value) all zero?", with F = a lower bound of the leading zeros of the word's
+// current minimum, which is an OR over the top planes.  Flagged chains (a superset of the true updates,
+// about 2x) are resolved exactly: the lane publishes its 64 planes to shared memory and the warp
+// re-assembles the flagged chain's 64-bit value with two ballots.
+// The first kBsScalarKeys keys of a strand (where a running minimum changes most often: the expected
+// number of updates of word w after t keys is the harmonic sum) and the keys with weight > 1 go through
+// the scalar pipeline first; so do strands too short to fill bundles.
+constexpr int kBsScalarKeys = 1024;
+constexpr int kBsTaps = 9;
+__device__ __constant__ int c_bs_tap_bits[kBsTaps] = {0, 4, 8, 10, 12, 14, 16, 18, 20};
+
+__device__ __forceinline__ void bs_step(uint32_t (&R)[64])
+{
+#pragma unroll
+    for (int i = 63; i >= 21; i--) R[i] ^= R[i - 21];      // x ^= x << 21
+#pragma unroll
+    for (int i = 0; i <= 28; i++) R[i] ^= R[i + 35];       // x ^= x >>> 35
+#pragma unroll
+    for (int i = 63; i >= 4; i--) R[i] ^= R[i - 4];        // x ^= x << 4
+}
+
+// 32x32 bit-matrix transpose in registers.  With this butterfly t[i] bit j == a[31-j] bit (31-i): bit p of
+// key c ends up in t[31-p] at bit position 31-c.
+template <int J>
+__device__ __forceinline__ void transpose_stage(uint32_t (&a)[32], uint32_t m)
+{
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        if ((k & J) == 0) {
+            uint32_t t = (a[k] ^ (a[k + J] >> J)) & m;
+            a[k] ^= t; a[k + J] ^= t << J;
+        }
+    }
+}
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32])
+{
+    transpose_stage<16>(a, 0x0000ffffu); transpose_stage<8>(a, 0x00ff00ffu); transpose_stage<4>(a, 0x0f0f0f0fu);
+    transpose_stage<2>(a, 0x33333333u); transpose_stage<1>(a, 0x55555555u);
+}
+
+// tap index for a word whose current minimum has biased high word tu (leading zeros F): largest tap <= F
+__device__ __forceinline__ uint32_t bs_tap_of(uint32_t hi_signed)
+{
+    const uint32_t tu = hi_signed ^ 0x80000000u;
+    const int F = tu ? __clz(tu) : 32;
+    return F < 4 ? 0 : F < 8 ? 1 : F < 10 ? 2 : F < 12 ? 3 : F < 14 ? 4 : F < 16 ? 5 : F < 18 ? 6 : F < 20 ? 7 : 8;
+}
+
+struct BsState {           // lane-private exact state in shared memory, element b at [b * 32]
+    uint32_t *hi, *lo, *out, *tap;
+};
+
+template <int B>
+__device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
+                                         uint32_t *stage /* [64][32] */, uint32_t *scratch /* [64] */, int lane)
+{
+    uint32_t R[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) R[i] = 0;
+    const int total = nb + 31;
+    for (int t = 0; t < total; t++) {
+        if ((t & 31) == 0) {
+            // stage the next 32 bundles: lane j transposes bundle t+j (low words, then high words)
+            __syncwarp();
+            const int bj = t + lane;
+            if (bj < nb) {
+                const uint64_t *kp = keys + (size_t)bj * 32;   // only 8-byte aligned (a strand's key region starts anywhere)
+                uint32_t w[32];
+#pragma unroll
+                for (int c = 0; c < 32; c++) w[c] = (uint32_t)kp[c];
+                transpose32(w);
+#pragma unroll
+                for (int pbit = 0; pbit < 32; pbit++) stage[pbit * 32 + lane] = w[31 - pbit];
+#pragma unroll
+                for (int c = 0; c < 32; c++) w[c] = (uint32_t)(kp[c] >> 32);
+                transpose32(w);
+#pragma unroll
+                for (int pbit = 0; pbit < 32; pbit++) stage[(32 + pbit) * 32 + lane] = w[31 - pbit];
+            }
+            __syncwarp();
+        }
+        // inject: lane 31 picks up bundle t, then everything rotates one lane up (lane 0 <- lane 31)
+        if (lane == 31 && t < nb) {
+#pragma unroll
+            for (int i = 0; i < 64; i++) R[i] = stage[i * 32 + (t & 31)];
+        }
+#pragma unroll
+        for (int i = 0; i < 64; i++) R[i] = __shfl_sync(kFull, R[i], (lane + 31) & 31);
+        const int bi = t - lane;                       // bundle this lane now holds
+        const bool valid = bi >= 0 && bi < nb;
+#pragma unroll 1
+        for (int b = 0; b < B; b++) {
+            bs_step(R);
+            // candidates: chains whose sign-biased value has its top tap_bits all zero
+            const uint32_t tap = st.tap[b * 32];
+            const uint32_t o1 = ~R[63] | R[62] | R[61] | R[60];
+            const uint32_t o2 = o1 | R[59] | R[58] | R[57] | R[56];
+            const uint32_t o3 = o2 | R[55] | R[54];
+            const uint32_t o4 = o3 | R[53] | R[52];
+            const uint32_t o5 = o4 | R[51] | R[50];
+            const uint32_t o6 = o5 | R[49] | R[48];
+            const uint32_t o7 = o6 | R[47] | R[46];
+            const uint32_t o8 = o7 | R[45] | R[44];
+            const uint32_t lo4 = (tap & 2) ? ((tap & 1) ? o3 : o2) : ((tap & 1) ? o1 : 0u);
+            const uint32_t hi4 = (tap & 2) ? ((tap & 1) ? o7 : o6) : ((tap & 1) ? o5 : o4);
+            const uint32_t o = (tap & 8) ? o8 : ((tap & 4) ? hi4 : lo4);
+            uint32_t cand = valid ? ~o : 0u;
+            unsigned evm = __ballot_sync(kFull, cand != 0);
+            while (evm) {                               // warp-uniform
+                const int L = __ffs(evm) - 1;
+                evm &= evm - 1;
+                if (lane == L) {
+#pragma unroll
+                    for (int i = 0; i < 64; i++) scratch[i] = R[i];
+                }
+                __syncwarp();
+                const uint32_t p_lo = scratch[lane], p_hi = scratch[32 + lane];
+                uint32_t cm = __shfl_sync(kFull, cand, L);
+                const int bL = __shfl_sync(kFull, bi, L);
+                while (cm) {                            // warp-uniform
+                    const int sb = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    const uint32_t xh = __ballot_sync(kFull, (p_hi >> sb) & 1u);
+                    const uint32_t xl = __ballot_sync(kFull, (p_lo >> sb) & 1u);
+                    if (lane == L) {
+                        const int32_t bh = (int32_t)st.hi[b * 32];
+                        if ((int32_t)xh < bh || ((int32_t)xh == bh && xl < st.lo[b * 32])) {   // MinHashSketch.java:144
+                            const uint64_t key = keys[(size_t)bL * 32 + (31 - sb)];
+                            st.hi[b * 32] = xh; st.lo[b * 32] = xl;
+                            st.out[b * 32] = ((lane * B + b) & 1) ? (uint32_t)(key >> 32) : (uint32_t)key;   // :146-149
+                            st.tap[b * 32] = bs_tap_of(xh);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(128)
+k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
+             int32_t *__restrict__ minhash, uint32_t *queue)
+{
+    // per warp: state [4][B][32] | stage [64][32] | scratch [64] ; static: key ring + weights for the scalar pipeline
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    __shared__ uint64_t s_kbuf[4][64];
+    __shared__ uint32_t s_wbuf[4][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int kPerWarp = 4 * B * 32 + 64 * 32 + 64;
+    uint32_t *wbase = s_dyn + (size_t)wib * kPerWarp;
+    BsState st;
+    st.hi = wbase + lane; st.lo = wbase + B * 32 + lane; st.out = wbase + 2 * B * 32 + lane; st.tap = wbase + 3 * B * 32 + lane;
+    uint32_t *stage = wbase + 4 * B * 32, *scratch = stage + 64 * 32;
+    for (;;) {
+        int s = 0;
+        if (lane == 0) s = (int)atomicAdd(queue, 1u);
+        s = __shfl_sync(kFull, s, 0);
+        if (s >= n_strands) break;
+        const StrandDesc d = desc[s];
+        const int nk = (int)d.len - k + 1;
+        const uint64_t *keys = sc.keys + d.koff;
+        const int nl = sc.nlight[s], nh = sc.nheavy[s];
+        const int nb = nl > kBsScalarKeys ? (nl - kBsScalarKeys) / 32 : 0;   // full bundles, taken from the end
+        const int n_sc = nl - 32 * nb;
+        LaneMins<B> m;
+#pragma unroll
+        for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
+        minhash_pipeline<B, false>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        if (nh > 0)
+            minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
+        int32_t *row = minhash + (size_t)d.row * H;
+        if (nb > 0) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                st.hi[b * 32] = (uint32_t)m.hi[b]; st.lo[b * 32] = m.lo[b]; st.out[b * 32] = (uint32_t)m.out[b];
+                st.tap[b * 32] = bs_tap_of((uint32_t)m.hi[b]);
+            }
+            __syncwarp();
+            bs_phase<B>(st, keys + n_sc, nb, stage, scratch, lane);
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < B; b++) { int word = lane * B + b; if (word < H) row[word] = (int32_t)st.out[b * 32]; }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int b = 0; b < B; b++) { int word = lane * B + b; if (word < H) row[word] = m.out[b]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1c: ordered bottom-S sketch
 // ---------------------------------------------------------------------------------------------
 // One CTA per strand.  Hash every ordered k-mer, radix-select the S smallest 64-bit keys
@@ -531,12 +737,34 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
     return cudaSuccess;
 }
 
+static int k1b_variant()
+{
+    // MHAPB_K1B=scalar selects the scalar systolic kernel (kept for A/B measurements); default bit-sliced
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("MHAPB_K1B"); v = (e && e[0] == 's') ? 0 : 1; }
+    return v;
+}
+
 template <int B>
 static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
                                     const SketchScratch &sc, int32_t *d_minhash)
 {
+    cudaError_t e;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash<B>, 256, 0);
+    if (k1b_variant() == 1 && B <= 32) {
+        const size_t smem = (size_t)4 * (4 * B * 32 + 64 * 32 + 64) * 4;
+        e = cudaFuncSetAttribute(k_minhash_bs<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash_bs<B>, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        int grid = sm_count() * per_sm;
+        int need = (n_strands + 3) / 4;
+        if (grid > need) grid = need;
+        k_minhash_bs<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2);
+        return cudaGetLastError();
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash<B>, 256, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     int grid = sm_count() * per_sm;
