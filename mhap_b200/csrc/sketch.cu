@@ -349,6 +349,7 @@ k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, Sket
 // the scalar pipeline first; so do strands too short to fill bundles.
 constexpr int kBsScalarKeys = 1024;
 constexpr int kBsTaps = 9;
+constexpr int kBsStage = 16;   // bundles transposed per staging round (lanes 0..15 transpose one each)
 __device__ __constant__ int c_bs_tap_bits[kBsTaps] = {0, 4, 8, 10, 12, 14, 16, 18, 20};
 
 __device__ __forceinline__ void bs_step(uint32_t (&R)[64])
@@ -394,37 +395,37 @@ struct BsState {           // lane-private exact state in shared memory, element
 
 template <int B>
 __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
-                                         uint32_t *stage /* [64][32] */, uint32_t *scratch /* [64] */, int lane)
+                                         uint32_t *stage /* [64][kBsStage] */, uint32_t *scratch /* [64] */, int lane)
 {
     uint32_t R[64];
 #pragma unroll
     for (int i = 0; i < 64; i++) R[i] = 0;
     const int total = nb + 31;
     for (int t = 0; t < total; t++) {
-        if ((t & 31) == 0) {
-            // stage the next 32 bundles: lane j transposes bundle t+j (low words, then high words)
+        if ((t & (kBsStage - 1)) == 0) {
+            // stage the next kBsStage bundles: lane j transposes bundle t+j (low words, then high words)
             __syncwarp();
             const int bj = t + lane;
-            if (bj < nb) {
+            if (lane < kBsStage && bj < nb) {
                 const uint64_t *kp = keys + (size_t)bj * 32;   // only 8-byte aligned (a strand's key region starts anywhere)
                 uint32_t w[32];
 #pragma unroll
                 for (int c = 0; c < 32; c++) w[c] = (uint32_t)kp[c];
                 transpose32(w);
 #pragma unroll
-                for (int pbit = 0; pbit < 32; pbit++) stage[pbit * 32 + lane] = w[31 - pbit];
+                for (int pbit = 0; pbit < 32; pbit++) stage[pbit * kBsStage + lane] = w[31 - pbit];
 #pragma unroll
                 for (int c = 0; c < 32; c++) w[c] = (uint32_t)(kp[c] >> 32);
                 transpose32(w);
 #pragma unroll
-                for (int pbit = 0; pbit < 32; pbit++) stage[(32 + pbit) * 32 + lane] = w[31 - pbit];
+                for (int pbit = 0; pbit < 32; pbit++) stage[(32 + pbit) * kBsStage + lane] = w[31 - pbit];
             }
             __syncwarp();
         }
         // inject: lane 31 picks up bundle t, then everything rotates one lane up (lane 0 <- lane 31)
         if (lane == 31 && t < nb) {
 #pragma unroll
-            for (int i = 0; i < 64; i++) R[i] = stage[i * 32 + (t & 31)];
+            for (int i = 0; i < 64; i++) R[i] = stage[i * kBsStage + (t & (kBsStage - 1))];
         }
 #pragma unroll
         for (int i = 0; i < 64; i++) R[i] = __shfl_sync(kFull, R[i], (lane + 31) & 31);
@@ -451,14 +452,31 @@ __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__re
             while (evm) {                               // warp-uniform
                 const int L = __ffs(evm) - 1;
                 evm &= evm - 1;
+                // high planes first: about half of the flagged chains are rejected on the high word alone
                 if (lane == L) {
 #pragma unroll
-                    for (int i = 0; i < 64; i++) scratch[i] = R[i];
+                    for (int i = 0; i < 32; i++) scratch[32 + i] = R[32 + i];
                 }
                 __syncwarp();
-                const uint32_t p_lo = scratch[lane], p_hi = scratch[32 + lane];
+                const uint32_t p_hi = scratch[32 + lane];
                 uint32_t cm = __shfl_sync(kFull, cand, L);
                 const int bL = __shfl_sync(kFull, bi, L);
+                const int32_t bhL = __shfl_sync(kFull, (int32_t)st.hi[b * 32], L);
+                uint32_t keep = 0;                      // flagged chains that pass the high-word test
+                for (uint32_t c2 = cm; c2; c2 &= c2 - 1) {
+                    const int sb = __ffs(c2) - 1;
+                    const uint32_t xh = __ballot_sync(kFull, (p_hi >> sb) & 1u);
+                    if ((int32_t)xh <= bhL) keep |= 1u << sb;
+                }
+                cm = keep;
+                if (cm) {
+                    if (lane == L) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) scratch[i] = R[i];
+                    }
+                    __syncwarp();
+                }
+                const uint32_t p_lo = cm ? scratch[lane] : 0u;
                 while (cm) {                            // warp-uniform
                     const int sb = __ffs(cm) - 1;
                     cm &= cm - 1;
@@ -481,7 +499,7 @@ __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__re
 }
 
 template <int B>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, B <= 16 ? 4 : 2)
 k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
              int32_t *__restrict__ minhash, uint32_t *queue)
 {
@@ -490,11 +508,11 @@ k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, S
     __shared__ uint64_t s_kbuf[4][64];
     __shared__ uint32_t s_wbuf[4][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    constexpr int kPerWarp = 4 * B * 32 + 64 * 32 + 64;
+    constexpr int kPerWarp = 4 * B * 32 + 64 * kBsStage + 64;
     uint32_t *wbase = s_dyn + (size_t)wib * kPerWarp;
     BsState st;
     st.hi = wbase + lane; st.lo = wbase + B * 32 + lane; st.out = wbase + 2 * B * 32 + lane; st.tap = wbase + 3 * B * 32 + lane;
-    uint32_t *stage = wbase + 4 * B * 32, *scratch = stage + 64 * 32;
+    uint32_t *stage = wbase + 4 * B * 32, *scratch = stage + 64 * kBsStage;
     for (;;) {
         int s = 0;
         if (lane == 0) s = (int)atomicAdd(queue, 1u);
@@ -752,7 +770,7 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
     cudaError_t e;
     int per_sm = 0;
     if (k1b_variant() == 1 && B <= 32) {
-        const size_t smem = (size_t)4 * (4 * B * 32 + 64 * 32 + 64) * 4;
+        const size_t smem = (size_t)4 * (4 * B * 32 + 64 * kBsStage + 64) * 4;
         e = cudaFuncSetAttribute(k_minhash_bs<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash_bs<B>, 128, smem);
