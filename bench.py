@@ -37,6 +37,11 @@ ALG_BYTES_PER_BASE = {  # (ceil(L/4)+8 in + strands*(4H + 8*min(
 }
 
 
+# DRAM traffic of one K1b launch per read, from the ncu --set full capture of k_minhash_bs<16>
+# (12 000 reads x 10 kbp: dram__bytes_read 1.9306 GB + dram__bytes_write 0.0513 GB): the 8-byte k-mer keys it streams
+K1B_DRAM_BYTES_PER_READ = (1.930553e9 + 51.26912e6) / 12000.0
+
+
 def alg_bytes_per_read(L, H, S, ok=12, strands=2):
     return (L + 3) // 4 + 8 + strands * (4 * H + 8 * min(S, L - ok + 1))
 
@@ -284,7 +289,8 @@ def _main(args, real_stdout):
             dist.destroy_process_group()
         return
 
-    peak_steps = eng.xorshift_peak()
+    peak_scalar, peak_bs = eng.xorshift_peaks()
+    peak_steps = max(peak_scalar, peak_bs)
     total_bases = total_reads * L
     k_ms = {k: v / args.steps for k, v in acc.items()}
     stats = last["stats"]
@@ -311,11 +317,13 @@ def _main(args, real_stdout):
         "counters": stats, "n_store": last["n_store"],
         "roofline": {"kernel": "k_minhash (K1b)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "traffic": None, "alg_bytes_per_launch": alg_bytes / n_chunks, "launches_per_step": n_chunks,
+                     "traffic": K1B_DRAM_BYTES_PER_READ * n_local / n_chunks, "traffic_source": "ncu --set full, profiles/r1g_k_minhash_bs_ncu_summary.txt: dram read+write of one launch / its reads",
+                     "alg_bytes_per_launch": alg_bytes / n_chunks, "launches_per_step": n_chunks,
                      "note": "K1b is integer-issue bound, not HBM bound (about 2*H XORShift-min steps per base against ~3 bytes); see int_issue"},
         "int_issue": {"kernel": "k_minhash (K1b)", "achieved_steps_per_s": steps_per_s, "peak_steps_per_s": peak_steps,
                       "frac": steps_per_s / peak_steps, "unit": "XORShift steps/s",
-                      "peak_source": "mhapb_xorshift_peak: the bare recurrence, 4 chains/thread, measured in this run"},
+                      "peak_scalar_steps_per_s": peak_scalar, "peak_bitsliced_steps_per_s": peak_bs,
+                      "peak_source": "mhapb_xorshift_peaks: the bare recurrence alone (no compare, no memory), scalar and bit-sliced forms, measured in this run; peak = the faster"},
         "e2e": {"value": total_bases / e2e_s / 1e9, "unit": "Gbases/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(n_local * L + 8 * (n_local + 1)) * world,
                 "d2h_bytes_per_step": int(stats["fully_compared"] * (12 + 32) + 24),

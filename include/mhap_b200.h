@@ -111,9 +111,11 @@ int  mhapb_get_timing(mhapb_ctx *ctx, mhapb_timing *out);
  * in pinned memory. */
 int  mhapb_host_alloc(size_t bytes, void **out);
 void mhapb_host_free(void *p);
-/* Micro-benchmark for the roofline denominator of K1b: independent 64-bit XORShift chains
- * (x ^= x<<21; x ^= x>>>35; x ^= x<<4) at full occupancy, no compare, no memory.  Returns the
- * sustained steps/s of this GPU at its current clocks. */
+/* Micro-benchmarks for the roofline denominator of K1b: the bare XORShift recurrence
+ * (x ^= x<<21; x ^= x>>>35; x ^= x<<4) at full occupancy, no compare, no memory, in its two
+ * formulations -- scalar (one chain per thread op) and bit-sliced (32 chains per thread, 132 XORs per
+ * step).  Sustained chain steps/s of this GPU at its current clocks; _peak returns the larger. */
+int  mhapb_xorshift_peaks(mhapb_ctx *ctx, double *scalar_steps_per_s, double *bitsliced_steps_per_s);
 int  mhapb_xorshift_peak(mhapb_ctx *ctx, double *steps_per_s);
 
 /* ---- K1: sketching ------------------------------------------------------------------------

@@ -179,7 +179,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         CU(ctx, ctx->nlight.ensure((size_t)n * 4));
         CU(ctx, ctx->nheavy.ensure((size_t)n * 4));
         CU(ctx, ctx->counters.ensure(64));
-        const size_t cap_short = (size_t)max_k_short + max_k_short / 2 + 8, cap_long = (size_t)max_k_long + max_k_long / 2 + 8;
+        const size_t cap_short = dedup_table_slots((uint32_t)max_k_short), cap_long = dedup_table_slots((uint32_t)max_k_long);
         const int g1 = hash_dedup_grid() * 2, g2 = ordered_grid();
         size_t dup_need = first_long > 0 ? (size_t)g1 * cap_short * 4 : 0;
         if (n_long) dup_need = std::max(dup_need, (size_t)g1 * cap_long * 4);
@@ -356,8 +356,14 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
         st.fully_compared = (int64_t)nc;
         if (nc > 0) {
             const uint32_t entries = 2u * (uint32_t)std::max(q.ord_stride, s.ord_stride) + 2u;
-            uint64_t budget = 4ull << 30;
+            // one thread per candidate in flight: the merge is a chain of dependent loads, so residency is what
+            // hides its latency; scratch is 12 bytes * entries per thread (worst case 2*S matches)
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            uint64_t budget = std::min<uint64_t>(16ull << 30, (uint64_t)(free_b + ctx->fscratch.cap) / 2);
+            budget = std::max<uint64_t>(budget, 256ull << 20);
             uint64_t max_threads = std::max<uint64_t>(128, budget / (12ull * entries));
+            max_threads = std::min<uint64_t>(max_threads, 148ull * 2048);
             uint32_t nth = (uint32_t)std::min<uint64_t>(nc, max_threads);
             nth = (nth + 127u) & ~127u;
             CU(ctx, ctx->fscratch.ensure((size_t)3 * entries * nth * 4));
@@ -534,16 +540,14 @@ int mhapb_host_alloc(size_t bytes, void **out)
 }
 void mhapb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-int mhapb_xorshift_peak(mhapb_ctx *ctx, double *steps_per_s)
+static int xorshift_peak_one(mhapb_ctx *ctx, int bitsliced, double *steps_per_s)
 {
-    if (!ctx || !steps_per_s) return MHAPB_EINVAL;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, ctx->eq.ensure(16));
     float best = 1e30f; double steps = 0;
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(ctx->ev[0], ctx->stream);
-        CU(ctx, launch_xorshift_peak(ctx->stream, ctx->eq.as<unsigned long long>(), &steps));
+        if (bitsliced) CU(ctx, launch_xorshift_peak_bs(ctx->stream, ctx->eq.as<unsigned long long>(), &steps));
+        else CU(ctx, launch_xorshift_peak(ctx->stream, ctx->eq.as<unsigned long long>(), &steps));
         cudaEventRecord(ctx->ev[1], ctx->stream);
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
@@ -551,6 +555,25 @@ int mhapb_xorshift_peak(mhapb_ctx *ctx, double *steps_per_s)
     }
     *steps_per_s = steps / (best * 1e-3);
     return MHAPB_OK;
+}
+
+int mhapb_xorshift_peaks(mhapb_ctx *ctx, double *scalar_steps_per_s, double *bitsliced_steps_per_s)
+{
+    if (!ctx || !scalar_steps_per_s || !bitsliced_steps_per_s) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = xorshift_peak_one(ctx, 0, scalar_steps_per_s);
+    if (rc) return rc;
+    return xorshift_peak_one(ctx, 1, bitsliced_steps_per_s);
+}
+
+int mhapb_xorshift_peak(mhapb_ctx *ctx, double *steps_per_s)
+{
+    double a = 0, b = 0;
+    if (!steps_per_s) return MHAPB_EINVAL;
+    int rc = mhapb_xorshift_peaks(ctx, &a, &b);
+    *steps_per_s = a > b ? a : b;
+    return rc;
 }
 
 int mhapb_sketch_device(mhapb_ctx *ctx, const mhapb_sketch_params *p, const void *d_bases, const uint64_t *h_offsets,

@@ -21,6 +21,9 @@ struct StrandDesc {
 constexpr int kShortMaxKmers = 16384;
 constexpr int kMaxNumHashes = 2048;
 constexpr int kMaxOrderedSketch = 4096;
+// slots of the K1a de-duplication table for a strand of nk k-mers: load factor <= 0.8, so two 10 kbp CTAs
+// (table + staged characters) fit one SM's shared memory and overlap each other's barrier phases
+__host__ __device__ inline uint32_t dedup_table_slots(uint32_t nk) { return nk + nk / 4 + 8; }
 
 struct SketchScratch {
     uint64_t *keys;      // [cap_kmers] distinct k-mer hashes per strand: light from the front, heavy from the back
@@ -46,6 +49,7 @@ cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const Strand
                            const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int *launches);
 // independent XORShift chains at full occupancy: the integer-issue ceiling K1b is measured against
 cudaError_t launch_xorshift_peak(cudaStream_t st, unsigned long long *d_sink, double *steps);
+cudaError_t launch_xorshift_peak_bs(cudaStream_t st, unsigned long long *d_sink, double *steps);
 int hash_dedup_grid();
 int ordered_grid();
 size_t dedup_table_cap_short();   // slots per block in SketchScratch.dupcnt

@@ -98,8 +98,8 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
         if (s >= s_end) break;
         const StrandDesc d = desc[s];
         const int nk = (int)d.len - k + 1;
-        // table sized for this strand: load factor <= 2/3
-        uint32_t C = (uint32_t)nk + (uint32_t)nk / 2 + 8;
+        // table sized for this strand (load factor <= 0.8)
+        uint32_t C = dedup_table_slots((uint32_t)nk);
         if (C > table_cap) C = table_cap;
 
         for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) table[i] = kEmptyKey;
@@ -501,7 +501,7 @@ __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__re
 template <int B>
 __global__ void __launch_bounds__(128, B <= 16 ? 4 : 2)
 k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
-             int32_t *__restrict__ minhash, uint32_t *queue)
+             int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys)
 {
     // per warp: state [4][B][32] | stage [64][32] | scratch [64] ; static: key ring + weights for the scalar pipeline
     extern __shared__ __align__(16) uint32_t s_dyn[];
@@ -522,7 +522,7 @@ k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, S
         const int nk = (int)d.len - k + 1;
         const uint64_t *keys = sc.keys + d.koff;
         const int nl = sc.nlight[s], nh = sc.nheavy[s];
-        const int nb = nl > kBsScalarKeys ? (nl - kBsScalarKeys) / 32 : 0;   // full bundles, taken from the end
+        const int nb = nl > scalar_keys ? (nl - scalar_keys) / 32 : 0;   // full bundles, taken from the end
         const int n_sc = nl - 32 * nb;
         LaneMins<B> m;
 #pragma unroll
@@ -708,7 +708,31 @@ static int sm_count()
     return g_sm_count;
 }
 
-static constexpr uint32_t kShortTableCap = kShortMaxKmers + kShortMaxKmers / 2 + 8;   // 24584 slots = 192 KB
+static constexpr uint32_t kShortTableCap = kShortMaxKmers + kShortMaxKmers / 4 + 8;   // 20488 slots = 160 KB
+
+// the bit-sliced recurrence alone: 132 XORs per 32 chain steps, nothing else
+__global__ void __launch_bounds__(256) k_xorshift_peak_bs(unsigned long long *sink)
+{
+    uint32_t R[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) R[i] = 0x9E3779B9u * (blockIdx.x * 256u + threadIdx.x + 1u) + i * 0x85EBCA6Bu;
+    for (int it = 0; it < kPeakIters / 2; it++) {
+#pragma unroll 1
+        for (int u = 0; u < 8; u++) bs_step(R);
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 64; i++) acc ^= R[i];
+    if (acc == 0x1234567u) atomicAdd(sink, 1ull);
+}
+
+cudaError_t launch_xorshift_peak_bs(cudaStream_t st, unsigned long long *d_sink, double *steps)
+{
+    const int grid = sm_count() * 2;
+    k_xorshift_peak_bs<<<grid, 256, 0, st>>>(d_sink);
+    *steps = (double)grid * 256.0 * (kPeakIters / 2) * 8.0 * 32.0;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_xorshift_peak(cudaStream_t st, unsigned long long *d_sink, double *steps)
 {
@@ -730,14 +754,14 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
 {
     cudaError_t e;
     if (first_long > 0) {
-        uint32_t cap = (uint32_t)max_kmers_short + (uint32_t)max_kmers_short / 2 + 8;
+        uint32_t cap = dedup_table_slots((uint32_t)max_kmers_short);
         uint32_t chars_cap = (uint32_t)align16((size_t)max_kmers_short + k);
         size_t smem = (size_t)cap * 8 + (size_t)((cap + 31) / 32) * 4 + chars_cap;
         auto kern = k == 16 ? k_hash_dedup<false, 16> : k_hash_dedup<false, 0>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int grid = hash_dedup_grid();
-        if (smem <= 100 * 1024) grid *= 2;
+        if (smem <= 113 * 1024) grid *= 2;
         if (grid > first_long) grid = first_long;
         // dupcnt rows are strided by the *launch's* cap so both variants can share the buffer
         kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, 0, first_long, k, unweighted, cap, chars_cap, sc, sc.counters + 0);
@@ -745,7 +769,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (first_long < n_strands) {
-        uint32_t cap = (uint32_t)max_kmers_long + (uint32_t)max_kmers_long / 2 + 8;
+        uint32_t cap = dedup_table_slots((uint32_t)max_kmers_long);
         int grid = hash_dedup_grid();
         if (grid > n_strands - first_long) grid = n_strands - first_long;
         k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, first_long, n_strands, k, unweighted, cap, 0, sc, sc.counters + 1);
@@ -779,7 +803,9 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         int grid = sm_count() * per_sm;
         int need = (n_strands + 3) / 4;
         if (grid > need) grid = need;
-        k_minhash_bs<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2);
+        static int scalar_keys = -1;
+        if (scalar_keys < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys < 0) scalar_keys = 0; }
+        k_minhash_bs<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys);
         return cudaGetLastError();
     }
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash<B>, 256, 0);

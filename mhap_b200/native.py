@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libmhap_b200.so")
 # every symbol include/mhap_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "mhapb_version", "mhapb_create", "mhapb_destroy", "mhapb_last_error", "mhapb_free", "mhapb_get_timing",
-    "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
+    "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_xorshift_peaks", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
     "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads",
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
@@ -92,6 +92,7 @@ def load():
     L.mhapb_host_alloc.argtypes = [C.c_size_t, P(vp)]
     L.mhapb_host_free.argtypes = [vp]; L.mhapb_host_free.restype = None
     L.mhapb_xorshift_peak.argtypes = [vp, P(C.c_double)]
+    L.mhapb_xorshift_peaks.argtypes = [vp, P(C.c_double), P(C.c_double)]
     L.mhapb_sketch.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
     L.mhapb_sketch_device.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
     L.mhapb_sketch_to_dat.argtypes = [vp, P(SketchParams), vp, vp, vp, u32, C.c_int, P(vp), P(u64), P(u32)]
@@ -161,6 +162,11 @@ class Engine:
         t = Timing()
         self._ck(self.L.mhapb_get_timing(self.h, C.byref(t)))
         return {f: getattr(t, f) for f, _ in Timing._fields_}
+
+    def xorshift_peaks(self) -> tuple[float, float]:
+        a = C.c_double(); b = C.c_double()
+        self._ck(self.L.mhapb_xorshift_peaks(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def xorshift_peak(self) -> float:
         v = C.c_double()
