@@ -77,7 +77,7 @@ struct mhapb_ctx {
     DevBuf bases, desc, keys, wts, nlight, nheavy, dupcnt, gtable, ohash, counters;
     DevBuf out_minhash, out_ord, out_ordn;
     // search scratch
-    DevBuf qlist, cand, ovl, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
+    DevBuf qlist, cand, ovl, ovf_list, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
     Store store;
     cudaEvent_t ev[8]{};
 };
@@ -355,28 +355,43 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
         const uint64_t nc = cnt[0];
         st.fully_compared = (int64_t)nc;
         if (nc > 0) {
-            const uint32_t entries = 2u * (uint32_t)std::max(q.ord_stride, s.ord_stride) + 2u;
-            // one thread per candidate in flight: the merge is a chain of dependent loads, so residency is what
-            // hides its latency; scratch is 12 bytes * entries per thread (worst case 2*S matches)
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            uint64_t budget = std::min<uint64_t>(16ull << 30, (uint64_t)(free_b + ctx->fscratch.cap) / 2);
-            budget = std::max<uint64_t>(budget, 256ull << 20);
-            uint64_t max_threads = std::max<uint64_t>(128, budget / (12ull * entries));
-            max_threads = std::min<uint64_t>(max_threads, 148ull * 2048);
-            uint32_t nth = (uint32_t)std::min<uint64_t>(nc, max_threads);
-            nth = (nth + 127u) & ~127u;
-            CU(ctx, ctx->fscratch.ensure((size_t)3 * entries * nth * 4));
             CU(ctx, ctx->ovl.ensure((size_t)nc * sizeof(OverlapOut)));
+            CU(ctx, ctx->ovf_list.ensure((size_t)nc * 4 + 16));
+            CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 64, ctx->stream));
             FilterArgs f{};
             f.cand = ctx->cand.as<Candidate>(); f.n_cand = nc;
             f.q_ord = q.d_ord; f.q_ord_n = q.d_ordn; f.q_lenk = q.d_lenk; f.q_stride = q.ord_stride;
             f.t_ord = s.ord.as<int32_t>(); f.t_ord_n = s.ord_n.as<int32_t>(); f.t_lenk = s.lenk.as<int32_t>(); f.t_stride = s.ord_stride;
             f.max_shift = sp->max_shift;
-            f.scratch = ctx->fscratch.as<int32_t>(); f.scratch_entries = entries; f.n_threads = nth;
             f.out = ctx->ovl.as<OverlapOut>();
+            f.ovf_list = ctx->ovf_list.as<uint32_t>(); f.ovf_count = ctx->scounters.as<unsigned long long>();
             cudaEventRecord(ctx->ev[2], ctx->stream);
-            CU(ctx, launch_filter(ctx->stream, f, &launches));
+            // warp-per-candidate kernel first; what it cannot hold in shared memory (more than 1024 match records,
+            // or sketches too large to stage) goes to the thread-per-candidate kernel
+            unsigned long long n_ovf = 0;
+            cudaError_t fe = launch_filter_warp(ctx->stream, f, &launches);
+            if (fe == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); n_ovf = nc; f.sel = nullptr; }
+            else {
+                CU(ctx, fe);
+                CU(ctx, cudaMemcpyAsync(&n_ovf, ctx->scounters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(ctx, cudaStreamSynchronize(ctx->stream));
+                f.sel = ctx->ovf_list.as<uint32_t>();
+            }
+            if (n_ovf > 0) {
+                const uint32_t entries = 2u * (uint32_t)std::max(q.ord_stride, s.ord_stride) + 2u;
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                uint64_t budget = std::min<uint64_t>(8ull << 30, (uint64_t)(free_b + ctx->fscratch.cap) / 2);
+                budget = std::max<uint64_t>(budget, 256ull << 20);
+                uint64_t max_threads = std::max<uint64_t>(128, budget / (12ull * entries));
+                max_threads = std::min<uint64_t>(max_threads, 148ull * 1024);
+                uint32_t nth = (uint32_t)std::min<uint64_t>(n_ovf, max_threads);
+                nth = (nth + 127u) & ~127u;
+                CU(ctx, ctx->fscratch.ensure((size_t)3 * entries * nth * 4));
+                f.n_sel = n_ovf;
+                f.scratch = ctx->fscratch.as<int32_t>(); f.scratch_entries = entries; f.n_threads = nth;
+                CU(ctx, launch_filter(ctx->stream, f, &launches));
+            }
             cudaEventRecord(ctx->ev[3], ctx->stream);
             std::vector<Candidate> hc(nc);
             std::vector<OverlapOut> ho(nc);
@@ -512,7 +527,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->bases, &ctx->desc, &ctx->keys, &ctx->wts, &ctx->nlight, &ctx->nheavy, &ctx->dupcnt, &ctx->gtable, &ctx->ohash,
-                      &ctx->counters, &ctx->out_minhash, &ctx->out_ord, &ctx->out_ordn, &ctx->qlist, &ctx->cand, &ctx->ovl, &ctx->fscratch,
+                      &ctx->counters, &ctx->out_minhash, &ctx->out_ord, &ctx->out_ordn, &ctx->qlist, &ctx->cand, &ctx->ovl, &ctx->ovf_list, &ctx->fscratch,
                       &ctx->scounters, &ctx->tmp_start, &ctx->block_sums, &ctx->q_minhash, &ctx->q_ord, &ctx->q_ordn, &ctx->q_lenk, &ctx->q_len,
                       &ctx->q_id, &ctx->eq, &ctx->store.minhash, &ctx->store.ord, &ctx->store.ord_n, &ctx->store.lenk, &ctx->store.len,
                       &ctx->store.id, &ctx->store.slots, &ctx->store.postings};

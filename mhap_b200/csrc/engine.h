@@ -89,10 +89,16 @@ struct FilterArgs {
     const int32_t *q_ord; const int32_t *q_ord_n; const int32_t *q_lenk; int q_stride;   // [nq][stride][2]
     const int32_t *t_ord; const int32_t *t_ord_n; const int32_t *t_lenk; int t_stride;
     double max_shift;
-    int32_t *scratch; uint32_t scratch_entries; uint32_t n_threads;   // 3 arrays [entries][n_threads]
+    int32_t *scratch; uint32_t scratch_entries; uint32_t n_threads;   // 3 arrays [entries][n_threads] (thread-per-candidate kernel)
     OverlapOut *out;
+    const uint32_t *sel; uint64_t n_sel;          // thread-per-candidate kernel: only candidates sel[0..n_sel) (NULL: all)
+    uint32_t *ovf_list; unsigned long long *ovf_count;   // warp kernel: candidates it hands to the thread-per-candidate kernel
 };
+// thread-per-candidate kernel (any sketch size, any match count; serial merge per thread)
 cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches);
+// warp-per-candidate kernel (sketches staged in shared memory, hash-range-partitioned merge); returns
+// cudaErrorInvalidConfiguration if the sketches do not fit shared memory (caller uses launch_filter)
+cudaError_t launch_filter_warp(cudaStream_t st, FilterArgs a, int *launches);
 
 cudaError_t launch_equal_count(cudaStream_t st, const int32_t *a, const int32_t *b, int H, int32_t *d_out, int *launches);
 

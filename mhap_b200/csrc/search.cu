@@ -10,6 +10,8 @@
 // HBM / L2 random-access bound integer work; no tensor cores.
 #include "engine.h"
 
+#include <cstdlib>
+
 namespace mhapb {
 
 static constexpr uint64_t kEmptySlot = ~0ull;
@@ -421,7 +423,9 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs a)
     sc.p2 = a.scratch + (size_t)a.scratch_entries * a.n_threads + tid;
     sc.tmp = a.scratch + 2 * (size_t)a.scratch_entries * a.n_threads + tid;
 
-    for (uint64_t ci = tid; ci < a.n_cand; ci += a.n_threads) {
+    const uint64_t n_work = a.sel ? a.n_sel : a.n_cand;
+    for (uint64_t wi = tid; wi < n_work; wi += a.n_threads) {
+        const uint64_t ci = a.sel ? a.sel[wi] : wi;
         const Candidate c = a.cand[ci];
         const int2 *A = reinterpret_cast<const int2 *>(a.q_ord) + (size_t)c.q * a.q_stride;
         const int2 *Bs = reinterpret_cast<const int2 *>(a.t_ord) + (size_t)c.t * a.t_stride;
@@ -491,6 +495,319 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs a)
         }
         a.out[ci] = o;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2c, warp-per-candidate (the default)
+// ---------------------------------------------------------------------------------------------
+// Both ordered sketches are staged in shared memory with coalesced loads.  recordMatchingKmers is a
+// merge-join on hash whose state never carries across hash values (elements of either sketch with a
+// hash the other side lacks are skipped without a record; the first/last handling of duplicate hashes
+// stays inside one hash value), so the hash axis is cut into 32 ranges at values taken from sketch A and
+// every lane runs the reference's sequential loop on its range; concatenating the lanes' records in lane
+// order reproduces the reference's record order.  Median = exact k-th smallest by an 8-bit radix select;
+// optimizeShifts = ordered compaction of pos1 runs; the bottom-k merge is partitioned the same way, the
+// lane in which the union count crosses k finishing it sequentially.
+constexpr int kFwRecCap = 512;      // match records kept in shared memory; more => thread-per-candidate kernel
+
+struct FwWindow { int32_t v1lo, v1hi, v2lo, v2hi, median, absmax; };
+
+__device__ __forceinline__ FwWindow fw_window(int32_t median, int32_t absmax, int32_t len1, int32_t len2)
+{
+    FwWindow w;
+    w.median = median; w.absmax = absmax;
+    w.v1lo = max(0, -median - absmax); w.v2lo = max(0, median - absmax);            // MatchData.valid1Lower/valid2Lower
+    w.v1hi = min(len1, len2 - median + absmax); w.v2hi = min(len2, len1 + median + absmax);
+    return w;
+}
+
+// Shared-memory layout of a staged sketch: element i lives at i + (i >> 5).  Lanes walk ranges that start
+// about n/32 elements apart (48 for S=1536, i.e. 96 words = a multiple of the 32 banks), so without the
+// skew every lane's loads would hit the same bank.
+struct FwSketch {
+    const int2 *p; bool skew;
+    __device__ __forceinline__ int2 operator[](int i) const { return skew ? p[i + (i >> 5)] : __ldg(p + i); }
+};
+
+__device__ __forceinline__ int fw_lower_bound(const FwSketch s, int n, int32_t h)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (s[mid].x < h) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// the reference loop (sketch/BottomOverlapSketch.java:428-515) on A[i1..e1) x B[i2..e2); out==nullptr counts only
+__device__ int fw_merge_range(const FwSketch A, int i1, int e1, const FwSketch Bs, int i2, int e2, const FwWindow &w, int2 *out)
+{
+    int count = 0;
+    if (i1 >= e1 || i2 >= e2) return 0;
+    int2 a = A[i1], b = Bs[i2];
+    for (;;) {
+        if (a.x < b.x || a.y < w.v1lo || a.y >= w.v1hi) { if (++i1 >= e1) break; a = A[i1]; }
+        else if (b.x < a.x || b.y < w.v2lo || b.y >= w.v2hi) { if (++i2 >= e2) break; b = Bs[i2]; }
+        else {
+            const int32_t diff = (b.y - a.y) - w.median;
+            if (diff > w.absmax) { if (++i1 >= e1) break; a = A[i1]; }
+            else if (diff < -w.absmax) { if (++i2 >= e2) break; b = Bs[i2]; }
+            else {
+                if (out) out[count] = make_int2(a.y, b.y);
+                count++;
+                int i1last = i1, i2last = i2;
+                int32_t p1 = a.y, p2 = b.y;
+                for (int t = i1 + 1; t < e1; t++) { const int2 x = A[t]; if (!(x.x == a.x && x.y >= w.v1lo && x.y < w.v1hi)) break; i1last = t; p1 = x.y; }
+                for (int t = i2 + 1; t < e2; t++) { const int2 x = Bs[t]; if (!(x.x == b.x && x.y >= w.v2lo && x.y < w.v2hi)) break; i2last = t; p2 = x.y; }
+                if (i1 != i1last || i2 != i2last) {
+                    if (out) out[count] = make_int2(p1, p2);
+                    count++;
+                    i1 = i1last + 1; i2 = i2last + 1;
+                } else { i1++; i2++; }
+                if (i1 >= e1 || i2 >= e2) break;
+                a = A[i1]; b = Bs[i2];
+            }
+        }
+    }
+    return count;
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total)
+{
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+    *total = __shfl_sync(kFull, incl, 31);
+    return incl - v;
+}
+
+// exact k-th smallest (0-based) of the shifts rec[i].y - rec[i].x, i < n: MSB-first 8-bit radix select
+__device__ int32_t fw_select_shift(const int2 *rec, int n, int k, uint32_t *hist, int lane)
+{
+    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k + 1;
+    for (int pass = 3; pass >= 0; pass--) {
+        const int shift = pass * 8;
+        for (int i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t key = (uint32_t)(rec[i].y - rec[i].x) ^ 0x80000000u;
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { c[q] = hist[lane * 8 + q]; sum += c[q]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+        const uint32_t excl = incl - sum;
+        uint32_t digit = 0, before = 0;
+        const bool mine = excl < remaining && remaining <= incl;
+        if (mine) {
+            uint32_t run = excl;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { if (run < remaining && remaining <= run + c[q]) { digit = lane * 8 + q; before = run; } run += c[q]; }
+        }
+        const unsigned who = __ballot_sync(kFull, mine);
+        const int src = __ffs(who) - 1;
+        digit = __shfl_sync(kFull, digit, src); before = __shfl_sync(kFull, before, src);
+        prefix |= digit << shift; mask |= 0xffu << shift; remaining -= before;
+        __syncwarp();
+    }
+    return (int32_t)(prefix ^ 0x80000000u);
+}
+
+// MatchData.performUpdate (sketch/BottomOverlapSketch.java:191-215) for count > 0
+__device__ __forceinline__ void fw_update(const int2 *rec, int count, int32_t len1, int32_t len2, double max_shift, uint32_t *hist, int lane,
+                                          int32_t *median, int32_t *absmax)
+{
+    const int32_t med = fw_select_shift(rec, count, count / 2, hist, lane);
+    const int32_t left = max(0, -med), right = min(len1, len2 - med), overlap = max(10, right - left);
+    *median = med;
+    *absmax = min(max(len1, len2), (int32_t)((double)overlap * max_shift));
+}
+
+template <bool STAGE>
+__global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a, int capA, int capB)
+{
+    extern __shared__ __align__(16) uint8_t fw_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t per_warp = (size_t)(capA + capB + kFwRecCap) * 8 + 256 * 4;
+    uint8_t *base = fw_smem + (size_t)wib * per_warp;
+    int2 *sA = reinterpret_cast<int2 *>(base);
+    int2 *sB = sA + capA;
+    int2 *rec = sB + capB;
+    // STAGE: both sketches copied to shared memory (skewed layout).  !STAGE: every lane walks its own contiguous
+    // range straight from L2/L1 (capA = capB = 0), which leaves room for 4x more resident warps.
+    uint32_t *hist = reinterpret_cast<uint32_t *>(rec + kFwRecCap);
+    const uint64_t warp_id = (uint64_t)blockIdx.x * wpb + wib, n_warps = (uint64_t)gridDim.x * wpb;
+
+    for (uint64_t ci = warp_id; ci < a.n_cand; ci += n_warps) {
+        const Candidate c = a.cand[ci];
+        const int nA = a.q_ord_n[c.q], nB = a.t_ord_n[c.t];
+        const int32_t len1 = a.q_lenk[c.q], len2 = a.t_lenk[c.t];
+        const int2 *gA = reinterpret_cast<const int2 *>(a.q_ord) + (size_t)c.q * a.q_stride;
+        const int2 *gB = reinterpret_cast<const int2 *>(a.t_ord) + (size_t)c.t * a.t_stride;
+        __syncwarp();
+        if (STAGE) {
+            for (int i = lane; i < nA; i += 32) sA[i + (i >> 5)] = __ldg(&gA[i]);
+            for (int i = lane; i < nB; i += 32) sB[i + (i >> 5)] = __ldg(&gB[i]);
+        }
+        __syncwarp();
+        const FwSketch A{STAGE ? sA : gA, STAGE}, Bs{STAGE ? sB : gB, STAGE};
+        OverlapOut o; o.a1 = o.a2 = o.b1 = o.b2 = o.valid = o.inter = o.kmin = 0; o.empty = 1;
+        bool overflow = false;
+
+        // hash ranges: lane l takes hashes in [h_l, h_{l+1}), h_l = A[l*nA/32].x (h_0 = -inf)
+        int a0 = 0, b0 = 0;
+        if (lane > 0 && nA > 0) {
+            const int32_t h = A[(int)(((long long)lane * nA) >> 5)].x;
+            a0 = fw_lower_bound(A, nA, h); b0 = fw_lower_bound(Bs, nB, h);
+        }
+        int a1 = __shfl_down_sync(kFull, a0, 1), b1 = __shfl_down_sync(kFull, b0, 1);
+        if (lane == 31) { a1 = nA; b1 = nB; }
+        if (a1 < a0) a1 = a0;   // equal splitters give empty ranges
+        if (b1 < b0) b1 = b0;
+
+        int count = 0;
+        int32_t median = 0, absmax = max(len1, len2) + 1;     // empty MatchData (BottomOverlapSketch.java:207-211)
+        for (int pass = 0; pass < 2 && !overflow; pass++) {
+            const FwWindow w = fw_window(median, absmax, len1, len2);
+            const int mine = fw_merge_range(A, a0, a1, Bs, b0, b1, w, nullptr);
+            int total;
+            const int off = warp_excl_scan(mine, lane, &total);
+            count = total;
+            if (total == 0) break;
+            if (total > kFwRecCap) { overflow = true; break; }
+            fw_merge_range(A, a0, a1, Bs, b0, b1, w, rec + off);
+            __syncwarp();
+            fw_update(rec, count, len1, len2, a.max_shift, hist, lane, &median, &absmax);
+        }
+        if (overflow) {
+            if (lane == 0) { unsigned long long p = atomicAdd(a.ovf_count, 1ull); a.ovf_list[p] = (uint32_t)ci; }
+            continue;
+        }
+        if (count > 0) {
+            // optimizeShifts (:156-189): within a run of equal pos1 keep the entry closest to the median (first on ties)
+            int out_n = 0;
+            for (int base_i = 0; base_i < count; base_i += 32) {
+                const int i = base_i + lane;
+                bool start = false;
+                int2 best = make_int2(0, 0);
+                if (i < count) {
+                    const int2 r = rec[i];
+                    start = i == 0 || rec[i - 1].x != r.x;
+                    if (start) {
+                        best = r;
+                        int32_t bd = abs((r.y - r.x) - median);
+                        for (int j = i + 1; j < count; j++) {
+                            const int2 x = rec[j];
+                            if (x.x != r.x) break;
+                            const int32_t d = abs((x.y - x.x) - median);
+                            if (bd > d) { bd = d; best = x; }
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(kFull, start);
+                __syncwarp();
+                if (start) rec[out_n + __popc(m & ((1u << lane) - 1))] = best;
+                out_n += __popc(m);
+                __syncwarp();
+            }
+            count = out_n;
+            fw_update(rec, count, len1, len2, a.max_shift, hist, lane, &median, &absmax);
+            // computeEdges (:90-137)
+            int32_t le1 = INT32_MAX, le2 = INT32_MAX, re1 = INT32_MIN, re2 = INT32_MIN, valid = 0;
+            for (int i = lane; i < count; i += 32) {
+                const int2 r = rec[i];
+                if (abs((r.y - r.x) - median) > absmax) continue;
+                le1 = min(le1, r.x); le2 = min(le2, r.y); re1 = max(re1, r.x); re2 = max(re2, r.y); valid++;
+            }
+#pragma unroll
+            for (int ofs = 16; ofs > 0; ofs >>= 1) {
+                le1 = min(le1, __shfl_xor_sync(kFull, le1, ofs)); le2 = min(le2, __shfl_xor_sync(kFull, le2, ofs));
+                re1 = max(re1, __shfl_xor_sync(kFull, re1, ofs)); re2 = max(re2, __shfl_xor_sync(kFull, re2, ofs));
+                valid += __shfl_xor_sync(kFull, valid, ofs);
+            }
+            if (valid >= 3) {
+                const int32_t n = valid;
+                o.a1 = max(0, java_round_div(n * le1 - re1, n - 1));
+                o.a2 = min(len1, java_round_div(n * re1 - le1, n - 1));
+                o.b1 = max(0, java_round_div(n * le2 - re2, n - 1));
+                o.b2 = min(len2, java_round_div(n * re2 - le2, n - 1));
+                o.valid = valid;
+                // computeKBottomSketchJaccard (:304-364) over the entries whose position is inside [a1,a2] / [b1,b2]
+                int sa = 0, sbn = 0;
+                for (int i = a0; i < a1; i++) { const int32_t p = A[i].y; sa += (p >= o.a1 && p <= o.a2); }
+                for (int j = b0; j < b1; j++) { const int32_t p = Bs[j].y; sbn += (p >= o.b1 && p <= o.b2); }
+                // this lane's share of the two-pointer walk run to exhaustion: equal pairings and union steps
+                int inter_l = 0;
+                {
+                    int i = a0, j = b0;
+                    for (;;) {
+                        while (i < a1 && !(A[i].y >= o.a1 && A[i].y <= o.a2)) i++;
+                        while (j < b1 && !(Bs[j].y >= o.b1 && Bs[j].y <= o.b2)) j++;
+                        if (i >= a1 || j >= b1) break;
+                        const int32_t ha = A[i].x, hb = Bs[j].x;
+                        if (ha < hb) i++; else if (ha > hb) j++; else { inter_l++; i++; j++; }
+                    }
+                }
+                const int union_l = sa + sbn - inter_l;
+                int s1, s2, utot;
+                warp_excl_scan(sa, lane, &s1);
+                warp_excl_scan(sbn, lane, &s2);
+                const int ubefore = warp_excl_scan(union_l, lane, &utot);
+                const int k = min(s1, s2);
+                int inter = 0;
+                if (k > 0) {
+                    if (ubefore + union_l <= k) inter = inter_l;                 // whole range inside the first k union steps
+                    else if (ubefore < k) {                                       // the range in which the walk stops
+                        int i = a0, j = b0, uni = ubefore;
+                        while (uni < k) {
+                            while (i < a1 && !(A[i].y >= o.a1 && A[i].y <= o.a2)) i++;
+                            while (j < b1 && !(Bs[j].y >= o.b1 && Bs[j].y <= o.b2)) j++;
+                            if (i >= a1) { j++; }                                 // only B entries left in range: each is one union step
+                            else if (j >= b1) { i++; }
+                            else {
+                                const int32_t ha = A[i].x, hb = Bs[j].x;
+                                if (ha < hb) i++; else if (ha > hb) j++; else { inter++; i++; j++; }
+                            }
+                            uni++;
+                        }
+                    }
+#pragma unroll
+                    for (int ofs = 16; ofs > 0; ofs >>= 1) inter += __shfl_xor_sync(kFull, inter, ofs);
+                }
+                o.inter = inter; o.kmin = k; o.empty = 0;
+            }
+        }
+        if (lane == 0) a.out[ci] = o;
+    }
+}
+
+cudaError_t launch_filter_warp(cudaStream_t st, FilterArgs a, int *launches)
+{
+    if (a.n_cand == 0) return cudaSuccess;
+    static int stage = -1;
+    if (stage < 0) { const char *e = getenv("MHAPB_K2C_STAGE"); stage = (e && e[0] == '1') ? 1 : 0; }
+    int capA = 0, capB = 0;
+    if (stage) { capA = (a.q_stride + a.q_stride / 32 + 4) & ~3; capB = (a.t_stride + a.t_stride / 32 + 4) & ~3; }
+    const size_t per_warp = (size_t)(capA + capB + kFwRecCap) * 8 + 256 * 4;
+    if (per_warp > 100 * 1024) return cudaErrorInvalidConfiguration;
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 110 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    auto kern = stage ? k_filter_warp<true> : k_filter_warp<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)sms * per_sm;
+    const uint64_t need = (a.n_cand + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, wpb * 32, smem, st>>>(a, capA, capB);
+    (*launches)++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches)

@@ -166,3 +166,21 @@ def test_query_range_partitions_self_search():
         for k in s:
             tot[k] += s[k]
     assert_same_hits(np.concatenate(parts), full_h, tot, full_s)
+
+
+def test_identical_reads_overflow_the_shared_match_buffer():
+    # exact copies share all 1536 ordered k-mers: more match records than the warp kernel keeps in shared
+    # memory, so these pairs are resolved by the thread-per-candidate kernel (same exact result)
+    rng = random.Random(21)
+    base = [rand_seq(rng, 4000) for _ in range(6)]
+    reads = []
+    for b in base:
+        reads += [b, b, orc.rc(b).decode(), b[:3500] + rand_seq(rng, 500)]
+    hits, stats, _ = _run_self(reads, H=128, S=1536, m=3, thr=0.5)
+    assert max(int(h["valid_count"]) for h in hits) > 1024   # > kFwRecCap
+
+
+def test_large_ordered_sketch_4096():
+    bases, offs = synth.dataset(60, 9000, seed=31, err=0.05)
+    reads = [bytes(bases[int(offs[i]):int(offs[i + 1])]) for i in range(60)]
+    _run_self(reads, H=64, S=4096, m=2, thr=0.6)
