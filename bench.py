@@ -5,8 +5,8 @@ Contract (one JSON line on stdout from rank 0):
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N ...            # the reference path on the host cores
 Under torchrun (N>1) one rank per GPU; reads are sharded (weak scaling: every rank holds one
-BASELINE configs[1] worth of reads), sketch blocks are all-gathered over NCCL, every rank indexes
-everything and queries its own shard.
+BASELINE configs[1] worth of reads), every rank sketches and indexes its own shard, sketch blocks are
+all-gathered over NCCL, and every rank queries its index with the forward sketches of all ranks.
 
 A "step" is one full self-overlap pass over the synthetic read set: K1 sketch (both strands) ->
 K2a index -> K2b probe/count -> K2c ordered filter -> hits on the host.
@@ -161,7 +161,7 @@ def workload_config(args):
             "reads_per_gpu": args.reads, "read_len": args.read_len, "k": 16, "num_hashes": args.num_hashes,
             "ordered_kmer_size": 12, "ordered_sketch_size": args.ordered_sketch_size, "error_rate": args.err,
             "coverage": 20, "seed": args.seed, "l2_policy": "inputs larger than L2 (1 GB of reads per GPU per step, 2.9 GB of sketches)",
-            "parallelism": f"reads sharded over {args.gpus} GPU(s); all-gather of sketch blocks; replicated index"}
+            "parallelism": f"reads sharded over {args.gpus} GPU(s); each rank indexes its shard; all-gather of sketch blocks; every rank queries its index with all forward sketches"}
 
 
 def main():
@@ -225,21 +225,23 @@ def _main(args, real_stdout):
 
     def device_step(resident=True, record=False):
         t_a = time.perf_counter()
-        block = be.sketch_shard(bases, offsets, ids, resident=resident)
+        block = be.store_shard(bases, offsets, ids, resident=resident)      # K1 + K2a on the local shard
         tm = eng.timing()
         gblock, counts = all_gather_blocks(block, dist if world > 1 else None)
         torch.cuda.synchronize()
         t_b = time.perf_counter()
-        be.load_store(gblock)
-        tm_i = eng.timing()
-        first = sum(counts[:rank])
-        hits, stats = be.search_range(first, counts[rank])
+        hits, stats = be.search_all(gblock)                                  # K2b + K2c: all forward sketches vs local index
         tm_s = eng.timing()
+        if world > 1:
+            keys = [k for k in sorted(stats) if k != "sequences_searched"]
+            t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            stats = dict(stats, **{k: int(v) for k, v in zip(keys, t.tolist())})
         t_c = time.perf_counter()
         if record:
-            for k in ("sketch_total_ms", "hash_dedup_ms", "minhash_ms", "ordered_ms"):
+            for k in ("sketch_total_ms", "hash_dedup_ms", "minhash_ms", "ordered_ms", "index_ms"):
                 acc[k] += tm[k]
-            acc["index_ms"] += tm_i["index_ms"]; acc["probe_ms"] += tm_s["probe_ms"]; acc["filter_ms"] += tm_s["filter_ms"]
+            acc["probe_ms"] += tm_s["probe_ms"]; acc["filter_ms"] += tm_s["filter_ms"]
             launches["n"] += tm_s["kernel_launches"]
             last.update(stats=stats, n_hits=len(hits), steps=tm["xorshift_steps"], wall_sketch=t_b - t_a, wall_search=t_c - t_b,
                         n_store=gblock.n)
@@ -313,7 +315,7 @@ def _main(args, real_stdout):
         "sketch_gbases_per_s": n_local * L / (k_ms["sketch_total_ms"] * 1e-3) / 1e9 * world,
         "overlaps_per_s": stats["fully_compared"] / ((k_ms["probe_ms"] + k_ms["filter_ms"]) * 1e-3) if k_ms["probe_ms"] + k_ms["filter_ms"] > 0 else None,
         "kernel_ms_per_step_rank0": k_ms,
-        "wall_ms_rank0": {"sketch_and_gather": last["wall_sketch"] * 1e3, "index_and_search": last["wall_search"] * 1e3},
+        "wall_ms_rank0": {"sketch_index_gather": last["wall_sketch"] * 1e3, "search": last["wall_search"] * 1e3},
         "counters": stats, "n_store": last["n_store"],
         "roofline": {"kernel": "k_minhash (K1b)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",

@@ -200,7 +200,7 @@ int64_t mhapb_store_size(mhapb_ctx *ctx);                          /* AbstractMa
 int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, int32_t *seq_len,
                     int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n);
 /* Device views of the store's blocks (for the all-gather): minhash [n][H] and ord [n][S][2]. */
-int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, int64_t *n,
+int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, void **d_ord_n, int64_t *n,
                             int32_t *num_hashes, int32_t *ord_stride);
 int mhapb_index_build(mhapb_ctx *ctx);
 
@@ -224,6 +224,15 @@ int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, c
                                 const int32_t *ord_hash_pos, const int32_t *ord_n,
                                 int32_t ord_stride, uint32_t n, mhapb_hit **out, uint64_t *n_out,
                                 mhapb_stats *stats);
+/* Query sketches whose blocks are already on this GPU (minhash [n][H], ord [n][ord_stride][2], ord_n [n]
+ * device pointers; the small columns on the host) against the store.  to_self=1 applies
+ * findMatches(sketch, toSelf=true)'s id rules (MinHashSearch.java:200,215-225) -- the multi-GPU self
+ * overlap: every rank stores its own shard and queries it with the all-gathered sketch blocks of every
+ * rank, so hit lists are disjoint by target and the index is built once across the job, not per rank. */
+int mhapb_search_sketches_device(mhapb_ctx *ctx, const mhapb_search_params *sp, int to_self, const int64_t *ids,
+                                 const uint8_t *is_fwd, const int32_t *seq_len, const int32_t *seq_len_kmers,
+                                 const void *d_minhash, const void *d_ord, const void *d_ord_n, int32_t ord_stride,
+                                 uint32_t n, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
 /* impl/MatchResult.java:46-65,98-113: one output line, no newline; returns its length. */
 int mhapb_format_match(const mhapb_hit *h, char *buf, size_t buflen);
 

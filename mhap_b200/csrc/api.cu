@@ -894,13 +894,14 @@ int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, i
     return MHAPB_OK;
 }
 
-int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, int64_t *n, int32_t *num_hashes, int32_t *ord_stride)
+int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, void **d_ord_n, int64_t *n, int32_t *num_hashes, int32_t *ord_stride)
 {
     if (!ctx) return MHAPB_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     Store &s = ctx->store;
     if (d_minhash) *d_minhash = s.minhash.p;
     if (d_ord) *d_ord = s.ord.p;
+    if (d_ord_n) *d_ord_n = s.ord_n.p;
     if (n) *n = s.n;
     if (num_hashes) *num_hashes = s.p.num_hashes;
     if (ord_stride) *ord_stride = s.ord_stride;
@@ -938,7 +939,7 @@ int mhapb_search_self(mhapb_ctx *ctx, const mhapb_search_params *sp, mhapb_hit *
 static int search_query_sketches_locked(mhapb_ctx *ctx, const mhapb_search_params *sp, const int64_t *ids, const uint8_t *is_fwd,
                                         const int32_t *seq_len, const int32_t *seq_len_kmers, const int32_t *d_minhash,
                                         const int32_t *d_ord, const int32_t *d_ordn, int32_t ord_stride, uint32_t n,
-                                        mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+                                        mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats, int to_self = 0)
 {
     CU(ctx, ctx->q_lenk.ensure((size_t)n * 4 + 4));
     CU(ctx, ctx->q_len.ensure((size_t)n * 4 + 4));
@@ -953,7 +954,7 @@ static int search_query_sketches_locked(mhapb_ctx *ctx, const mhapb_search_param
     q.d_lenk = ctx->q_lenk.as<int32_t>(); q.d_len = ctx->q_len.as<int32_t>(); q.d_id = ctx->q_id.as<int64_t>(); q.ord_stride = ord_stride;
     q.h_id = ids; q.h_fwd = is_fwd; q.h_len = seq_len;
     for (uint32_t i = 0; i < n; i++) if (is_fwd[i]) q.list.push_back(i);   // AbstractMatchSearch.java:225 dequeue(true)
-    return search_core(ctx, sp, q, 0, out, n_out, stats);
+    return search_core(ctx, sp, q, to_self, out, n_out, stats);
 }
 
 int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, const int64_t *ids, const uint8_t *is_fwd,
@@ -978,6 +979,20 @@ int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, c
     }
     return search_query_sketches_locked(ctx, sp, ids, is_fwd, seq_len, seq_len_kmers, ctx->q_minhash.as<int32_t>(),
                                         ctx->q_ord.as<int32_t>(), ctx->q_ordn.as<int32_t>(), ord_stride, n, out, n_out, stats);
+}
+
+int mhapb_search_sketches_device(mhapb_ctx *ctx, const mhapb_search_params *sp, int to_self, const int64_t *ids, const uint8_t *is_fwd,
+                                 const int32_t *seq_len, const int32_t *seq_len_kmers, const void *d_minhash, const void *d_ord,
+                                 const void *d_ord_n, int32_t ord_stride, uint32_t n, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+{
+    if (!ctx || !sp) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (!s.configured || s.n == 0) return fail(ctx, MHAPB_ESTATE, "search on an empty store");
+    if (n && (!ids || !is_fwd || !seq_len || !seq_len_kmers || !d_minhash || !d_ord || !d_ord_n)) return fail(ctx, MHAPB_EINVAL, "null query column");
+    return search_query_sketches_locked(ctx, sp, ids, is_fwd, seq_len, seq_len_kmers, (const int32_t *)d_minhash, (const int32_t *)d_ord,
+                                        (const int32_t *)d_ord_n, ord_stride, n, out, n_out, stats, to_self ? 1 : 0);
 }
 
 int mhapb_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, const char *bases, const uint64_t *offsets,

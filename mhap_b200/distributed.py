@@ -1,14 +1,16 @@
-"""Multi-GPU self-overlap: shard reads, sketch locally, all-gather sketch blocks, query own shard.
+"""Multi-GPU self-overlap: shard reads, sketch + index locally, all-gather sketch blocks, query everything.
 
 The reference is one JVM ("Distributed communication backend: none"); its users
-partition by hand.  Here the path shards naturally with ONE exchange step (SURVEY.md 8e):
+partition by hand.  Here the path shards naturally with ONE exchange step:
 
-  1. reads are partitioned contiguously over the ranks; K1 runs per shard, no communication;
+  1. reads are partitioned contiguously over the ranks; K1 runs per shard, no communication; every
+     rank stores and indexes ONLY its own shard (K2a is 1/N of the job per rank, not replicated);
   2. the per-shard sketch blocks (min-hashes [n][H], ordered sketches [n][S][2] and the small
      per-sketch columns) are all-gathered -- NCCL over NVLink on GPUs, gloo in the CPU tests;
-  3. every rank builds the full inverted index (replicated) and queries only its own shard's
-     forward sketches, so the hit lists are disjoint by fromId and the order-independent counters
-     (MhapMain.java:572-590) are summed with an all-reduce.
+  3. every rank queries its local index with the forward sketches of ALL ranks under the self-search
+     id rules (MinHashSearch.java:200,215-225), so each overlap (query, target) is found exactly once,
+     on the rank that owns the target; the order-independent counters (MhapMain.java:572-590) are
+     additive over target shards and are summed with an all-reduce.
 
 The compute is behind a small backend protocol so the host logic can be exercised with gloo on CPU
 (tests use an oracle-backed stand-in; the product backend is GpuBackend over the C ABI).
@@ -83,24 +85,28 @@ def all_gather_blocks(block: SketchBlock, dist=None) -> tuple[SketchBlock, list[
 def sharded_self_overlap(backend, bases, offsets, ids, dist=None):
     """One rank's part of a sharded self-overlap.  `bases/offsets/ids` are THIS rank's reads.
 
-    Returns (hits of this rank's queries, job-wide stats dict, info dict)."""
-    block = backend.sketch_shard(bases, offsets, ids)
-    gblock, counts = all_gather_blocks(block, dist)
-    rank = dist.get_rank() if (dist is not None and dist.is_initialized()) else 0
-    backend.load_store(gblock)
-    first = sum(counts[:rank])
-    hits, stats = backend.search_range(first, counts[rank])
+    Returns (hits whose target lives on this rank, job-wide stats dict, info dict)."""
+    block = backend.store_shard(bases, offsets, ids)          # sketch + store + index the local shard
+    gblock, counts = all_gather_blocks(block, dist)           # the one exchange step
+    hits, stats = backend.search_all(gblock)                  # all forward sketches vs the local index
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-        keys = sorted(stats)
+        keys = [k for k in sorted(stats) if k != "sequences_searched"]
         t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device=gblock.ids.device)
         dist.all_reduce(t)
-        stats = {k: int(v) for k, v in zip(keys, t.tolist())}
-    return hits, stats, dict(counts=counts, first=first, n_store=gblock.n)
+        stats = dict(stats, **{k: int(v) for k, v in zip(keys, t.tolist())})   # every rank searched every query once
+    return hits, stats, dict(counts=counts, n_store=gblock.n)
+
+
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class GpuBackend:
-    """The product backend: K1/K2 through the C ABI on this rank's GPU, blocks in torch CUDA tensors
-    (torch is only the allocator and the NCCL plumbing here)."""
+    """The product backend: K1/K2 through the C ABI on this rank's GPU.  torch is only the view over
+    the store's device blocks and the NCCL plumbing."""
 
     def __init__(self, engine: native.Engine, params: native.SketchParams, search: native.SearchParams):
         self.e, self.p, self.sp = engine, params, search
@@ -108,44 +114,51 @@ class GpuBackend:
         self.d_bases = None
 
     def upload(self, bases: np.ndarray):
-        """H2D of this rank's read characters (pinned source recommended)."""
+        """H2D of this rank's read characters (pinned source recommended) for the device-resident entry point."""
         t = torch.from_numpy(bases)
         if self.d_bases is None or self.d_bases.numel() < t.numel():
             self.d_bases = torch.empty(max(1, t.numel()), dtype=torch.uint8, device=self.dev)
         self.d_bases[: t.numel()].copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
 
-    def sketch_shard(self, bases, offsets, ids, resident=False) -> SketchBlock:
-        if not resident:
-            self.upload(bases)
+    def store_shard(self, bases, offsets, ids, resident=False) -> SketchBlock:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = offsets.size - 1
-        H, S, k, ok = self.p.num_hashes, self.p.ordered_sketch_size, self.p.kmer_size, self.p.ordered_kmer_size
-        mh = torch.empty((2 * n, H), dtype=torch.int32, device=self.dev)
-        od = torch.empty((2 * n, S, 2), dtype=torch.int32, device=self.dev)
-        on = torch.empty(2 * n, dtype=torch.int32, device=self.dev)
-        torch.cuda.current_stream(self.dev).synchronize()
-        self.e.sketch_device(self.d_bases.data_ptr(), offsets, self.p, True, mh.data_ptr(), od.data_ptr(), on.data_ptr())
+        k, ok = self.p.kmer_size, self.p.ordered_kmer_size
+        ids = np.arange(1, n + 1, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        self.e.store_reset(self.p)
+        if resident:
+            # reads already in HBM (bench's device-resident leg): sketch into torch blocks, then hand them to the store
+            H, S = self.p.num_hashes, self.p.ordered_sketch_size
+            mh = torch.empty((2 * n, H), dtype=torch.int32, device=self.dev)
+            od = torch.empty((2 * n, S, 2), dtype=torch.int32, device=self.dev)
+            on = torch.empty(2 * n, dtype=torch.int32, device=self.dev)
+            torch.cuda.current_stream(self.dev).synchronize()
+            self.e.sketch_device(self.d_bases.data_ptr(), offsets, self.p, True, mh.data_ptr(), od.data_ptr(), on.data_ptr())
+        else:
+            self.e.store_add_reads(bases, offsets, ids)          # H2D + K1 straight into the store
         lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
         ok_read = (lens >= self.p.min_olap_length) & (lens - k + 1 >= 1) & (lens - ok + 1 >= 1)
-        ids = np.arange(1, n + 1, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
-        if not ok_read.all():
-            keep = torch.from_numpy(np.repeat(ok_read, 2)).to(self.dev)
-            mh, od, on = mh[keep].contiguous(), od[keep].contiguous(), on[keep].contiguous()
         v = np.nonzero(ok_read)[0]
-        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.dev)
-        return SketchBlock(ids=to(np.repeat(ids[v], 2), np.int64), is_fwd=to(np.tile([1, 0], v.size), np.uint8),
-                           seq_len=to(np.repeat(lens[v], 2), np.int32), seq_len_kmers=to(np.repeat(lens[v] - ok + 1, 2), np.int32),
-                           ord_n=on, minhash=mh, ord=od)
-
-    def load_store(self, g: SketchBlock):
-        self.e.store_reset(self.p)
-        torch.cuda.synchronize(self.dev)
-        self.e.store_add_sketches_device(g.ids.cpu().numpy(), g.is_fwd.cpu().numpy(), g.seq_len.cpu().numpy(),
-                                         g.seq_len_kmers.cpu().numpy(), g.minhash.data_ptr(), g.ord.data_ptr(), g.ord_n.cpu().numpy())
+        meta = dict(ids=np.repeat(ids[v], 2), is_fwd=np.tile(np.array([1, 0], np.uint8), v.size),
+                    seq_len=np.repeat(lens[v], 2).astype(np.int32), seq_len_kmers=np.repeat(lens[v] - ok + 1, 2).astype(np.int32))
+        if resident:
+            if not ok_read.all():
+                keep = torch.from_numpy(np.repeat(ok_read, 2)).to(self.dev)
+                mh, od, on = mh[keep].contiguous(), od[keep].contiguous(), on[keep].contiguous()
+            self.e.store_add_sketches_device(meta["ids"], meta["is_fwd"], meta["seq_len"], meta["seq_len_kmers"],
+                                             mh.data_ptr(), od.data_ptr(), on.cpu().numpy())
+        d_mh, d_od, d_on, ns, H, S = self.e.store_device_ptrs()
+        assert ns == 2 * v.size
         self.e.index_build()
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.dev)
+        view = lambda ptr, shape: torch.as_tensor(_DevArray(ptr, shape, "<i4"), device=self.dev) if ns else torch.empty(shape, dtype=torch.int32, device=self.dev)
+        return SketchBlock(ids=to(meta["ids"], np.int64), is_fwd=to(meta["is_fwd"], np.uint8), seq_len=to(meta["seq_len"], np.int32),
+                           seq_len_kmers=to(meta["seq_len_kmers"], np.int32), ord_n=view(d_on, (ns,)),
+                           minhash=view(d_mh, (ns, H)), ord=view(d_od, (ns, S, 2)))
 
-    def search_range(self, first: int, count: int):
-        sp = native.SearchParams(self.sp.num_min_matches, self.sp.min_store_length, self.sp.max_shift, self.sp.accept_score,
-                                 self.sp.keep_all, 0, first, count)
-        return self.e.search_self(sp)
+    def search_all(self, g: SketchBlock):
+        torch.cuda.synchronize(self.dev)
+        return self.e.search_sketches_device(self.sp, True, g.ids.cpu().numpy(), g.is_fwd.cpu().numpy(), g.seq_len.cpu().numpy(),
+                                             g.seq_len_kmers.cpu().numpy(), g.minhash.data_ptr(), g.ord.data_ptr(),
+                                             g.ord_n.data_ptr(), int(g.ord.shape[1]))

@@ -21,7 +21,7 @@ EXPORTS = [
     "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads",
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
-    "mhapb_search_query_sketches", "mhapb_format_match", "mhapb_minhash_equal_count",
+    "mhapb_search_query_sketches", "mhapb_search_sketches_device", "mhapb_format_match", "mhapb_minhash_equal_count",
 ]
 
 
@@ -105,11 +105,12 @@ def load():
     L.mhapb_store_add_sketches_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32]
     L.mhapb_store_size.argtypes = [vp]; L.mhapb_store_size.restype = i64
     L.mhapb_store_get.argtypes = [vp, i64, P(i64), P(i32), P(i32), P(i32), vp, vp, P(i32)]
-    L.mhapb_store_device_ptrs.argtypes = [vp, P(vp), P(vp), P(i64), P(i32), P(i32)]
+    L.mhapb_store_device_ptrs.argtypes = [vp, P(vp), P(vp), P(vp), P(i64), P(i32), P(i32)]
     L.mhapb_index_build.argtypes = [vp]
     L.mhapb_search_self.argtypes = [vp, P(SearchParams), P(vp), P(u64), P(Stats)]
     L.mhapb_search_query_reads.argtypes = [vp, P(SearchParams), vp, vp, vp, u32, P(vp), P(u64), P(Stats)]
     L.mhapb_search_query_sketches.argtypes = [vp, P(SearchParams), vp, vp, vp, vp, vp, vp, vp, i32, u32, P(vp), P(u64), P(Stats)]
+    L.mhapb_search_sketches_device.argtypes = [vp, P(SearchParams), C.c_int, vp, vp, vp, vp, vp, vp, vp, i32, u32, P(vp), P(u64), P(Stats)]
     L.mhapb_format_match.argtypes = [P(Hit), C.c_char_p, C.c_size_t]
     L.mhapb_minhash_equal_count.argtypes = [vp, i64, i64, P(i32)]
     _lib = L
@@ -247,9 +248,9 @@ class Engine:
         return dict(id=id_.value, is_fwd=bool(fwd.value), seq_len=sl.value, seq_len_kmers=slk.value, minhash=mh, ord=od[:on.value].copy())
 
     def store_device_ptrs(self):
-        a = C.c_void_p(); b = C.c_void_p(); n = C.c_int64(); H = C.c_int32(); S = C.c_int32()
-        self._ck(self.L.mhapb_store_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(n), C.byref(H), C.byref(S)))
-        return a.value, b.value, n.value, H.value, S.value
+        a = C.c_void_p(); b = C.c_void_p(); c = C.c_void_p(); n = C.c_int64(); H = C.c_int32(); S = C.c_int32()
+        self._ck(self.L.mhapb_store_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n), C.byref(H), C.byref(S)))
+        return a.value, b.value, c.value, n.value, H.value, S.value
 
     def index_build(self):
         self._ck(self.L.mhapb_index_build(self.h))
@@ -287,6 +288,15 @@ class Engine:
         self._ck(self.L.mhapb_search_query_sketches(self.h, C.byref(sp), _ptr(ids), _ptr(is_fwd), _ptr(seq_len), _ptr(slk),
                                                     _ptr(minhash), _ptr(ord_hp), _ptr(ord_n), ord_hp.shape[1], ids.size,
                                                     C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
+    def search_sketches_device(self, sp: SearchParams, to_self: bool, ids, is_fwd, seq_len, seq_len_kmers, d_minhash: int, d_ord: int,
+                               d_ord_n: int, ord_stride: int):
+        ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
+        seq_len = np.ascontiguousarray(seq_len, dtype=np.int32); slk = np.ascontiguousarray(seq_len_kmers, dtype=np.int32)
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        self._ck(self.L.mhapb_search_sketches_device(self.h, C.byref(sp), int(to_self), _ptr(ids), _ptr(is_fwd), _ptr(seq_len), _ptr(slk),
+                                                     d_minhash, d_ord, d_ord_n, ord_stride, ids.size, C.byref(out), C.byref(n), C.byref(st)))
         return self._collect(out, n, st)
 
     def minhash_equal_count(self, i: int, j: int) -> int:

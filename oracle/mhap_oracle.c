@@ -864,6 +864,14 @@ int mo_search_query(mo_store *s, const mo_store *q, const mo_search_params *sp, 
     return run_search(s, q->sk, q->n, 0, sp, threads, keep_all, out, n_out, stats);
 }
 
+/* Queries from another store under the self-search id rules (toSelf = true): the sharded multi-GPU job, where a
+ * rank's store holds only its shard and the queries are every rank's forward sketches. */
+int mo_search_query_self(mo_store *s, const mo_store *q, const mo_search_params *sp, int threads, int keep_all,
+                         mo_hit **out, int64_t *n_out, mo_stats *stats)
+{
+    return run_search(s, q->sk, q->n, 1, sp, threads, keep_all, out, n_out, stats);
+}
+
 void mo_free(void *p) { free(p); }
 
 /* MatchResult.java:46-65,98-113 */

@@ -128,6 +128,8 @@ int       mo_search_self_range(mo_store *s, int64_t first, int64_t count, const 
 /* findMatches(streamer) (AbstractMatchSearch.java:203-285): queries come from another store. */
 int       mo_search_query(mo_store *s, const mo_store *queries, const mo_search_params *sp, int threads,
                           int keep_all, mo_hit **out, int64_t *n_out, mo_stats *stats);
+int       mo_search_query_self(mo_store *s, const mo_store *queries, const mo_search_params *sp, int threads,
+                               int keep_all, mo_hit **out, int64_t *n_out, mo_stats *stats);
 void      mo_free(void *p);
 
 /* impl/MatchResult.java:46-65,98-113 : one output line (no newline); returns strlen. */

@@ -103,6 +103,7 @@ def lib():
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Stats)]
         L.mo_search_query.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SearchParams), C.c_int, C.c_int,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Stats)]
+        L.mo_search_query_self.argtypes = L.mo_search_query.argtypes
         L.mo_free.argtypes = [C.c_void_p]
         L.mo_free.restype = None
         L.mo_format_match.argtypes = [C.POINTER(Hit), C.c_char_p, C.c_size_t]
@@ -283,10 +284,10 @@ class Store:
         return self._collect(out, n, st)
 
     def search_query(self, queries: "Store", num_min_matches=3, min_store_length=0, max_shift=0.2, accept_score=0.78,
-                     threads=1, keep_all=False):
+                     threads=1, keep_all=False, to_self=False):
         sp = SearchParams(num_min_matches, min_store_length, max_shift, accept_score)
         out = C.c_void_p(); n = C.c_int64(); st = Stats()
-        lib().mo_search_query(self._h, queries._h, C.byref(sp), threads, int(keep_all), C.byref(out), C.byref(n), C.byref(st))
+        (lib().mo_search_query_self if to_self else lib().mo_search_query)(self._h, queries._h, C.byref(sp), threads, int(keep_all), C.byref(out), C.byref(n), C.byref(st))
         return self._collect(out, n, st)
 
 

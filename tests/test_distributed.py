@@ -17,12 +17,15 @@ H, S = 64, 200
 
 
 class OracleBackend:
+    """Oracle stand-in for GpuBackend: the local shard is stored and indexed, every rank's sketches query it."""
+
     def __init__(self):
         self.store = None
 
-    def sketch_shard(self, bases, offsets, ids):
+    def store_shard(self, bases, offsets, ids):
         st = orc.Store(num_hashes=H, ordered_size=S)
         st.add_reads(bases, offsets, ids=ids)
+        self.store = st
         rows = [st.get(i) for i in range(len(st))]
         n = len(rows)
         od = np.zeros((n, S, 2), np.int32)
@@ -35,14 +38,15 @@ class OracleBackend:
                            ord_n=t(np.array([r["ord"].shape[0] for r in rows], np.int32)),
                            minhash=t(np.stack([r["minhash"] for r in rows]) if n else np.zeros((0, H), np.int32)), ord=t(od))
 
-    def load_store(self, g):
-        self.store = orc.Store(num_hashes=H, ordered_size=S)
+    def search_all(self, g):
+        qs = orc.Store(num_hashes=H, ordered_size=S)
         for i in range(g.n):
-            self.store.add_sketch(int(g.ids[i]), bool(g.is_fwd[i]), int(g.seq_len[i]), g.minhash[i].numpy(), int(g.seq_len_kmers[i]),
-                                  g.ord[i, :int(g.ord_n[i])].numpy())
-
-    def search_range(self, first, count):
-        r = self.store.search_self_range(first, count, keep_all=True)
+            qs.add_sketch(int(g.ids[i]), bool(g.is_fwd[i]), int(g.seq_len[i]), g.minhash[i].numpy(), int(g.seq_len_kmers[i]),
+                          g.ord[i, :int(g.ord_n[i])].numpy())
+        if len(self.store) == 0:
+            return np.zeros(0, orc.HIT_DTYPE), dict(elements_processed=0, sequences_hit=0, fully_compared=0, matches_processed=0,
+                                                   sequences_searched=int(g.is_fwd.sum()))
+        r = self.store.search_query(qs, keep_all=True, to_self=True)
         return r.hits, r.stats
 
 
@@ -106,11 +110,11 @@ def test_sharded_self_overlap_equals_single_process(world):
     for rank, hits, stats, info in res:
         assert stats == ref.stats                      # all-reduced, job-wide counters on every rank
         assert info["n_store"] == len(st) and sum(info["counts"]) == len(st)
-    # query ranges are disjoint by fromId
+    # hit lists are disjoint by target (toId)
     owners = {}
     for rank, hits, _, _ in res:
         for k in hits:
-            assert owners.setdefault(k[0], rank) == rank
+            assert owners.setdefault(k[1], rank) == rank
 
 
 def test_shard_range_covers_everything():
