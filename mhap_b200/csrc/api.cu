@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -77,7 +78,7 @@ struct mhapb_ctx {
     DevBuf bases, desc, keys, wts, nlight, nheavy, dupcnt, gtable, ohash, counters;
     DevBuf out_minhash, out_ord, out_ordn;
     // search scratch
-    DevBuf qlist, cand, ovl, ovf_list, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
+    DevBuf qlist, cand, ovl, cand2, ovl2, ovf_list, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
     Store store;
     cudaEvent_t ev[8]{};
 };
@@ -324,7 +325,7 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
     const int64_t nq = (int64_t)q.list.size();
     mhapb_stats st{};
     st.sequences_searched = nq;
-    std::vector<mhapb_hit> hits;
+    mhapb_hit *hit_arr = nullptr; size_t n_hits = 0;   // malloc'd result, filled by the scoring threads
     int launches = 0;
     ctx->timing.probe_ms = ctx->timing.filter_ms = 0;
     if (nq > 0) {
@@ -393,47 +394,93 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
                 CU(ctx, launch_filter(ctx->stream, f, &launches));
             }
             cudaEventRecord(ctx->ev[3], ctx->stream);
-            std::vector<Candidate> hc(nc);
-            std::vector<OverlapOut> ho(nc);
-            CU(ctx, cudaMemcpyAsync(hc.data(), ctx->cand.p, nc * sizeof(Candidate), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaMemcpyAsync(ho.data(), ctx->ovl.p, nc * sizeof(OverlapOut), cudaMemcpyDeviceToHost, ctx->stream));
+            // Only pairs that can still reach the threshold travel to the host.  score >= accept  <=>  jaccard >= T/(2-T) with
+            // T = accept^ok (jaccardToIdentity is increasing); the device test uses that bound lowered by 1e-9 relative, the
+            // exact double-precision decision (MinHashSearch.java:229) is taken below on the survivors.
+            const int ok = s.p.ordered_kmer_size;
+            double jmin = 0.0;
+            if (sp->accept_score > 0.0) {
+                const double T = std::pow(sp->accept_score, (double)ok);
+                jmin = T < 2.0 ? (T / (2.0 - T)) * (1.0 - 1e-9) - 1e-12 : 2.0;
+                if (jmin < 0.0) jmin = 0.0;
+            }
+            const int keep_all = sp->keep_all || sp->accept_score <= 0.0;
+            CU(ctx, ctx->cand2.ensure(nc * sizeof(Candidate)));
+            CU(ctx, ctx->ovl2.ensure(nc * sizeof(OverlapOut)));
+            CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 64, ctx->stream));
+            CU(ctx, launch_compact_hits(ctx->stream, ctx->cand.as<Candidate>(), ctx->ovl.as<OverlapOut>(), nc, jmin, keep_all,
+                                        ctx->cand2.as<Candidate>(), ctx->ovl2.as<OverlapOut>(), ctx->scounters.as<unsigned long long>(), &launches));
+            unsigned long long nkeep = 0;
+            CU(ctx, cudaMemcpyAsync(&nkeep, ctx->scounters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
             CU(ctx, cudaStreamSynchronize(ctx->stream));
             cudaEventElapsedTime(&ctx->timing.filter_ms, ctx->ev[2], ctx->ev[3]);
-            const int ok = s.p.ordered_kmer_size;
-            hits.reserve(nc / 2 + 16);
-            for (uint64_t i = 0; i < nc; i++) {
-                const OverlapOut &o = ho[i];
-                double score = 0.0;   // OverlapInfo.EMPTY
-                if (!o.empty) {
-                    double jac = o.kmin ? (double)o.inter / (double)o.kmin : 0.0;
-                    score = jaccard_to_identity(jac, ok);
+            std::vector<Candidate> hc(nkeep);
+            std::vector<OverlapOut> ho(nkeep);
+            if (nkeep) {
+                CU(ctx, cudaMemcpyAsync(hc.data(), ctx->cand2.p, nkeep * sizeof(Candidate), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(ctx, cudaMemcpyAsync(ho.data(), ctx->ovl2.p, nkeep * sizeof(OverlapOut), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            // score + MatchResult fields, split over host threads (order of hits is unspecified, as in the reference)
+            const unsigned nthr = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), nkeep / 4096 + 1));
+            std::vector<std::vector<mhapb_hit>> part(nthr);
+            std::vector<int64_t> acc(nthr, 0);
+            auto work = [&](unsigned t) {
+                const uint64_t lo = nkeep * t / nthr, hi = nkeep * (t + 1) / nthr;
+                std::vector<mhapb_hit> &outv = part[t];
+                outv.reserve((size_t)(hi - lo));
+                for (uint64_t i = lo; i < hi; i++) {
+                    const OverlapOut &o = ho[i];
+                    double score = 0.0;   // OverlapInfo.EMPTY
+                    if (!o.empty) {
+                        double jac = o.kmin ? (double)o.inter / (double)o.kmin : 0.0;
+                        score = jaccard_to_identity(jac, ok);
+                    }
+                    const bool accept = score >= sp->accept_score;   // MinHashSearch.java:229
+                    if (accept) acc[t]++;
+                    if (!accept && !sp->keep_all) continue;
+                    mhapb_hit h{};
+                    const uint32_t qi = hc[i].q, ti = hc[i].t;
+                    h.from_id = q.h_id[qi]; h.to_id = s.h_id[ti];
+                    h.from_fwd = q.h_fwd[qi]; h.to_fwd = s.h_fwd[ti];
+                    h.hit_count = (int32_t)hc[i].count;
+                    h.a1 = o.a1; h.a2 = o.a2; h.b1 = o.b1; h.b2 = o.b2;
+                    h.valid_count = o.valid; h.intersect = o.inter; h.kmin = o.kmin;
+                    h.from_len = q.h_len[qi]; h.to_len = s.h_len[ti];
+                    h.score = score; h.accepted = accept ? 1 : 0;
+                    outv.push_back(h);
                 }
-                const bool accept = score >= sp->accept_score;   // MinHashSearch.java:229
-                if (accept) st.matches_processed++;
-                if (!accept && !sp->keep_all) continue;
-                mhapb_hit h{};
-                const uint32_t qi = hc[i].q, ti = hc[i].t;
-                h.from_id = q.h_id[qi]; h.to_id = s.h_id[ti];
-                h.from_fwd = q.h_fwd[qi]; h.to_fwd = s.h_fwd[ti];
-                h.hit_count = (int32_t)hc[i].count;
-                h.a1 = o.a1; h.a2 = o.a2; h.b1 = o.b1; h.b2 = o.b2;
-                h.valid_count = o.valid; h.intersect = o.inter; h.kmin = o.kmin;
-                h.from_len = q.h_len[qi]; h.to_len = s.h_len[ti];
-                h.score = score; h.accepted = accept ? 1 : 0;
-                hits.push_back(h);
+            };
+            if (nthr == 1) work(0);
+            else {
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nthr; t++) th.emplace_back(work, t);
+                for (auto &x : th) x.join();
+            }
+            size_t total = 0;
+            std::vector<size_t> offs(nthr, 0);
+            for (unsigned t = 0; t < nthr; t++) { offs[t] = total; total += part[t].size(); st.matches_processed += acc[t]; }
+            hit_arr = (mhapb_hit *)malloc(sizeof(mhapb_hit) * std::max<size_t>(1, total));
+            if (!hit_arr) return fail(ctx, MHAPB_ENOMEM, "malloc hits");
+            n_hits = total;
+            auto copy_part = [&](unsigned t) { if (!part[t].empty()) memcpy(hit_arr + offs[t], part[t].data(), sizeof(mhapb_hit) * part[t].size()); };
+            if (nthr == 1) copy_part(0);
+            else {
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < nthr; t++) th.emplace_back(copy_part, t);
+                for (auto &x : th) x.join();
             }
         }
     }
     ctx->timing.kernel_launches += launches;
     ctx->timing.search_total_ms = ctx->timing.probe_ms + ctx->timing.filter_ms;
     if (stats) *stats = st;
-    if (n_out) *n_out = hits.size();
+    if (n_out) *n_out = n_hits;
     if (out) {
-        mhapb_hit *arr = (mhapb_hit *)malloc(sizeof(mhapb_hit) * std::max<size_t>(1, hits.size()));
-        if (!arr) return fail(ctx, MHAPB_ENOMEM, "malloc hits");
-        if (!hits.empty()) memcpy(arr, hits.data(), sizeof(mhapb_hit) * hits.size());
-        *out = arr;
-    }
+        if (!hit_arr) hit_arr = (mhapb_hit *)malloc(sizeof(mhapb_hit));
+        if (!hit_arr) return fail(ctx, MHAPB_ENOMEM, "malloc hits");
+        *out = hit_arr;
+    } else free(hit_arr);
     return MHAPB_OK;
 }
 
@@ -527,7 +574,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->bases, &ctx->desc, &ctx->keys, &ctx->wts, &ctx->nlight, &ctx->nheavy, &ctx->dupcnt, &ctx->gtable, &ctx->ohash,
-                      &ctx->counters, &ctx->out_minhash, &ctx->out_ord, &ctx->out_ordn, &ctx->qlist, &ctx->cand, &ctx->ovl, &ctx->ovf_list, &ctx->fscratch,
+                      &ctx->counters, &ctx->out_minhash, &ctx->out_ord, &ctx->out_ordn, &ctx->qlist, &ctx->cand, &ctx->ovl, &ctx->cand2, &ctx->ovl2, &ctx->ovf_list, &ctx->fscratch,
                       &ctx->scounters, &ctx->tmp_start, &ctx->block_sums, &ctx->q_minhash, &ctx->q_ord, &ctx->q_ordn, &ctx->q_lenk, &ctx->q_len,
                       &ctx->q_id, &ctx->eq, &ctx->store.minhash, &ctx->store.ord, &ctx->store.ord_n, &ctx->store.lenk, &ctx->store.len,
                       &ctx->store.id, &ctx->store.slots, &ctx->store.postings};

@@ -100,6 +100,12 @@ cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches);
 // cudaErrorInvalidConfiguration if the sketches do not fit shared memory (caller uses launch_filter)
 cudaError_t launch_filter_warp(cudaStream_t st, FilterArgs a, int *launches);
 
+// Compact the (candidate, overlap) pairs that can still pass the score threshold: non-empty overlaps whose bottom-k
+// jaccard inter/kmin is >= jmin (a bound the caller lowers by a safety margin; the exact double-precision score
+// test stays on the host).  keep_all copies everything.  d_count: 64-bit cursor, zero on entry.
+cudaError_t launch_compact_hits(cudaStream_t st, const Candidate *cand, const OverlapOut *ovl, uint64_t n, double jmin, int keep_all,
+                                Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *d_count, int *launches);
+
 cudaError_t launch_equal_count(cudaStream_t st, const int32_t *a, const int32_t *b, int H, int32_t *d_out, int *launches);
 
 } // namespace mhapb

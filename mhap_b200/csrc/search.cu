@@ -10,6 +10,7 @@
 // HBM / L2 random-access bound integer work; no tensor cores.
 #include "engine.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace mhapb {
@@ -508,7 +509,9 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs a)
 // order reproduces the reference's record order.  Median = exact k-th smallest by an 8-bit radix select;
 // optimizeShifts = ordered compaction of pos1 runs; the bottom-k merge is partitioned the same way, the
 // lane in which the union count crosses k finishing it sequentially.
-constexpr int kFwRecCap = 512;      // match records kept in shared memory; more => thread-per-candidate kernel
+constexpr int kFwRecCap = 512;      // match records kept in shared memory per warp
+constexpr int kFwLaneCap = kFwRecCap / 2 / 32;   // private first-try slot per lane (8 records)
+// (a pair with more match records than kFwRecCap goes to the thread-per-candidate kernel)
 
 struct FwWindow { int32_t v1lo, v1hi, v2lo, v2hi, median, absmax; };
 
@@ -536,8 +539,9 @@ __device__ __forceinline__ int fw_lower_bound(const FwSketch s, int n, int32_t h
     return lo;
 }
 
-// the reference loop (sketch/BottomOverlapSketch.java:428-515) on A[i1..e1) x B[i2..e2); out==nullptr counts only
-__device__ int fw_merge_range(const FwSketch A, int i1, int e1, const FwSketch Bs, int i2, int e2, const FwWindow &w, int2 *out)
+// the reference loop (sketch/BottomOverlapSketch.java:428-515) on A[i1..e1) x B[i2..e2): returns the number of match
+// records and stores the first `cap` of them in out
+__device__ int fw_merge_range(const FwSketch A, int i1, int e1, const FwSketch Bs, int i2, int e2, const FwWindow &w, int2 *out, int cap)
 {
     int count = 0;
     if (i1 >= e1 || i2 >= e2) return 0;
@@ -550,14 +554,14 @@ __device__ int fw_merge_range(const FwSketch A, int i1, int e1, const FwSketch B
             if (diff > w.absmax) { if (++i1 >= e1) break; a = A[i1]; }
             else if (diff < -w.absmax) { if (++i2 >= e2) break; b = Bs[i2]; }
             else {
-                if (out) out[count] = make_int2(a.y, b.y);
+                if (count < cap) out[count] = make_int2(a.y, b.y);
                 count++;
                 int i1last = i1, i2last = i2;
                 int32_t p1 = a.y, p2 = b.y;
                 for (int t = i1 + 1; t < e1; t++) { const int2 x = A[t]; if (!(x.x == a.x && x.y >= w.v1lo && x.y < w.v1hi)) break; i1last = t; p1 = x.y; }
                 for (int t = i2 + 1; t < e2; t++) { const int2 x = Bs[t]; if (!(x.x == b.x && x.y >= w.v2lo && x.y < w.v2hi)) break; i2last = t; p2 = x.y; }
                 if (i1 != i1last || i2 != i2last) {
-                    if (out) out[count] = make_int2(p1, p2);
+                    if (count < cap) out[count] = make_int2(p1, p2);
                     count++;
                     i1 = i1last + 1; i2 = i2last + 1;
                 } else { i1++; i2++; }
@@ -670,13 +674,20 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a, int capA, int
         int32_t median = 0, absmax = max(len1, len2) + 1;     // empty MatchData (BottomOverlapSketch.java:207-211)
         for (int pass = 0; pass < 2 && !overflow; pass++) {
             const FwWindow w = fw_window(median, absmax, len1, len2);
-            const int mine = fw_merge_range(A, a0, a1, Bs, b0, b1, w, nullptr);
+            // one merge in the common case: every lane records into a private slot of kFwLaneCap entries in the upper half
+            // of the buffer, then the slots are packed in lane order into the lower half; a lane with more matches (or a
+            // pair with more than half the buffer) repeats the merge writing at its final offset
+            int2 *slot = rec + kFwRecCap / 2 + lane * kFwLaneCap;
+            const int mine = fw_merge_range(A, a0, a1, Bs, b0, b1, w, slot, kFwLaneCap);
             int total;
             const int off = warp_excl_scan(mine, lane, &total);
             count = total;
             if (total == 0) break;
             if (total > kFwRecCap) { overflow = true; break; }
-            fw_merge_range(A, a0, a1, Bs, b0, b1, w, rec + off);
+            const bool fits = __all_sync(kFull, mine <= kFwLaneCap) && total <= kFwRecCap / 2;
+            __syncwarp();
+            if (fits) { for (int j = 0; j < mine; j++) rec[off + j] = slot[j]; }
+            else fw_merge_range(A, a0, a1, Bs, b0, b1, w, rec + off, mine);
             __syncwarp();
             fw_update(rec, count, len1, len2, a.max_shift, hist, lane, &median, &absmax);
         }
@@ -815,6 +826,43 @@ cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches)
     if (a.n_cand == 0) return cudaSuccess;
     unsigned grid = (a.n_threads + 127) / 128;
     k_filter<<<grid, 128, 0, st>>>(a);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// result compaction: only pairs that can still pass the threshold travel to the host
+// ---------------------------------------------------------------------------------------------
+__global__ void k_compact_hits(const Candidate *__restrict__ cand, const OverlapOut *__restrict__ ovl, uint64_t n, double jmin, int keep_all,
+                               Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *count)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        bool keep = false;
+        OverlapOut o;
+        if (i < n) {
+            o = ovl[i];
+            keep = keep_all || (!o.empty && o.kmin > 0 && (double)o.inter >= jmin * (double)o.kmin);
+        }
+        const unsigned m = __ballot_sync(kFull, keep);
+        if (m) {
+            unsigned long long p = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) p = atomicAdd(count, (unsigned long long)__popc(m));
+            p = __shfl_sync(kFull, p, leader) + __popc(m & ((1u << lane) - 1));
+            if (keep) { cand_out[p] = cand[i]; ovl_out[p] = o; }
+        }
+    }
+}
+
+cudaError_t launch_compact_hits(cudaStream_t st, const Candidate *cand, const OverlapOut *ovl, uint64_t n, double jmin, int keep_all,
+                                Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *d_count, int *launches)
+{
+    if (n == 0) return cudaSuccess;
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t grid = std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 8);
+    k_compact_hits<<<(unsigned)grid, 256, 0, st>>>(cand, ovl, n, jmin, keep_all, cand_out, ovl_out, d_count);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -258,7 +258,8 @@ class Engine:
     # ---- search ----
     def _collect(self, out, n, st):
         if n.value:
-            hits = np.frombuffer(C.string_at(out.value, n.value * C.sizeof(Hit)), dtype=HIT_DTYPE).copy()
+            raw = (C.c_char * (n.value * C.sizeof(Hit))).from_address(out.value)
+            hits = np.frombuffer(raw, dtype=HIT_DTYPE).copy()      # one copy out of the library's buffer
         else:
             hits = np.zeros(0, dtype=HIT_DTYPE)
         self.L.mhapb_free(out)
