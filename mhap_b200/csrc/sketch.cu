@@ -498,6 +498,185 @@ __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__re
     }
 }
 
+// ---- lock-step variant of the bit-sliced phase (the default) --------------------------------------
+// Instead of handing bundles from lane to lane, every lane keeps its own bundle for the whole chain and the
+// 32 lanes walk the H words in lock step, so at any moment the whole warp works on ONE word: its exact
+// minimum (and the filter depth derived from it) is a single warp-uniform value read by a broadcast LDS.
+// That removes the 64 shuffles per hop, the pipeline fill/drain (31 of 311 hops for a 10 kbp strand) and the
+// per-lane tap select (the OR over the top planes is a fall-through switch on a uniform value, 1-bit
+// granularity).  Flagged chains are resolved one at a time against the shared exact state as before.
+constexpr int kBsMaxDepth = 26;
+
+__device__ __forceinline__ uint32_t bs_depth_of(uint32_t hi_signed)
+{
+    const uint32_t tu = hi_signed ^ 0x80000000u;     // sign-biased high word of the word's current minimum
+    const int F = tu ? __clz(tu) : 32;               // x < min  =>  the top F biased bits of x are zero
+    return (uint32_t)min(F, kBsMaxDepth);
+}
+
+struct BsShared { uint32_t *hi, *lo, *out, *depth; };   // [Hpad] each, indexed by word
+
+__device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
+                                                  uint32_t *scratch /* [64] */, int lane)
+{
+    uint32_t R[64];
+    for (int r0 = 0; r0 < nb; r0 += 32) {
+        const int bi = r0 + lane;
+        const bool valid = bi < nb;
+        {   // load this lane's 32 keys and transpose them into bit planes (low words, then high words)
+            const uint64_t *kp = keys + (size_t)(valid ? bi : 0) * 32;
+            uint32_t w[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) w[c] = (uint32_t)kp[c];
+            transpose32(w);
+#pragma unroll
+            for (int pbit = 0; pbit < 32; pbit++) R[pbit] = w[31 - pbit];
+#pragma unroll
+            for (int c = 0; c < 32; c++) w[c] = (uint32_t)(kp[c] >> 32);
+            transpose32(w);
+#pragma unroll
+            for (int pbit = 0; pbit < 32; pbit++) R[32 + pbit] = w[31 - pbit];
+        }
+#pragma unroll 1
+        for (int wd = 0; wd < H; wd++) {
+            bs_step(R);
+            // chains whose sign-biased value has its top `depth` bits all zero (warp-uniform depth)
+            uint32_t o = 0;
+            switch (st.depth[wd]) {
+            case 26: o |= R[38];
+            case 25: o |= R[39];
+            case 24: o |= R[40];
+            case 23: o |= R[41];
+            case 22: o |= R[42];
+            case 21: o |= R[43];
+            case 20: o |= R[44];
+            case 19: o |= R[45];
+            case 18: o |= R[46];
+            case 17: o |= R[47];
+            case 16: o |= R[48];
+            case 15: o |= R[49];
+            case 14: o |= R[50];
+            case 13: o |= R[51];
+            case 12: o |= R[52];
+            case 11: o |= R[53];
+            case 10: o |= R[54];
+            case 9: o |= R[55];
+            case 8: o |= R[56];
+            case 7: o |= R[57];
+            case 6: o |= R[58];
+            case 5: o |= R[59];
+            case 4: o |= R[60];
+            case 3: o |= R[61];
+            case 2: o |= R[62];
+            case 1: o |= ~R[63];
+            default: break;
+            }
+            uint32_t cand = valid ? ~o : 0u;
+            unsigned evm = __ballot_sync(kFull, cand != 0);
+            while (evm) {                               // warp-uniform
+                const int L = __ffs(evm) - 1;
+                evm &= evm - 1;
+                // high planes first: about half of the flagged chains are rejected on the high word alone
+                if (lane == L) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) scratch[32 + i] = R[32 + i];
+                }
+                __syncwarp();
+                const uint32_t p_hi = scratch[32 + lane];
+                uint32_t cm = __shfl_sync(kFull, cand, L);
+                const int32_t bh0 = (int32_t)st.hi[wd];
+                uint32_t keep = 0;
+                for (uint32_t c2 = cm; c2; c2 &= c2 - 1) {
+                    const int sb = __ffs(c2) - 1;
+                    const uint32_t xh = __ballot_sync(kFull, (p_hi >> sb) & 1u);
+                    if ((int32_t)xh <= bh0) keep |= 1u << sb;
+                }
+                cm = keep;
+                if (cm) {
+                    if (lane == L) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) scratch[i] = R[i];
+                    }
+                    __syncwarp();
+                }
+                const uint32_t p_lo = cm ? scratch[lane] : 0u;
+                while (cm) {                            // warp-uniform
+                    const int sb = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    const uint32_t xh = __ballot_sync(kFull, (p_hi >> sb) & 1u);
+                    const uint32_t xl = __ballot_sync(kFull, (p_lo >> sb) & 1u);
+                    const int32_t bh = (int32_t)st.hi[wd];
+                    if ((int32_t)xh < bh || ((int32_t)xh == bh && xl < st.lo[wd])) {   // MinHashSketch.java:144, uniform
+                        __syncwarp();
+                        if (lane == L) {
+                            const uint64_t key = keys[(size_t)(r0 + L) * 32 + (31 - sb)];
+                            st.hi[wd] = xh; st.lo[wd] = xl;
+                            st.out[wd] = (wd & 1) ? (uint32_t)(key >> 32) : (uint32_t)key;   // :146-149
+                            st.depth[wd] = bs_depth_of(xh);
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(128, B <= 16 ? 4 : (B <= 32 ? 3 : 1))
+k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
+              int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys)
+{
+    // per warp: state [4][B*32] | scratch [64] ; static: key ring + weights for the scalar pipeline
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    __shared__ uint64_t s_kbuf[4][64];
+    __shared__ uint32_t s_wbuf[4][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int HP = B * 32;
+    constexpr int kPerWarp = 4 * HP + 64;
+    uint32_t *wbase = s_dyn + (size_t)wib * kPerWarp;
+    BsShared st;
+    st.hi = wbase; st.lo = wbase + HP; st.out = wbase + 2 * HP; st.depth = wbase + 3 * HP;
+    uint32_t *scratch = wbase + 4 * HP;
+    for (;;) {
+        int s = 0;
+        if (lane == 0) s = (int)atomicAdd(queue, 1u);
+        s = __shfl_sync(kFull, s, 0);
+        if (s >= n_strands) break;
+        const StrandDesc d = desc[s];
+        const int nk = (int)d.len - k + 1;
+        const uint64_t *keys = sc.keys + d.koff;
+        const int nl = sc.nlight[s], nh = sc.nheavy[s];
+        const int nb = nl > scalar_keys ? (nl - scalar_keys) / 32 : 0;   // full bundles, taken from the end
+        const int n_sc = nl - 32 * nb;
+        LaneMins<B> m;
+#pragma unroll
+        for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
+        minhash_pipeline<B, false>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        if (nh > 0)
+            minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
+        int32_t *row = minhash + (size_t)d.row * H;
+        if (nb > 0) {
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const int word = lane * B + b;
+                st.hi[word] = (uint32_t)m.hi[b]; st.lo[word] = m.lo[b]; st.out[word] = (uint32_t)m.out[b];
+                st.depth[word] = bs_depth_of((uint32_t)m.hi[b]);
+            }
+            __syncwarp();
+            bs_phase_lockstep(st, H, keys + n_sc, nb, scratch, lane);
+            __syncwarp();
+            for (int word = lane; word < H; word += 32) row[word] = (int32_t)st.out[word];
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int b = 0; b < B; b++) { int word = lane * B + b; if (word < H) row[word] = m.out[b]; }
+        }
+    }
+}
+
 template <int B>
 __global__ void __launch_bounds__(128, B <= 16 ? 4 : 2)
 k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
@@ -781,9 +960,10 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
 
 static int k1b_variant()
 {
-    // MHAPB_K1B=scalar selects the scalar systolic kernel (kept for A/B measurements); default bit-sliced
+    // MHAPB_K1B=scalar selects the scalar systolic kernel, =bitsliced-systolic the first bit-sliced kernel (both kept
+    // for A/B measurements); default: bit-sliced lock-step
     static int v = -1;
-    if (v < 0) { const char *e = getenv("MHAPB_K1B"); v = (e && e[0] == 's') ? 0 : 1; }
+    if (v < 0) { const char *e = getenv("MHAPB_K1B"); v = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : 2; }
     return v;
 }
 
@@ -793,6 +973,21 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
 {
     cudaError_t e;
     int per_sm = 0;
+    if (k1b_variant() == 2 && B <= 32) {
+        const size_t smem = (size_t)4 * (4 * B * 32 + 64) * 4;
+        e = cudaFuncSetAttribute(k_minhash_bs2<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash_bs2<B>, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        int grid = sm_count() * per_sm;
+        int need = (n_strands + 3) / 4;
+        if (grid > need) grid = need;
+        static int scalar_keys2 = -1;
+        if (scalar_keys2 < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys2 = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys2 < 0) scalar_keys2 = 0; }
+        k_minhash_bs2<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys2);
+        return cudaGetLastError();
+    }
     if (k1b_variant() == 1 && B <= 32) {
         const size_t smem = (size_t)4 * (4 * B * 32 + 64 * kBsStage + 64) * 4;
         e = cudaFuncSetAttribute(k_minhash_bs<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
