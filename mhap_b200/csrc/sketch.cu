@@ -624,7 +624,7 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
 }
 
 template <int B>
-__global__ void __launch_bounds__(128, B <= 16 ? 4 : (B <= 32 ? 3 : 1))
+__global__ void __launch_bounds__(128, B <= 16 ? 5 : (B <= 32 ? 3 : 1))
 k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
               int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys)
 {
