@@ -71,6 +71,7 @@ struct Store {
 struct mhapb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // K1c runs here, concurrently with K1b of the same chunk
     std::mutex mu;
     std::string err;
     mhapb_timing timing{};
@@ -117,6 +118,15 @@ inline int read_status(const mhapb_sketch_params &p, uint64_t len)
 
 struct Elapsed { float hash = 0, minhash = 0, ordered = 0; };
 
+bool overlap_k1c()
+{
+    static int v = -1;
+    // measured on B200 (configs[1]): with K1c sharing the SMs with the alu-bound K1b it stretches from 34 ms to
+    // 434 ms per step and becomes the critical path (1.79 vs 1.96 Gbases/s), so the overlap is off unless asked for
+    if (v < 0) { const char *e = getenv("MHAPB_OVERLAP_K1C"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v != 0;
+}
+
 // Sketch reads whose characters are at d_bases (device).  row_of_slot[slot] (slot = read*per+strand)
 // gives the output row or -1 to skip.  Outputs are device arrays.
 int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_bases, const uint64_t *h_offsets,
@@ -145,7 +155,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     const uint64_t chunk_cap = 256ull << 20;   // k-mers of key scratch per chunk (2 GB keys + 1 GB weights)
     const int max_chunk_strands = 1 << 20;
     int launches = 0;
-    std::vector<cudaEvent_t> evs;
+    std::vector<cudaEvent_t> evs, cevs;
     auto ev_new = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e); };
 
     size_t pos = 0;
@@ -200,21 +210,43 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         sc.dupcnt = ctx->dupcnt.as<uint32_t>(); sc.gtable = ctx->gtable.as<uint64_t>();
         sc.ohash = ctx->ohash.as<uint32_t>(); sc.counters = ctx->counters.as<uint32_t>();
         const StrandDesc *dd = ctx->desc.as<StrandDesc>();
-        ev_new();
+        // K1a -> K1b on the main stream; K1c (independent of both: it only needs the reads) on the second stream,
+        // released when K1a is done so that it shares the SMs with the alu-bound K1b instead of the
+        // shared-memory-hungry K1a.  K1c is launched first with one CTA per SM, K1b fills the rest.
+        ev_new();                                                     // [0] before K1a
         CU(ctx, launch_hash_dedup(ctx->stream, d_bases, dd, n, first_long, max_k_short, max_k_long, k, p.unweighted, sc, &launches));
-        ev_new();
+        ev_new();                                                     // [1] after K1a
+        cudaEvent_t c0 = nullptr, c1 = nullptr;
+        const bool overlap = overlap_k1c() && d_ord && d_minhash;
+        if (overlap) {
+            CU(ctx, cudaStreamWaitEvent(ctx->stream2, evs.back(), 0));
+            cudaEventCreate(&c0); cudaEventCreate(&c1);
+            cudaEventRecord(c0, ctx->stream2);
+            CU(ctx, launch_ordered(ctx->stream2, d_bases, dd, n, first_long, max_len_short, max_len_long, ok, S, ord_stride, sc, d_ord, d_ord_n, 1, &launches));
+            cudaEventRecord(c1, ctx->stream2);
+        }
         if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n, k, H, sc, d_minhash, &launches));
-        ev_new();
-        if (d_ord) CU(ctx, launch_ordered(ctx->stream, d_bases, dd, n, first_long, max_len_short, max_len_long, ok, S, ord_stride, sc, d_ord, d_ord_n, &launches));
-        ev_new();
+        ev_new();                                                     // [2] after K1b
+        if (overlap) {
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, c1, 0));         // the next chunk reuses the descriptors
+            cevs.push_back(c0); cevs.push_back(c1);
+        } else if (d_ord) {
+            CU(ctx, launch_ordered(ctx->stream, d_bases, dd, n, first_long, max_len_short, max_len_long, ok, S, ord_stride, sc, d_ord, d_ord_n, 0, &launches));
+        }
+        ev_new();                                                     // [3] end of chunk
         // the next chunk reuses desc/keys: the stream orders it, but the pageable host vector is copied synchronously above
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i + 3 < evs.size(); i += 4) {
         float a = 0, b = 0, c = 0;
         cudaEventElapsedTime(&a, evs[i], evs[i + 1]); cudaEventElapsedTime(&b, evs[i + 1], evs[i + 2]); cudaEventElapsedTime(&c, evs[i + 2], evs[i + 3]);
-        ctx->timing.hash_dedup_ms += a; ctx->timing.minhash_ms += b; ctx->timing.ordered_ms += c;
+        ctx->timing.hash_dedup_ms += a; ctx->timing.minhash_ms += b;
+        if (cevs.empty()) ctx->timing.ordered_ms += c;
     }
+    for (size_t i = 0; i + 1 < cevs.size(); i += 2) {   // K1c timed on its own stream (it overlaps K1b)
+        float c = 0; cudaEventElapsedTime(&c, cevs[i], cevs[i + 1]); ctx->timing.ordered_ms += c;
+    }
+    for (auto e : cevs) cudaEventDestroy(e);
     if (evs.size() >= 2) { float t = 0; cudaEventElapsedTime(&t, evs.front(), evs.back()); ctx->timing.sketch_total_ms += t; }
     for (auto e : evs) cudaEventDestroy(e);
     ctx->timing.kernel_launches += launches;
@@ -563,6 +595,7 @@ int mhapb_create(int device_id, mhapb_ctx **out)
     mhapb_ctx *c = new mhapb_ctx();
     c->device = device_id;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, MHAPB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return fail(nullptr, MHAPB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
     *out = c;
     return MHAPB_OK;
@@ -581,6 +614,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
     for (auto b : bufs) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 

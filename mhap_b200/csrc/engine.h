@@ -46,7 +46,7 @@ cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_stra
 // K1c: MurmurHash3_x86_32 of every ordered k-mer, bottom-S by (signed hash, position), sorted.
 cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
                            int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,
-                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int *launches);
+                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int max_ctas_per_sm /* 0: default */, int *launches);
 // independent XORShift chains at full occupancy: the integer-issue ceiling K1b is measured against
 cudaError_t launch_xorshift_peak(cudaStream_t st, unsigned long long *d_sink, double *steps);
 cudaError_t launch_xorshift_peak_bs(cudaStream_t st, unsigned long long *d_sink, double *steps);

@@ -1033,7 +1033,7 @@ cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_stra
 
 cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
                            int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,
-                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int *launches)
+                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int max_ctas_per_sm, int *launches)
 {
     cudaError_t e;
     uint32_t sel_cap = 1; while ((int)sel_cap < S) sel_cap <<= 1;
@@ -1044,7 +1044,9 @@ cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const Strand
         auto kern = ok == 12 ? k_ordered<false, 12> : k_ordered<false, 0>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int grid = sm_count() * (smem <= 100 * 1024 ? 2 : 1);
+        int per_sm = smem <= 100 * 1024 ? 2 : 1;
+        if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
+        int grid = sm_count() * per_sm;
         if (grid > first_long) grid = first_long;
         kern<<<grid, 512, smem, st>>>(d_bases, d_desc, 0, first_long, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 3);
         (*launches)++;
