@@ -23,7 +23,8 @@ constexpr int kMaxNumHashes = 2048;
 constexpr int kMaxOrderedSketch = 4096;
 // slots of the K1a de-duplication table for a strand of nk k-mers: load factor <= 0.8, so two 10 kbp CTAs
 // (table + staged characters) fit one SM's shared memory and overlap each other's barrier phases
-__host__ __device__ inline uint32_t dedup_table_slots(uint32_t nk) { return nk + nk / 4 + 8; }
+// (odd, so that the power-of-two probe strides of the double hashing below visit every slot)
+__host__ __device__ inline uint32_t dedup_table_slots(uint32_t nk) { return (nk + nk / 4 + 8) | 1u; }
 
 struct SketchScratch {
     uint64_t *keys;      // [cap_kmers] distinct k-mer hashes per strand: light from the front, heavy from the back
