@@ -10,6 +10,7 @@
 // bound by integer issue, not HBM -- see DESIGN.md.
 #include "engine.h"
 #include "hash.cuh"
+#include "bs_step.cuh"
 
 #include <cstdlib>
 
@@ -125,7 +126,8 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
                     // an empty one.  ncu on the first version (linear probing, CAS per probe) showed the probe loop running
                     // 14 times per warp with 4 of 32 lanes active.
                     uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * C) >> 32);
-                    const uint32_t stride = 1u << ((uint32_t)h & 7u);
+                    uint32_t stride = 1u << ((uint32_t)h & 7u);
+                    if (stride >= C) stride = 1u;   // tiny strands: keep slot + stride - C inside the table
                     for (;;) {
                         unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&table[slot]);
                         if (old == kEmptyKey)
@@ -354,12 +356,14 @@ k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, Sket
 // The first kBsScalarKeys keys of a strand (where a running minimum changes most often: the expected
 // number of updates of word w after t keys is the harmonic sum) and the keys with weight > 1 go through
 // the scalar pipeline first; so do strands too short to fill bundles.
-constexpr int kBsScalarKeys = 1024;
+constexpr int kBsScalarKeys = 768;
 constexpr int kBsTaps = 9;
 constexpr int kBsStage = 16;   // bundles transposed per staging round (lanes 0..15 transpose one each)
 __device__ __constant__ int c_bs_tap_bits[kBsTaps] = {0, 4, 8, 10, 12, 14, 16, 18, 20};
 
-__device__ __forceinline__ void bs_step(uint32_t (&R)[64])
+// The plain plane form of the step: 43 + 29 + 60 = 132 two-input XORs.  Kept as the statement of what
+// bs_step() (bs_step.cuh, generated: the same linear map as 92 three-input XORs) must equal.
+__device__ __forceinline__ void bs_step_plain(uint32_t (&R)[64])
 {
 #pragma unroll
     for (int i = 63; i >= 21; i--) R[i] ^= R[i - 21];      // x ^= x << 21
@@ -521,8 +525,62 @@ __device__ __forceinline__ uint32_t bs_depth_of(uint32_t hi_signed)
     return (uint32_t)min(F, kBsMaxDepth);
 }
 
+// Prefix filter of the lock-step kernel: bit c of the result is set when chain c's sign-biased value has its top
+// `depth` bits all zero (and the lane holds a real bundle).  depth is warp-uniform, 0..kBsMaxDepth.  Written in PTX
+// so that it is ONE indexed branch (brx.idx -> BRX through a table) into one of two pure fall-through chains that
+// OR two planes per LOP3 -- even depths pair (63,62),(61,60),.., odd depths pair (62,61),(60,59),.. and fold plane 63
+// into the last LOP3 -- so depth d costs ceil(d/2)+1 LOP3.  (The C++ switch of the same shape is compiled to a
+// compare/branch tree: ~12 extra alu-pipe instructions per word step.)
+__device__ __forceinline__ uint32_t bs_prefix_filter(const uint32_t (&R)[64], uint32_t depth, uint32_t vmask)
+{
+    uint32_t cand;
+    asm volatile(
+        "{\n\t"
+        ".reg .u32 o;\n\t"
+        "bsf_tbl: .branchtargets bsf_d0, bsf_d1, bsf_d2, bsf_d3, bsf_d4, bsf_d5, bsf_d6, bsf_d7, bsf_d8, bsf_d9, bsf_d10, bsf_d11, bsf_d12, bsf_d13, bsf_d14, bsf_d15, bsf_d16, bsf_d17, bsf_d18, bsf_d19, bsf_d20, bsf_d21, bsf_d22, bsf_d23, bsf_d24, bsf_d25, bsf_d26;\n\t"
+        "mov.u32 o, 0;\n\t"
+        "brx.idx.uni %1, bsf_tbl;\n\t"
+        "bsf_d26: lop3.b32 o, %3, %4, o, 0xFE;\n\t"   // R38 | R39
+        "bsf_d24: lop3.b32 o, %5, %6, o, 0xFE;\n\t"   // R40 | R41
+        "bsf_d22: lop3.b32 o, %7, %8, o, 0xFE;\n\t"   // R42 | R43
+        "bsf_d20: lop3.b32 o, %9, %10, o, 0xFE;\n\t"   // R44 | R45
+        "bsf_d18: lop3.b32 o, %11, %12, o, 0xFE;\n\t"   // R46 | R47
+        "bsf_d16: lop3.b32 o, %13, %14, o, 0xFE;\n\t"   // R48 | R49
+        "bsf_d14: lop3.b32 o, %15, %16, o, 0xFE;\n\t"   // R50 | R51
+        "bsf_d12: lop3.b32 o, %17, %18, o, 0xFE;\n\t"   // R52 | R53
+        "bsf_d10: lop3.b32 o, %19, %20, o, 0xFE;\n\t"   // R54 | R55
+        "bsf_d8: lop3.b32 o, %21, %22, o, 0xFE;\n\t"   // R56 | R57
+        "bsf_d6: lop3.b32 o, %23, %24, o, 0xFE;\n\t"   // R58 | R59
+        "bsf_d4: lop3.b32 o, %25, %26, o, 0xFE;\n\t"   // R60 | R61
+        "bsf_d2: lop3.b32 o, %27, %28, o, 0xFB;\n\t"   // R62 | ~R63
+        "bsf_d0: lop3.b32 %0, o, %2, 0, 0x0C;\n\t"   // ~o & vmask
+        "bra.uni bsf_end;\n\t"
+        "bsf_d25: lop3.b32 o, %4, %5, o, 0xFE;\n\t"   // R39 | R40
+        "bsf_d23: lop3.b32 o, %6, %7, o, 0xFE;\n\t"   // R41 | R42
+        "bsf_d21: lop3.b32 o, %8, %9, o, 0xFE;\n\t"   // R43 | R44
+        "bsf_d19: lop3.b32 o, %10, %11, o, 0xFE;\n\t"   // R45 | R46
+        "bsf_d17: lop3.b32 o, %12, %13, o, 0xFE;\n\t"   // R47 | R48
+        "bsf_d15: lop3.b32 o, %14, %15, o, 0xFE;\n\t"   // R49 | R50
+        "bsf_d13: lop3.b32 o, %16, %17, o, 0xFE;\n\t"   // R51 | R52
+        "bsf_d11: lop3.b32 o, %18, %19, o, 0xFE;\n\t"   // R53 | R54
+        "bsf_d9: lop3.b32 o, %20, %21, o, 0xFE;\n\t"   // R55 | R56
+        "bsf_d7: lop3.b32 o, %22, %23, o, 0xFE;\n\t"   // R57 | R58
+        "bsf_d5: lop3.b32 o, %24, %25, o, 0xFE;\n\t"   // R59 | R60
+        "bsf_d3: lop3.b32 o, %26, %27, o, 0xFE;\n\t"   // R61 | R62
+        "bsf_d1: lop3.b32 %0, o, %28, %2, 0x08;\n\t"   // ~o & R63 & vmask
+        "bsf_end:\n\t"
+        "}"
+        : "=r"(cand)
+        : "r"(depth), "r"(vmask),
+          "r"(R[38]), "r"(R[39]), "r"(R[40]), "r"(R[41]), "r"(R[42]), "r"(R[43]), "r"(R[44]), "r"(R[45]), "r"(R[46]), "r"(R[47]),
+          "r"(R[48]), "r"(R[49]), "r"(R[50]), "r"(R[51]), "r"(R[52]), "r"(R[53]), "r"(R[54]), "r"(R[55]), "r"(R[56]), "r"(R[57]),
+          "r"(R[58]), "r"(R[59]), "r"(R[60]), "r"(R[61]), "r"(R[62]), "r"(R[63]));
+    return cand;
+}
+
 struct BsShared { uint32_t *hi, *lo, *out, *depth; };   // [Hpad] each, indexed by word
 
+template <bool PAIRED>
 __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
                                                   uint32_t *scratch /* [64] */, int lane)
 {
@@ -530,6 +588,7 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
     for (int r0 = 0; r0 < nb; r0 += 32) {
         const int bi = r0 + lane;
         const bool valid = bi < nb;
+        const uint32_t vmask = valid ? ~0u : 0u;
         {   // load this lane's 32 keys and transpose them into bit planes (low words, then high words)
             const uint64_t *kp = keys + (size_t)(valid ? bi : 0) * 32;
             uint32_t w[32];
@@ -548,6 +607,8 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
         for (int wd = 0; wd < H; wd++) {
             bs_step(R);
             // chains whose sign-biased value has its top `depth` bits all zero (warp-uniform depth)
+            uint32_t cand;
+            if constexpr (!PAIRED) {
             uint32_t o = 0;
             switch (st.depth[wd]) {
             case 26: o |= R[38];
@@ -578,7 +639,10 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
             case 1: o |= ~R[63];
             default: break;
             }
-            uint32_t cand = valid ? ~o : 0u;
+            cand = valid ? ~o : 0u;
+            } else {
+                cand = bs_prefix_filter(R, st.depth[wd], vmask);
+            }
             unsigned evm = __ballot_sync(kFull, cand != 0);
             while (evm) {                               // warp-uniform
                 const int L = __ffs(evm) - 1;
@@ -630,7 +694,7 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
     }
 }
 
-template <int B>
+template <int B, bool PAIRED>
 __global__ void __launch_bounds__(128, B <= 16 ? 5 : (B <= 32 ? 3 : 1))
 k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
               int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys)
@@ -673,7 +737,7 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
                 st.depth[word] = bs_depth_of((uint32_t)m.hi[b]);
             }
             __syncwarp();
-            bs_phase_lockstep(st, H, keys + n_sc, nb, scratch, lane);
+            bs_phase_lockstep<PAIRED>(st, H, keys + n_sc, nb, scratch, lane);
             __syncwarp();
             for (int word = lane; word < H; word += 32) row[word] = (int32_t)st.out[word];
             __syncwarp();
@@ -896,7 +960,7 @@ static int sm_count()
 
 static constexpr uint32_t kShortTableCap = (kShortMaxKmers + kShortMaxKmers / 4 + 8) | 1;   // 20489 slots = 160 KB
 
-// the bit-sliced recurrence alone: 132 XORs per 32 chain steps, nothing else
+// the bit-sliced recurrence alone (bs_step.cuh: 92 three-input XORs per 32 chain steps), nothing else
 __global__ void __launch_bounds__(256) k_xorshift_peak_bs(unsigned long long *sink)
 {
     uint32_t R[64];
@@ -982,9 +1046,13 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
     int per_sm = 0;
     if (k1b_variant() == 2 && B <= 32) {
         const size_t smem = (size_t)4 * (4 * B * 32 + 64) * 4;
-        e = cudaFuncSetAttribute(k_minhash_bs2<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // MHAPB_BS_FILTER=single keeps the one-plane-per-LOP3 prefix filter for A/B runs; default: two planes per LOP3
+        static int paired = -1;
+        if (paired < 0) { const char *ev = getenv("MHAPB_BS_FILTER"); paired = (ev && ev[0] == 's') ? 0 : 1; }
+        auto kern = paired ? k_minhash_bs2<B, true> : k_minhash_bs2<B, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash_bs2<B>, 128, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         int grid = sm_count() * per_sm;
@@ -992,7 +1060,7 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         if (grid > need) grid = need;
         static int scalar_keys2 = -1;
         if (scalar_keys2 < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys2 = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys2 < 0) scalar_keys2 = 0; }
-        k_minhash_bs2<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys2);
+        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys2);
         return cudaGetLastError();
     }
     if (k1b_variant() == 1 && B <= 32) {

@@ -219,8 +219,184 @@ int64_t mo_kmer_hashes_int(const char *seq, int64_t len, int k, int canonical, i
 /* sketch/MinHashSketch.java:51-179                                                          */
 /* ======================================================================================== */
 
-int mo_minhash_sketch(const char *seq, int64_t len, int k, int num_hashes, int unweighted,
-                      int32_t *hashes)
+/* ---- sketch/FrequencyCounts.java ------------------------------------------------------------ */
+struct mo_filter {
+    mo_filter_params p;
+    /* fractionCounts: Long2DoubleOpenHashMap, here open addressing over (hash, fraction) */
+    int64_t *mkey; double *mval; uint8_t *mused; size_t mcap; int64_t mn;
+    double max_value, min_value, min_idf, max_idf;       /* :223-229 */
+    /* validMers: Guava BloomFilter<Long> (only when remove_unique > 0) */
+    uint64_t *bits; int64_t bit_size; int32_t num_hash_functions;
+};
+
+static void filter_map_put(mo_filter *f, int64_t key, double val)
+{
+    if ((size_t)(f->mn + 1) * 2 > f->mcap) {
+        size_t nc = f->mcap ? f->mcap * 2 : 64;
+        int64_t *ok = f->mkey; double *ov = f->mval; uint8_t *ou = f->mused; size_t oc = f->mcap;
+        f->mkey = (int64_t *)calloc(nc, sizeof(int64_t)); f->mval = (double *)calloc(nc, sizeof(double));
+        f->mused = (uint8_t *)calloc(nc, 1); f->mcap = nc; f->mn = 0;
+        for (size_t i = 0; i < oc; i++) if (ou[i]) filter_map_put(f, ok[i], ov[i]);
+        free(ok); free(ov); free(ou);
+    }
+    size_t q = (size_t)fmix64((uint64_t)key) & (f->mcap - 1);
+    while (f->mused[q] && f->mkey[q] != key) q = (q + 1) & (f->mcap - 1);
+    if (!f->mused[q]) { f->mused[q] = 1; f->mkey[q] = key; f->mn++; }
+    f->mval[q] = val;                                     /* Map.put: a repeated k-mer keeps the last value */
+}
+
+static int filter_map_get(const mo_filter *f, int64_t key, double *val)
+{
+    if (!f->mcap) return 0;
+    size_t q = (size_t)fmix64((uint64_t)key) & (f->mcap - 1);
+    while (f->mused[q]) {
+        if (f->mkey[q] == key) { *val = f->mval[q]; return 1; }
+        q = (q + 1) & (f->mcap - 1);
+    }
+    return 0;
+}
+
+/* Guava 19.0 BloomFilterStrategies.MURMUR128_MITZ_64 with Funnel (value, sink) -> sink.putLong(value):
+ * murmur3_128(seed 0) of the 8 little-endian bytes; hash1/hash2 = lower/upper eight bytes; bit i =
+ * ((hash1 + i*hash2) & Long.MAX_VALUE) % bitSize. */
+static void bloom_hashes(int64_t value, uint64_t h[2])
+{
+    uint8_t b[8];
+    for (int i = 0; i < 8; i++) b[i] = (uint8_t)((uint64_t)value >> (8 * i));
+    mo_murmur3_x64_128(b, 8, 0, h);
+}
+static void bloom_put(mo_filter *f, int64_t value)
+{
+    uint64_t h[2]; bloom_hashes(value, h);
+    uint64_t c = h[0];
+    for (int i = 0; i < f->num_hash_functions; i++) {
+        uint64_t bit = (c & 0x7fffffffffffffffull) % (uint64_t)f->bit_size;
+        f->bits[bit >> 6] |= 1ull << (bit & 63);
+        c += h[1];
+    }
+}
+static int bloom_might_contain(const mo_filter *f, int64_t value)
+{
+    uint64_t h[2]; bloom_hashes(value, h);
+    uint64_t c = h[0];
+    for (int i = 0; i < f->num_hash_functions; i++) {
+        uint64_t bit = (c & 0x7fffffffffffffffull) % (uint64_t)f->bit_size;
+        if (!(f->bits[bit >> 6] & (1ull << (bit & 63)))) return 0;
+        c += h[1];
+    }
+    return 1;
+}
+
+static double filter_idf(const mo_filter *f, double freq) { return log(f->max_value / freq - f->p.offset); }   /* :250-254 */
+
+/* FrequencyCounts ctor :63-230 */
+mo_filter *mo_filter_parse(const char *text, int64_t len, const mo_filter_params *p)
+{
+    mo_filter *f = (mo_filter *)calloc(1, sizeof(mo_filter));
+    f->p = *p;
+    f->max_value = -INFINITY;
+    const char *cur = text, *end = text + len;
+    int64_t size_bloom = 1;
+    /* first line: "<sizeBloom> <sizeRepeat>" (:91-117) */
+    {
+        const char *nl = memchr(cur, '\n', (size_t)(end - cur));
+        const char *le = nl ? nl : end;
+        if (le > cur) {
+            char tmp[128]; size_t n = (size_t)(le - cur) < sizeof(tmp) - 1 ? (size_t)(le - cur) : sizeof(tmp) - 1;
+            memcpy(tmp, cur, n); tmp[n] = 0;
+            long long a = 0, b = 0;
+            if (sscanf(tmp, "%lld %lld", &a, &b) >= 1) size_bloom = a;
+            if (size_bloom == 0) size_bloom = 1;
+        }
+        cur = nl ? nl + 1 : end;
+    }
+    if (p->remove_unique > 0) {
+        /* BloomFilter.create(funnel, expectedInsertions, fpp): optimalNumOfBits / optimalNumOfHashFunctions */
+        const double fpp = 1.0e-5;
+        int64_t n = size_bloom;
+        int64_t num_bits = (int64_t)(-(double)n * log(fpp) / (log(2.0) * log(2.0)));
+        int nh = (int)floor((double)num_bits / (double)n * log(2.0) + 0.5);
+        f->num_hash_functions = nh < 1 ? 1 : nh;
+        int64_t words = (num_bits + 63) / 64;             /* LongMath.divide(bits, 64, CEILING) */
+        if (words < 1) words = 1;
+        f->bits = (uint64_t *)calloc((size_t)words, 8);
+        f->bit_size = words * 64;                         /* BitArray.bitSize() */
+    }
+    char kbuf[4096], rcbuf[4096];
+    while (cur < end) {
+        const char *nl = memchr(cur, '\n', (size_t)(end - cur));
+        const char *le = nl ? nl : end;
+        const char *q = cur;
+        /* String.split("\\s+", 3): a leading separator yields an empty first token (k-mer of length 0: no hash, caught) */
+        const char *t0 = q;
+        while (q < le && !(*q == ' ' || *q == '\t' || *q == '\r' || *q == '\f' || *q == '\v')) q++;
+        size_t klen = (size_t)(q - t0);
+        if (klen >= 1 && klen < sizeof(kbuf)) {
+            memcpy(kbuf, t0, klen);
+            const char *str = kbuf;
+            if (p->canonical) str = canonical_kmer(kbuf, (int)klen, rcbuf);     /* HashUtils.java:246-251 */
+            uint8_t u16[2 * sizeof(kbuf)];
+            utf16le(str, (int)klen, u16);
+            uint64_t h[2];
+            mo_murmur3_x64_128(u16, 2 * klen, 0, h);
+            while (q < le && (*q == ' ' || *q == '\t' || *q == '\r' || *q == '\f' || *q == '\v')) q++;
+            if (q < le) {                                 /* str.length >= 2 (:178-193) */
+                char num[64]; size_t n = 0;
+                while (q < le && n < sizeof(num) - 1 && !(*q == ' ' || *q == '\t' || *q == '\r')) num[n++] = *q++;
+                num[n] = 0;
+                char *ep; double percent = strtod(num, &ep);
+                if (ep != num && *ep == 0) {
+                    if (percent >= p->filter_cutoff) {
+                        if (percent > f->max_value) f->max_value = percent;
+                        filter_map_put(f, (int64_t)h[0], percent);
+                    }
+                } else { cur = nl ? nl + 1 : end; continue; }   /* NumberFormatException: the line is skipped (:204-207) */
+            }
+            if (p->remove_unique > 0) bloom_put(f, (int64_t)h[0]);
+        }
+        cur = nl ? nl + 1 : end;
+    }
+    f->min_value = p->filter_cutoff;                      /* :226 */
+    f->min_idf = filter_idf(f, f->max_value);             /* :228 */
+    f->max_idf = filter_idf(f, f->min_value);             /* :229 */
+    return f;
+}
+
+void mo_filter_free(mo_filter *f)
+{
+    if (!f) return;
+    free(f->mkey); free(f->mval); free(f->mused); free(f->bits); free(f);
+}
+int64_t mo_filter_size(const mo_filter *f) { return f->mn; }
+double mo_filter_max_value(const mo_filter *f) { return f->max_value; }
+int64_t mo_filter_export(const mo_filter *f, int64_t *hashes, double *fractions)
+{
+    int64_t n = 0;
+    for (size_t i = 0; i < f->mcap; i++) if (f->mused[i]) { hashes[n] = f->mkey[i]; fractions[n] = f->mval[i]; n++; }
+    return n;
+}
+int64_t mo_filter_bloom_export(const mo_filter *f, const uint64_t **words, int32_t *nh)
+{
+    *words = f->bits; *nh = f->num_hash_functions; return f->bits ? f->bit_size : 0;
+}
+int mo_filter_is_popular(const mo_filter *f, int64_t hash) { double v; return filter_map_get(f, hash, &v); }
+int mo_filter_keep_kmer(const mo_filter *f, int64_t hash)
+{
+    if (f->p.remove_unique == 1) return bloom_might_contain(f, hash);
+    return 1;
+}
+double mo_filter_scaled_idf(const mo_filter *f, int64_t hash)
+{
+    if (f->p.remove_unique == 2 && f->bits && !bloom_might_contain(f, hash)) return 1.0;   /* :292-293 */
+    double val;
+    if (!filter_map_get(f, hash, &val)) return f->p.range;                                /* :295-297 */
+    double idf = filter_idf(f, val);
+    double scale = (f->max_idf - f->min_idf) / (f->p.range - 1.0);
+    return 1.0 + (idf - f->min_idf) / scale;
+}
+
+int mo_minhash_sketch_filtered(const char *seq, int64_t len, int k, int num_hashes, double repeat_weight,
+                               const mo_filter *f, int32_t *hashes)
 {
     int64_t n = len - k + 1;
     if (n < 1) return 1; /* :55-56 ZeroNGramsFoundException */
@@ -237,6 +413,7 @@ int mo_minhash_sketch(const char *seq, int64_t len, int k, int num_hashes, int u
     int32_t *counts = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
     int64_t ndistinct = 0;
     for (int64_t i = 0; i < n; i++) {
+        if (f && !mo_filter_keep_kmer(f, kmer[i])) continue;   /* :70-71 */
         uint64_t h = fmix64((uint64_t)kmer[i]);
         size_t p = (size_t)h & (cap - 1);
         for (;;) {
@@ -249,6 +426,7 @@ int mo_minhash_sketch(const char *seq, int64_t len, int k, int num_hashes, int u
         }
     }
     free(slot); free(kmer);
+    if (ndistinct == 0) { free(keys); free(counts); return 1; }   /* :84-85 */
 
     /* :87-90 */
     int nh = num_hashes < 1 ? 1 : num_hashes;
@@ -257,11 +435,24 @@ int mo_minhash_sketch(const char *seq, int64_t len, int k, int num_hashes, int u
     for (int i = 0; i < num_hashes; i++) best[i] = INT64_MAX;
 
     /* :95-154 */
+    int64_t number_valid = 0;
     for (int64_t e = 0; e < ndistinct; e++) {
         int64_t key = keys[e];
         int32_t weight = counts[e];
-        if (unweighted) weight = 1; /* :101-107, no filter */
+        if (repeat_weight < 0.0) {                        /* :101-107 original MHAP */
+            weight = 1;
+            if (f && mo_filter_is_popular(f, key)) weight = 0;
+        } else if (f) {
+            if (repeat_weight >= 0.0 && repeat_weight < 1.0) {   /* :111-124 tf-idf */
+                double tf = f->p.no_tf ? 1.0 : (double)weight;   /* FrequencyCounts.tfWeight :312-318 */
+                double idf = mo_filter_scaled_idf(f, key);
+                double r = floor(tf * idf + 0.5);                /* Math.round */
+                weight = (r != r) ? 0 : (r > 2147483647.0 ? 2147483647 : (int32_t)r);
+                if (weight < 1) weight = 1;
+            }
+        }
         if (weight <= 0) continue;
+        number_valid++;
         uint64_t x = (uint64_t)key;
         for (int word = 0; word < num_hashes; word++) {
             for (int c = 0; c < weight; c++) {
@@ -277,7 +468,13 @@ int mo_minhash_sketch(const char *seq, int64_t len, int k, int num_hashes, int u
         }
     }
     free(best); free(keys); free(counts);
-    return 0;
+    return number_valid <= 0 ? 1 : 0;                     /* :156-157 */
+}
+
+int mo_minhash_sketch(const char *seq, int64_t len, int k, int num_hashes, int unweighted,
+                      int32_t *hashes)
+{
+    return mo_minhash_sketch_filtered(seq, len, k, num_hashes, unweighted ? -1.0 : 0.9, NULL, hashes);
 }
 
 /* ======================================================================================== */
@@ -537,6 +734,7 @@ struct mo_store {
     uint64_t *tkey; uint32_t *tcount; uint64_t *toff; size_t tcap;
     int32_t *postings;
     int indexed_n;
+    const mo_filter *filter; double repeat_weight; int has_filter_cfg;
 };
 
 mo_store *mo_store_new(const mo_sketch_params *p)
@@ -563,6 +761,11 @@ void mo_store_free(mo_store *s)
     free(s);
 }
 
+void mo_store_set_filter(mo_store *s, const mo_filter *f, double repeat_weight)
+{
+    s->filter = f; s->repeat_weight = repeat_weight; s->has_filter_cfg = 1;
+}
+
 static void store_reserve(mo_store *s, int64_t extra)
 {
     if (s->n + extra > s->cap) {
@@ -574,12 +777,12 @@ static void store_reserve(mo_store *s, int64_t extra)
 }
 
 /* SequenceSketch.java:106-116 : returns 0 ok, 1 zero n-grams */
-static int make_sketch(const mo_sketch_params *p, const char *seq, int64_t len, int64_t id, int is_fwd, sketch_t *out)
+static int make_sketch(const mo_sketch_params *p, const mo_filter *filter, double repeat_weight, const char *seq, int64_t len, int64_t id, int is_fwd, sketch_t *out)
 {
     memset(out, 0, sizeof(*out));
     out->id = id; out->is_fwd = is_fwd; out->seq_len = (int32_t)len;
     out->minhash = (int32_t *)malloc(sizeof(int32_t) * (size_t)(p->num_hashes > 0 ? p->num_hashes : 1));
-    if (mo_minhash_sketch(seq, len, p->kmer_size, p->num_hashes, p->unweighted, out->minhash)) {
+    if (mo_minhash_sketch_filtered(seq, len, p->kmer_size, p->num_hashes, repeat_weight, filter, out->minhash)) {
         free(out->minhash); out->minhash = NULL; return 1;
     }
     int64_t no = len - p->ordered_kmer_size + 1;
@@ -594,6 +797,7 @@ static int make_sketch(const mo_sketch_params *p, const char *seq, int64_t len, 
 typedef struct {
     const mo_sketch_params *p; const char *bases; const uint64_t *offsets; const int64_t *ids;
     int64_t n_reads; int both; sketch_t *tmp; uint8_t *ok; int64_t *next; pthread_mutex_t *mu;
+    const mo_filter *filter; double repeat_weight;
 } add_job;
 
 static void *add_worker(void *arg)
@@ -611,12 +815,12 @@ static void *add_worker(void *arg)
         /* FastaData.java:194 upper-cases */
         char *up = (char *)malloc((size_t)len + 1);
         for (int64_t c = 0; c < len; c++) { char ch = seq[c]; up[c] = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch; }
-        if (make_sketch(j->p, up, len, j->ids[i], 1, &j->tmp[per * i]) == 0) {
+        if (make_sketch(j->p, j->filter, j->repeat_weight, up, len, j->ids[i], 1, &j->tmp[per * i]) == 0) {
             j->ok[per * i] = 1;
             if (j->both) {
                 char *r = (char *)malloc((size_t)len + 1);
                 mo_rc(up, len, r); /* Sequence.java:75-78 */
-                if (make_sketch(j->p, r, len, j->ids[i], 0, &j->tmp[per * i + 1]) == 0) j->ok[per * i + 1] = 1;
+                if (make_sketch(j->p, j->filter, j->repeat_weight, r, len, j->ids[i], 0, &j->tmp[per * i + 1]) == 0) j->ok[per * i + 1] = 1;
                 free(r);
             }
         }
@@ -633,7 +837,8 @@ int64_t mo_store_add_reads(mo_store *s, const char *bases, const uint64_t *offse
     uint8_t *ok = (uint8_t *)calloc((size_t)(n_reads * per + 1), 1);
     int64_t next = 0;
     pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
-    add_job job = { &s->p, bases, offsets, ids, n_reads, both_strands, tmp, ok, &next, &mu };
+    add_job job = { &s->p, bases, offsets, ids, n_reads, both_strands, tmp, ok, &next, &mu,
+                    s->filter, s->has_filter_cfg ? s->repeat_weight : (s->p.unweighted ? -1.0 : 0.9) };
     if (threads < 1) threads = 1;
     if (threads == 1) add_worker(&job);
     else {

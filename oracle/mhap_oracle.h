@@ -45,6 +45,32 @@ int64_t mo_kmer_hashes_int(const char *seq, int64_t len, int k, int canonical, i
 int mo_minhash_sketch(const char *seq, int64_t len, int k, int num_hashes, int unweighted,
                       int32_t *out_hashes);
 
+/* ---- the -f k-mer filter (sketch/FrequencyCounts.java:63-320) --------------------------- */
+/* Guava 19.0 BloomFilter (create(funnel putLong, expectedInsertions, 1e-5), strategy MURMUR128_MITZ_64) is a
+ * further un-vendored dependency, restated from its published algorithm for --supress-noise 1/2. */
+typedef struct mo_filter mo_filter;
+typedef struct {
+    double  filter_cutoff;   /* --filter-threshold (1e-5), FrequencyCounts ctor :63 */
+    double  offset;          /* main/MhapMain.java:348-350: repeatWeight when 0<=repeatWeight<1, else 0 */
+    double  range;           /* --repeat-idf-scale (3.0) */
+    int32_t remove_unique;   /* --supress-noise 0/1/2 */
+    int32_t no_tf;           /* --no-tf */
+    int32_t canonical;       /* doReverseCompliment = !--no-rc (filter k-mers ARE canonicalised, reads are not) */
+} mo_filter_params;
+/* text = the whole filter file: first line "<sizeBloom> <sizeRepeat>", then "<k-mer> <fraction> [..]" lines. */
+mo_filter *mo_filter_parse(const char *text, int64_t len, const mo_filter_params *p);
+void       mo_filter_free(mo_filter *f);
+int64_t    mo_filter_size(const mo_filter *f);                           /* entries with fraction >= cutoff */
+double     mo_filter_max_value(const mo_filter *f);
+int64_t    mo_filter_export(const mo_filter *f, int64_t *hashes, double *fractions);   /* the map, any order */
+int64_t    mo_filter_bloom_export(const mo_filter *f, const uint64_t **words, int32_t *num_hash_functions); /* returns bit size (0 = none) */
+int        mo_filter_is_popular(const mo_filter *f, int64_t hash);      /* :262 */
+int        mo_filter_keep_kmer(const mo_filter *f, int64_t hash);       /* :267 */
+double     mo_filter_scaled_idf(const mo_filter *f, int64_t hash);      /* :285-309 */
+/* sketch/MinHashSketch.java:51-179 with a filter (f may be NULL) and the full repeatWeight semantics. */
+int mo_minhash_sketch_filtered(const char *seq, int64_t len, int k, int num_hashes, double repeat_weight,
+                               const mo_filter *f, int32_t *out_hashes);
+
 /* sketch/BottomOverlapSketch.java:525-559.  out_hash_pos = [n][2]; returns n (or -1 zero n-grams),
  * *seq_len_kmers = len-ok+1. */
 int32_t mo_bottom_sketch(const char *seq, int64_t len, int ok, int sketch_size,
@@ -102,6 +128,8 @@ typedef struct {
 
 mo_store *mo_store_new(const mo_sketch_params *p);
 void      mo_store_free(mo_store *s);
+/* sketches added afterwards use the filter and repeat_weight (the store does not own f). */
+void      mo_store_set_filter(mo_store *s, const mo_filter *f, double repeat_weight);
 /* Sketch reads (concatenated ASCII, offsets[n+1]); ids[i] = header id.  both_strands: fwd then rc
  * per read (SequenceSketchStreamer.java:123-156).  Reads shorter than min_olap_length are skipped.
  * threads>1 splits reads over a pthread pool.  Returns number of sketches appended. */

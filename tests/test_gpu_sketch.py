@@ -57,6 +57,15 @@ def test_other_kmer_sizes_and_hash_counts(k, ok, H):
     check_sketch_parity(reads, k=k, H=H, ok=ok, S=64, min_olap=0)
 
 
+def test_every_tiny_length():
+    # every strand length from below k up to a few hundred: the dedup table is fitted per strand, so its capacity
+    # crosses every small value (a table smaller than the largest probe stride once indexed out of bounds)
+    rng = random.Random(5)
+    reads = [rand_seq(rng, n) for n in range(10, 330)]
+    check_sketch_parity(reads, H=32, S=64, min_olap=0, both=False)
+    check_sketch_parity(reads, H=32, S=64, min_olap=0, both=False, unweighted=True)
+
+
 def test_homopolymer_and_tandem_repeat_reads():
     # weights in the hundreds (tf weighting, MinHashSketch.java:98-125) and ordered hashes that all tie
     reads = ["A" * 400, "AC" * 300, "ACG" * 250 + "T" * 50, "ACGTTGCA" * 100 + "N" * 30 + "ACGTTGCA" * 20]

@@ -1,0 +1,148 @@
+#!/usr/bin/env python3
+"""Generate mhap_b200/csrc/bs_step.cuh: one XORShift step (MinHashSketch.java:140-143, x ^= x<<21; x ^= x>>>35;
+x ^= x<<4) on 64 bit planes as a straight-line program of THREE-input XORs (one LOP3 each).
+
+The plain plane form is 43 + 29 + 60 = 132 two-input XORs.  With a = x^(x<<21), b = a^(a>>>35), c = b^(b<<4):
+  * an intermediate with two terms can stay implicit when every consumer still has <= 3 terms, and
+  * c_i = a_i ^ a_{i-4} ^ c_{i+35} for 4 <= i <= 28 (because a_{i+35} ^ a_{i+31} is exactly c_{i+35}), which
+    removes most of the b stage.
+Which nodes stay implicit / which c_i use the identity is a small combinatorial search (simulated annealing,
+`--search`); the best assignment found (92 gates) is baked in below so the header is reproducible.
+The generated program is checked against the scalar recurrence before it is written.
+
+usage: gen_bs_step.py [--search [seed]] > mhap_b200/csrc/bs_step.cuh
+"""
+import math, random, re, sys
+
+# best assignment found by --search (92 gates)
+impl = [('a', 28), ('a', 29), ('a', 30), ('a', 31), ('a', 36), ('a', 37), ('a', 38), ('a', 39), ('a', 44), ('a', 45), ('a', 46), ('a', 47), ('a', 52), ('a', 53), ('a', 54), ('a', 55), ('a', 60), ('a', 61), ('a', 62), ('a', 63), ('b', 0), ('b', 1), ('b', 5), ('b', 7), ('b', 8), ('b', 9), ('b', 10), ('b', 12), ('b', 13), ('b', 15), ('b', 16), ('b', 18), ('b', 19), ('b', 21), ('b', 22), ('b', 24), ('b', 26), ('b', 28)]
+f2 = [4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28]
+
+def evaluate(impl, f2):
+    need = set(); cost = 0
+    def A(i):
+        if i < 21: return [('x', i)]
+        if ('a', i) in impl: return [('x', i), ('x', i-21)]
+        need.add(('a', i)); return [('a', i)]
+    def Bt(i):
+        if i > 28: return A(i)
+        if ('b', i) in impl: return A(i) + A(i+35)
+        need.add(('b', i)); return [('b', i)]
+    ct = lambda n: 0 if n <= 1 else n // 2
+    for i in range(64):
+        if i < 4:
+            if ('b', i) in impl: cost += ct(len(Bt(i)))
+            else: need.add(('b', i))
+        elif i <= 28 and i in f2:
+            cost += ct(len(A(i) + A(i-4)) + 1)
+        else:
+            cost += ct(len(Bt(i) + Bt(i-4)))
+    done = set()
+    while need - done:
+        n = (need - done).pop(); done.add(n)
+        k, i = n
+        if k == 'a': cost += 1
+        else: cost += ct(len(A(i) + A(i+35)))
+    return cost
+
+
+def search(seed):
+    nodes = [('a', i) for i in range(21, 64)] + [('b', i) for i in range(0, 29)] + [('f', i) for i in range(4, 29)]
+    best = None
+    random.seed(seed)
+    for restart in range(24):
+        impl = set(); f2 = set(range(4, 29)) if restart % 2 else set(); cur = evaluate(impl, f2); T = 1.0
+        for it in range(30000):
+            n = random.choice(nodes)
+            if n[0] == 'f': f2 ^= {n[1]}
+            else: impl ^= {n}
+            new = evaluate(impl, f2)
+            if new <= cur or random.random() < math.exp((cur - new) / T): cur = new
+            else:
+                if n[0] == 'f': f2 ^= {n[1]}
+                else: impl ^= {n}
+            T = max(0.05, T * 0.9998)
+            if best is None or cur < best[0]: best = (cur, set(impl), set(f2))
+        print(restart, cur, best[0], file=sys.stderr)
+    return best
+
+
+def generate(impl, f2):
+    lines = []; defined = {}; tmpn = [0]
+    def sym(t):
+        k, i = t
+        return f"R[{i}]" if k == 'x' else f"{k}{i}"
+    def A(i):
+        if i < 21: return [('x', i)]
+        if ('a', i) in impl: return [('x', i), ('x', i-21)]
+        ensure(('a', i)); return [('a', i)]
+    def Bt(i):
+        if i > 28: return A(i)
+        if ('b', i) in impl: return A(i) + A(i+35)
+        ensure(('b', i)); return [('b', i)]
+    def emit(name, terms):
+        terms = [sym(t) for t in terms]
+        while len(terms) > 3:
+            t = f"t{tmpn[0]}"; tmpn[0] += 1
+            lines.append(f"const uint32_t {t} = {terms[0]} ^ {terms[1]} ^ {terms[2]};"); terms = [t] + terms[3:]
+        lines.append(f"const uint32_t {name} = {' ^ '.join(terms)};")
+    def ensure(n):
+        if n in defined: return
+        defined[n] = 1
+        k, i = n
+        if k == 'a': emit(f"a{i}", [('x', i), ('x', i-21)])
+        else: emit(f"b{i}", A(i) + A(i+35))
+    def ensure_c(i):
+        if ('c', i) in defined: return
+        defined[('c', i)] = 1
+        if i < 4:
+            if ('b', i) in impl: emit(f"c{i}", Bt(i))
+            else:
+                ensure(('b', i)); lines.append(f"const uint32_t c{i} = b{i};")
+        elif i <= 28 and i in f2:
+            ensure_c(i + 35)
+            emit(f"c{i}", A(i) + A(i-4) + [('c', i+35)])
+        else:
+            emit(f"c{i}", Bt(i) + Bt(i-4))
+    for i in range(63, -1, -1): ensure_c(i)
+    return lines
+
+
+def check(lines):
+    M = (1 << 64) - 1
+    rnd = random.Random(7)
+    for _ in range(500):
+        x = rnd.getrandbits(64)
+        R = [(x >> i) & 1 for i in range(64)]
+        env = {}
+        for line in lines:
+            m = re.match(r'const uint32_t (\w+) = (.*);', line)
+            env[m.group(1)] = eval(m.group(2), {}, dict(env, R=R))
+        y = sum(env[f'c{i}'] << i for i in range(64))
+        r = x; r ^= (r << 21) & M; r ^= r >> 35; r ^= (r << 4) & M
+        assert y == r
+
+
+def main():
+    global impl, f2
+    if len(sys.argv) > 1 and sys.argv[1] == '--search':
+        cost, impl, f2 = search(int(sys.argv[2]) if len(sys.argv) > 2 else 3)
+        print("found", cost, file=sys.stderr)
+    impl_s, f2_s = set(impl), set(f2)
+    lines = generate(impl_s, f2_s)
+    check(lines)
+    nops = sum('^' in l for l in lines)
+    assert nops == evaluate(impl_s, f2_s)
+    print("// bs_step.cuh -- GENERATED by tools/gen_bs_step.py, do not edit.")
+    print(f"// One XORShift step (MinHashSketch.java:140-143) of 32 bit-sliced chains: R[i] = bit i of 32 chain states.")
+    print(f"// {nops} three-input XORs (one LOP3 each) instead of the 132 two-input XORs of the plain plane form;")
+    print("// checked against the scalar recurrence by the generator and by tools/ubench_bitslice.cu.")
+    print("#pragma once\n#include <cstdint>\n")
+    print("__device__ __forceinline__ void bs_step(uint32_t (&R)[64])\n{")
+    for l in lines: print("    " + l)
+    for j in range(0, 64, 8): print("    " + " ".join(f"R[{i}] = c{i};" for i in range(j, j + 8)))
+    print("}")
+
+
+if __name__ == '__main__':
+    main()
