@@ -526,12 +526,12 @@ __device__ __forceinline__ uint32_t bs_depth_of(uint32_t hi_signed)
 }
 
 // Prefix filter of the lock-step kernel: bit c of the result is set when chain c's sign-biased value has its top
-// `depth` bits all zero (and the lane holds a real bundle).  depth is warp-uniform, 0..kBsMaxDepth.  Written in PTX
+// `depth` bits all zero.  depth is warp-uniform, 0..kBsMaxDepth.  Written in PTX
 // so that it is ONE indexed branch (brx.idx -> BRX through a table) into one of two pure fall-through chains that
 // OR two planes per LOP3 -- even depths pair (63,62),(61,60),.., odd depths pair (62,61),(60,59),.. and fold plane 63
 // into the last LOP3 -- so depth d costs ceil(d/2)+1 LOP3.  (The C++ switch of the same shape is compiled to a
 // compare/branch tree: ~12 extra alu-pipe instructions per word step.)
-__device__ __forceinline__ uint32_t bs_prefix_filter(const uint32_t (&R)[64], uint32_t depth, uint32_t vmask)
+__device__ __forceinline__ uint32_t bs_prefix_filter(const uint32_t (&R)[64], uint32_t depth)
 {
     uint32_t cand;
     asm volatile(
@@ -553,7 +553,7 @@ __device__ __forceinline__ uint32_t bs_prefix_filter(const uint32_t (&R)[64], ui
         "bsf_d6: lop3.b32 o, %23, %24, o, 0xFE;\n\t"   // R58 | R59
         "bsf_d4: lop3.b32 o, %25, %26, o, 0xFE;\n\t"   // R60 | R61
         "bsf_d2: lop3.b32 o, %27, %28, o, 0xFB;\n\t"   // R62 | ~R63
-        "bsf_d0: lop3.b32 %0, o, %2, 0, 0x0C;\n\t"   // ~o & vmask
+        "bsf_d0: not.b32 %0, o;\n\t"   // depth 0 (minimum still Long.MAX_VALUE): every chain is a candidate
         "bra.uni bsf_end;\n\t"
         "bsf_d25: lop3.b32 o, %4, %5, o, 0xFE;\n\t"   // R39 | R40
         "bsf_d23: lop3.b32 o, %6, %7, o, 0xFE;\n\t"   // R41 | R42
@@ -567,11 +567,11 @@ __device__ __forceinline__ uint32_t bs_prefix_filter(const uint32_t (&R)[64], ui
         "bsf_d7: lop3.b32 o, %22, %23, o, 0xFE;\n\t"   // R57 | R58
         "bsf_d5: lop3.b32 o, %24, %25, o, 0xFE;\n\t"   // R59 | R60
         "bsf_d3: lop3.b32 o, %26, %27, o, 0xFE;\n\t"   // R61 | R62
-        "bsf_d1: lop3.b32 %0, o, %28, %2, 0x08;\n\t"   // ~o & R63 & vmask
+        "bsf_d1: lop3.b32 %0, o, %28, 0, 0x0C;\n\t"   // ~o & R63
         "bsf_end:\n\t"
         "}"
         : "=r"(cand)
-        : "r"(depth), "r"(vmask),
+        : "r"(depth), "r"(0),
           "r"(R[38]), "r"(R[39]), "r"(R[40]), "r"(R[41]), "r"(R[42]), "r"(R[43]), "r"(R[44]), "r"(R[45]), "r"(R[46]), "r"(R[47]),
           "r"(R[48]), "r"(R[49]), "r"(R[50]), "r"(R[51]), "r"(R[52]), "r"(R[53]), "r"(R[54]), "r"(R[55]), "r"(R[56]), "r"(R[57]),
           "r"(R[58]), "r"(R[59]), "r"(R[60]), "r"(R[61]), "r"(R[62]), "r"(R[63]));
@@ -588,9 +588,8 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
     for (int r0 = 0; r0 < nb; r0 += 32) {
         const int bi = r0 + lane;
         const bool valid = bi < nb;
-        const uint32_t vmask = valid ? ~0u : 0u;
-        {   // load this lane's 32 keys and transpose them into bit planes (low words, then high words)
-            const uint64_t *kp = keys + (size_t)(valid ? bi : 0) * 32;
+        if (valid) {   // load this lane's 32 keys and transpose them into bit planes (low words, then high words)
+            const uint64_t *kp = keys + (size_t)bi * 32;
             uint32_t w[32];
 #pragma unroll
             for (int c = 0; c < 32; c++) w[c] = (uint32_t)kp[c];
@@ -602,12 +601,22 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
             transpose32(w);
 #pragma unroll
             for (int pbit = 0; pbit < 32; pbit++) R[32 + pbit] = w[31 - pbit];
+        } else {
+            // a lane without a bundle carries 32 all-zero chains: 0 is a fixed point of the XORShift map and, sign-biased,
+            // has its top bit set, so these chains pass no prefix filter of depth >= 1 and need no mask on the hot path
+            // (depth 0 flags everything; the rare path below drops them)
+#pragma unroll
+            for (int i = 0; i < 64; i++) R[i] = 0;
         }
+        // the word loop carries a shared-window address and a countdown instead of (base + 4*wd, wd < H): written as C
+        // the compiler re-derives the base from %tid every iteration (three S2R and six integer ops per word step)
+        uint32_t daddr = (uint32_t)__cvta_generic_to_shared(st.depth);
 #pragma unroll 1
-        for (int wd = 0; wd < H; wd++) {
+        for (int left = H; left > 0; left--, daddr += 4) {
             bs_step(R);
             // chains whose sign-biased value has its top `depth` bits all zero (warp-uniform depth)
             uint32_t cand;
+            const int wd = H - left;
             if constexpr (!PAIRED) {
             uint32_t o = 0;
             switch (st.depth[wd]) {
@@ -639,10 +648,14 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
             case 1: o |= ~R[63];
             default: break;
             }
-            cand = valid ? ~o : 0u;
+            cand = ~o;
             } else {
-                cand = bs_prefix_filter(R, st.depth[wd], vmask);
+                uint32_t depth;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(depth) : "r"(daddr) : "memory");
+                cand = bs_prefix_filter(R, depth);
             }
+            if (__any_sync(kFull, cand != 0)) {
+            if (!valid) cand = 0;
             unsigned evm = __ballot_sync(kFull, cand != 0);
             while (evm) {                               // warp-uniform
                 const int L = __ffs(evm) - 1;
@@ -689,6 +702,7 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
                     }
                 }
                 __syncwarp();
+            }
             }
         }
     }

@@ -35,6 +35,11 @@ class SketchParams(C.Structure):
                 ("ordered_sketch_size", C.c_int32), ("unweighted", C.c_int32), ("min_olap_length", C.c_int32)]
 
 
+class FilterParams(C.Structure):
+    _fields_ = [("filter_cutoff", C.c_double), ("offset", C.c_double), ("range", C.c_double),
+                ("remove_unique", C.c_int32), ("no_tf", C.c_int32), ("canonical", C.c_int32)]
+
+
 class SearchParams(C.Structure):
     _fields_ = [("num_min_matches", C.c_int32), ("min_store_length", C.c_int32), ("max_shift", C.c_double),
                 ("accept_score", C.c_double)]
@@ -76,6 +81,25 @@ def lib():
         L.mo_kmer_hashes_int.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         L.mo_kmer_hashes_int.restype = C.c_int64
         L.mo_minhash_sketch.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.mo_filter_parse.argtypes = [C.c_char_p, C.c_int64, C.POINTER(FilterParams)]
+        L.mo_filter_parse.restype = C.c_void_p
+        L.mo_filter_free.argtypes = [C.c_void_p]
+        L.mo_filter_free.restype = None
+        L.mo_filter_size.argtypes = [C.c_void_p]
+        L.mo_filter_size.restype = C.c_int64
+        L.mo_filter_max_value.argtypes = [C.c_void_p]
+        L.mo_filter_max_value.restype = C.c_double
+        L.mo_filter_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mo_filter_export.restype = C.c_int64
+        L.mo_filter_bloom_export.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+        L.mo_filter_bloom_export.restype = C.c_int64
+        L.mo_filter_is_popular.argtypes = [C.c_void_p, C.c_int64]
+        L.mo_filter_keep_kmer.argtypes = [C.c_void_p, C.c_int64]
+        L.mo_filter_scaled_idf.argtypes = [C.c_void_p, C.c_int64]
+        L.mo_filter_scaled_idf.restype = C.c_double
+        L.mo_minhash_sketch_filtered.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.mo_store_set_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        L.mo_store_set_filter.restype = None
         L.mo_bottom_sketch.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32)]
         L.mo_bottom_sketch.restype = C.c_int32
         L.mo_overlap_info.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int,
@@ -164,6 +188,71 @@ def minhash_sketch(seq, k: int, num_hashes: int, unweighted: bool = False):
     return None if st else out
 
 
+class KmerFilter:
+    """FrequencyCounts (sketch/FrequencyCounts.java) built from the text of a -f filter file.
+
+    offset follows main/MhapMain.java:348-350: repeat_weight when 0 <= repeat_weight < 1, else 0."""
+
+    def __init__(self, text, repeat_weight=0.9, filter_cutoff=1.0e-5, idf_scale=3.0, supress_noise=0, no_tf=False, canonical=True):
+        t = _b(text)
+        self.repeat_weight = float(repeat_weight)
+        offset = self.repeat_weight if 0.0 <= self.repeat_weight < 1.0 else 0.0
+        self.params = FilterParams(filter_cutoff, offset, idf_scale, supress_noise, int(no_tf), int(canonical))
+        self._h = lib().mo_filter_parse(t, len(t), C.byref(self.params))
+
+    def close(self):
+        if self._h:
+            lib().mo_filter_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib().mo_filter_size(self._h))
+
+    @property
+    def max_value(self):
+        return float(lib().mo_filter_max_value(self._h))
+
+    def export(self):
+        """(int64 hashes, float64 fractions) of the repeat map."""
+        n = len(self)
+        h = np.zeros(max(n, 1), dtype=np.int64); f = np.zeros(max(n, 1), dtype=np.float64)
+        lib().mo_filter_export(self._h, h.ctypes.data, f.ctypes.data)
+        return h[:n], f[:n]
+
+    def bloom(self):
+        """(uint64 words, bit_size, num_hash_functions) of the Guava-layout Bloom filter, or (None, 0, 0)."""
+        w = C.c_void_p(); nh = C.c_int32()
+        bits = int(lib().mo_filter_bloom_export(self._h, C.byref(w), C.byref(nh)))
+        if not bits:
+            return None, 0, 0
+        words = np.ctypeslib.as_array(C.cast(w, C.POINTER(C.c_uint64)), shape=(bits // 64,)).copy()
+        return words, bits, int(nh.value)
+
+    def is_popular(self, h):
+        return bool(lib().mo_filter_is_popular(self._h, int(h)))
+
+    def keep_kmer(self, h):
+        return bool(lib().mo_filter_keep_kmer(self._h, int(h)))
+
+    def scaled_idf(self, h):
+        return float(lib().mo_filter_scaled_idf(self._h, int(h)))
+
+
+def minhash_sketch_filtered(seq, k: int, num_hashes: int, repeat_weight: float = 0.9, kmer_filter: "KmerFilter | None" = None):
+    """MinHashSketch.java:51-179 with the -f filter; None when the reference would throw ZeroNGramsFoundException."""
+    s = _b(seq)
+    out = np.zeros(max(1, num_hashes), dtype=np.int32)
+    st = lib().mo_minhash_sketch_filtered(s, len(s), k, num_hashes, float(repeat_weight), kmer_filter._h if kmer_filter else None,
+                                          out.ctypes.data)
+    return None if st else out
+
+
 def bottom_sketch(seq, ok: int, sketch_size: int):
     """Returns (int32[n,2] (hash,pos), seq_len_kmers) or (None, seq_len_kmers)."""
     s = _b(seq)
@@ -221,6 +310,11 @@ class Store:
             self.close()
         except Exception:
             pass
+
+    def set_filter(self, kmer_filter: "KmerFilter | None", repeat_weight: float = 0.9):
+        """Sketches added afterwards use the -f filter and the full --repeat-weight semantics."""
+        self._filter = kmer_filter   # keep it alive
+        lib().mo_store_set_filter(self._h, kmer_filter._h if kmer_filter else None, float(repeat_weight))
 
     def add_reads(self, bases: np.ndarray, offsets: np.ndarray, ids=None, both_strands=True, threads=1, id_offset=0) -> int:
         bases = np.ascontiguousarray(bases, dtype=np.uint8)

@@ -130,6 +130,124 @@ def minhash_sketch(seq: str, k: int, H: int, unweighted: bool = False):  # sketc
     return out
 
 
+class FrequencyCounts:  # sketch/FrequencyCounts.java:63-320
+    """The -f k-mer filter, written from the Java source independently of mhap_oracle.c.
+
+    The Bloom filter follows Guava 19.0's published BloomFilter.create / BloomFilterStrategies.MURMUR128_MITZ_64."""
+
+    def __init__(self, text: str, filter_cutoff=1.0e-5, offset=0.0, remove_unique=0, no_tf=False, range_=3.0, canonical=True):
+        self.cutoff, self.offset, self.remove_unique, self.no_tf, self.range = filter_cutoff, offset, remove_unique, no_tf, range_
+        lines = text.split("\n")
+        first = lines[0].strip().split() if lines and lines[0].strip() else []
+        size_bloom = int(first[0]) if first else 1
+        if size_bloom == 0:
+            size_bloom = 1
+        self.fraction = {}
+        self.max_value = -math.inf
+        self.bits = None
+        if remove_unique > 0:
+            nbits = int(-size_bloom * math.log(1.0e-5) / (math.log(2) * math.log(2)))   # optimalNumOfBits
+            self.nfun = max(1, _jround(nbits / size_bloom * math.log(2)))                 # optimalNumOfHashFunctions
+            self.bit_size = max(1, -(-nbits // 64)) * 64
+            self.bits = bytearray(self.bit_size // 8)
+        for line in lines[1:]:
+            tok = line.split(None, 2) if not line[:1].isspace() else [""]   # Java split keeps a leading empty token
+            if not tok or not tok[0]:
+                continue
+            kmer = tok[0]
+            if canonical:                                                  # HashUtils.java:246-251
+                r = rc(kmer) if kmer == kmer.upper() else "".join(_COMP.get(c, c) for c in reversed(kmer))
+                if r < kmer:
+                    kmer = r
+            h = _s64(murmur3_x64_128(_utf16(kmer), 0)[0])
+            if len(tok) >= 2:
+                try:
+                    pct = float(tok[1])
+                except ValueError:
+                    continue
+                if pct >= filter_cutoff:
+                    self.max_value = max(self.max_value, pct)
+                    self.fraction[h] = pct
+            if self.bits is not None:
+                for bit in self._bloom_bits(h):
+                    self.bits[bit >> 3] |= 1 << (bit & 7)
+        self.min_value = filter_cutoff
+        self.min_idf = self._idf(self.max_value)
+        self.max_idf = self._idf(self.min_value)
+
+    def _idf(self, freq):
+        try:
+            return math.log(self.max_value / freq - self.offset)
+        except (ValueError, ZeroDivisionError):
+            return math.nan
+
+    def _bloom_bits(self, h):
+        h1, h2 = murmur3_x64_128((h & M64).to_bytes(8, "little"), 0)
+        c = h1
+        for _ in range(self.nfun):
+            yield (c & ((1 << 63) - 1)) % self.bit_size
+            c = (c + h2) & M64
+
+    def might_contain(self, h):
+        return all(self.bits[b >> 3] >> (b & 7) & 1 for b in self._bloom_bits(h))
+
+    def keep_kmer(self, h):
+        return self.might_contain(h) if self.remove_unique == 1 else True
+
+    def is_popular(self, h):
+        return h in self.fraction
+
+    def scaled_idf(self, h):
+        if self.remove_unique == 2 and self.bits is not None and not self.might_contain(h):
+            return 1.0
+        if h not in self.fraction:
+            return self.range
+        idf = self._idf(self.fraction[h])
+        d = self.range - 1.0
+        scale = (self.max_idf - self.min_idf) / d if d != 0.0 else math.inf
+        return 1.0 + (idf - self.min_idf) / scale if scale != 0.0 else math.nan
+
+
+def minhash_sketch_filtered(seq: str, k: int, H: int, repeat_weight: float, fc: "FrequencyCounts | None"):
+    """sketch/MinHashSketch.java:51-179 with kmerFilter != null paths."""
+    if len(seq) - k + 1 < 1:
+        return None
+    counts = {}
+    for h in kmer_hashes_long(seq, k):
+        if fc is not None and not fc.keep_kmer(h):
+            continue
+        counts[h] = counts.get(h, 0) + 1
+    if not counts:
+        return None
+    best = [(1 << 63) - 1] * H
+    out = [0] * max(1, H)
+    valid = 0
+    for key, cnt in counts.items():
+        w = cnt
+        if repeat_weight < 0.0:
+            w = 0 if (fc is not None and fc.is_popular(key)) else 1
+        elif fc is not None and 0.0 <= repeat_weight < 1.0:
+            tf = 1.0 if fc.no_tf else float(cnt)
+            v = tf * fc.scaled_idf(key)
+            w = 0 if v != v else _jround(v)
+            if w < 1:
+                w = 1
+        if w <= 0:
+            continue
+        valid += 1
+        x = key & M64
+        for word in range(H):
+            for _ in range(w):
+                x ^= (x << 21) & M64
+                x ^= x >> 35
+                x ^= (x << 4) & M64
+                sx = _s64(x)
+                if sx < best[word]:
+                    best[word] = sx
+                    out[word] = _s32(key & M32) if word % 2 == 0 else _s32((key & M64) >> 32)
+    return out if valid > 0 else None
+
+
 def bottom_sketch(seq: str, ok: int, size: int):  # sketch/BottomOverlapSketch.java:525-559
     n = len(seq) - ok + 1
     if n <= 0:

@@ -84,8 +84,9 @@ def generate(impl, f2):
         terms = [sym(t) for t in terms]
         while len(terms) > 3:
             t = f"t{tmpn[0]}"; tmpn[0] += 1
-            lines.append(f"const uint32_t {t} = {terms[0]} ^ {terms[1]} ^ {terms[2]};"); terms = [t] + terms[3:]
-        lines.append(f"const uint32_t {name} = {' ^ '.join(terms)};")
+            lines.append(f"const uint32_t {t} = bs_xor3({terms[0]}, {terms[1]}, {terms[2]});"); terms = [t] + terms[3:]
+        if len(terms) == 3: lines.append(f"const uint32_t {name} = bs_xor3({', '.join(terms)});")
+        else: lines.append(f"const uint32_t {name} = {' ^ '.join(terms)};")
     def ensure(n):
         if n in defined: return
         defined[n] = 1
@@ -117,7 +118,7 @@ def check(lines):
         env = {}
         for line in lines:
             m = re.match(r'const uint32_t (\w+) = (.*);', line)
-            env[m.group(1)] = eval(m.group(2), {}, dict(env, R=R))
+            env[m.group(1)] = eval(m.group(2), {}, dict(env, R=R, bs_xor3=lambda a, b, c: a ^ b ^ c))
         y = sum(env[f'c{i}'] << i for i in range(64))
         r = x; r ^= (r << 21) & M; r ^= r >> 35; r ^= (r << 4) & M
         assert y == r
@@ -131,13 +132,17 @@ def main():
     impl_s, f2_s = set(impl), set(f2)
     lines = generate(impl_s, f2_s)
     check(lines)
-    nops = sum('^' in l for l in lines)
+    nops = sum('^' in l or 'bs_xor3' in l for l in lines)
     assert nops == evaluate(impl_s, f2_s)
     print("// bs_step.cuh -- GENERATED by tools/gen_bs_step.py, do not edit.")
     print(f"// One XORShift step (MinHashSketch.java:140-143) of 32 bit-sliced chains: R[i] = bit i of 32 chain states.")
     print(f"// {nops} three-input XORs (one LOP3 each) instead of the 132 two-input XORs of the plain plane form;")
     print("// checked against the scalar recurrence by the generator and by tools/ubench_bitslice.cu.")
     print("#pragma once\n#include <cstdint>\n")
+    print("// a ^ b ^ c as ONE lop3 (LUT 0x96).  Inline PTX on purpose: written as C, nvcc re-associates the three-input")
+    print("// XORs to share two-input sub-terms and the step comes out at ~117 LOP3 again (counted in SASS).")
+    print("__device__ __forceinline__ uint32_t bs_xor3(uint32_t a, uint32_t b, uint32_t c)")
+    print('{\n    uint32_t d;\n    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));\n    return d;\n}\n')
     print("__device__ __forceinline__ void bs_step(uint32_t (&R)[64])\n{")
     for l in lines: print("    " + l)
     for j in range(0, 64, 8): print("    " + " ".join(f"R[{i}] = c{i};" for i in range(j, j + 8)))
