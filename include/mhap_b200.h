@@ -118,6 +118,41 @@ void mhapb_host_free(void *p);
 int  mhapb_xorshift_peaks(mhapb_ctx *ctx, double *scalar_steps_per_s, double *bitsliced_steps_per_s);
 int  mhapb_xorshift_peak(mhapb_ctx *ctx, double *steps_per_s);
 
+/* ---- the -f k-mer filter -------------------------------------------------------------------
+ * Replaces sketch/FrequencyCounts.java:63-320 (built by main/MhapMain.java:340-372 from the -f file) and the weight
+ * rule it feeds, sketch/MinHashSketch.java:66-130:
+ *   repeat_weight < 0        weight 1, k-mers present in the repeat map are dropped           (:101-107)
+ *   0 <= repeat_weight < 1   weight = max(1, round(tf * scaledIdf(k-mer))), offset = repeat_weight  (:109-124)
+ *   repeat_weight >= 1       weight = tf (the filter only acts through --supress-noise 1)
+ *   supress_noise 1          k-mers not in the file are removed before counting (keepKmer, :70-71)
+ *   supress_noise 2          k-mers not in the file get idf 1 (FrequencyCounts.java:292-293)
+ * The filter belongs to the context and applies to every later sketching call (mhapb_sketch*, mhapb_store_add_reads,
+ * mhapb_search_query_reads) until mhapb_filter_clear; those calls must pass unweighted = (repeat_weight < 0).
+ * With a filter a strand can lose all its k-mers (ZeroNGramsFoundException, MinHashSketch.java:84,156): status 1 when
+ * the forward strand is empty (the read is skipped, impl/SequenceSketchStreamer.java:225-240), status 3 when only the
+ * reverse strand is (the forward sketch alone is kept).
+ * The membership test of --supress-noise is Guava 19.0's BloomFilter (create(funnel putLong, n, 1e-5), strategy
+ * MURMUR128_MITZ_64), an un-vendored dependency restated from its published algorithm. */
+typedef struct {
+    double  filter_cutoff;     /* --filter-threshold, 1e-5: fractions below it are not repeats */
+    double  repeat_weight;     /* --repeat-weight, 0.9 */
+    double  idf_scale;         /* --repeat-idf-scale, 3.0 (>= 1) */
+    int32_t supress_noise;     /* --supress-noise, 0 */
+    int32_t no_tf;             /* --no-tf */
+} mhapb_filter_params;
+
+/* HashUtils.computeSequenceHashesLong(kmer, kmer.length(), 0, doReverseCompliment)[0] (sketch/HashUtils.java:237-258):
+ * the key the filter file's k-mers are stored under (canonical = !--no-rc; reads themselves are never canonicalised). */
+int mhapb_kmer_hash(const char *kmer, int32_t len, int canonical, int64_t *out_hash);
+/* The state FrequencyCounts' constructor leaves behind: (hash, fraction) pairs of the file (entries below the cutoff
+ * are ignored like :183) and, for supress_noise > 0, the Bloom filter's bit array (bloom_bits a multiple of 64). */
+int mhapb_filter_set(mhapb_ctx *ctx, const mhapb_filter_params *p, const int64_t *hashes, const double *fractions, uint64_t n,
+                     const uint64_t *bloom_words, uint64_t bloom_bits, int32_t bloom_num_hash_functions);
+/* Same from the text of a filter file ("<sizeBloom> <sizeRepeat>" then "<k-mer> <fraction> ..." lines): the parsing
+ * half of the FrequencyCounts constructor.  n_repeat (optional) = entries at or above the cutoff. */
+int mhapb_filter_load_text(mhapb_ctx *ctx, const mhapb_filter_params *p, const char *text, uint64_t len, int canonical, int64_t *n_repeat);
+int mhapb_filter_clear(mhapb_ctx *ctx);
+
 /* ---- K1: sketching ------------------------------------------------------------------------
  * Replaces SequenceSketchStreamer.getSketch (impl/SequenceSketchStreamer.java:262-266) applied
  * to a batch of reads, i.e. new SequenceSketch(seq, k, H, ok, os, filter=null, true, repeatWeight)

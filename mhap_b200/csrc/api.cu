@@ -3,6 +3,7 @@
 // No CPU fallback: every compute entry point launches the kernels in sketch.cu / search.cu.
 #include "../../include/mhap_b200.h"
 #include "engine.h"
+#include "hash.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -13,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -82,6 +84,11 @@ struct mhapb_ctx {
     DevBuf qlist, cand, ovl, cand2, ovl2, ovf_list, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
     Store store;
     cudaEvent_t ev[8]{};
+    // the -f k-mer filter (FrequencyCounts); view.mode == 0 when none is set
+    DevBuf f_keys, f_idf, f_used, f_bloom;
+    KmerFilterView filter{};
+    mhapb_filter_params filter_params{};
+    bool filter_set = false;
 };
 
 namespace {
@@ -129,10 +136,29 @@ bool overlap_k1c()
 
 // Sketch reads whose characters are at d_bases (device).  row_of_slot[slot] (slot = read*per+strand)
 // gives the output row or -1 to skip.  Outputs are device arrays.
+// The weight rule in force for a sketch call: the context's filter (if any) under the call's repeat-weight class.
+// Returns the view by value; light_weight is the weight of a once-seen k-mer outside the repeat map.
+KmerFilterView filter_view(const mhapb_ctx *ctx)
+{
+    KmerFilterView v = ctx->filter;
+    if (!ctx->filter_set) { v = KmerFilterView{}; v.mode = 0; v.light_weight = 1; }
+    return v;
+}
+// k-mers can be dropped (and a strand end up with none: ZeroNGramsFoundException, MinHashSketch.java:84,156)
+bool filter_can_empty(const KmerFilterView &v) { return v.mode == 1 || v.remove_unique == 1; }
+// dup counts are not needed when the weight ignores tf
+int filter_unweighted(const KmerFilterView &v, int unweighted) { return v.mode == 0 ? unweighted : (v.mode == 1 || (v.mode == 2 && v.no_tf)) ? 1 : 0; }
+
+// slot_valid (optional, size n_reads*per): set to 0 for strands whose every k-mer was filtered out.
 int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_bases, const uint64_t *h_offsets,
                 uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
-                int32_t *d_ord, int ord_stride, int32_t *d_ord_n)
+                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid = nullptr)
 {
+    const KmerFilterView flt = filter_view(ctx);
+    if (ctx->filter_set && (ctx->filter_params.repeat_weight < 0.0) != (p.unweighted != 0))
+        return fail(ctx, MHAPB_EINVAL, "sketch params unweighted=%d contradict the filter's repeat_weight %g", p.unweighted, ctx->filter_params.repeat_weight);
+    const bool want_valid = slot_valid && filter_can_empty(flt);
+    std::vector<int32_t> h_nl, h_nh;
     const int per = both ? 2 : 1;
     const int k = p.kmer_size, ok = p.ordered_kmer_size, H = p.num_hashes, S = p.ordered_sketch_size;
     std::vector<StrandDesc> all;
@@ -144,7 +170,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         for (int s = 0; s < per; s++) {
             int64_t row = row_of_slot[(size_t)r * per + s];
             if (row < 0) continue;
-            StrandDesc d; d.base_off = h_offsets[r]; d.koff = 0; d.len = (uint32_t)len; d.row = (uint32_t)row; d.rc = (uint32_t)s; d.pad = 0;
+            StrandDesc d; d.base_off = h_offsets[r]; d.koff = 0; d.len = (uint32_t)len; d.row = (uint32_t)row; d.rc = (uint32_t)s; d.slot = (uint32_t)((size_t)r * per + s);
             all.push_back(d);
         }
     }
@@ -214,8 +240,15 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         // released when K1a is done so that it shares the SMs with the alu-bound K1b instead of the
         // shared-memory-hungry K1a.  K1c is launched first with one CTA per SM, K1b fills the rest.
         ev_new();                                                     // [0] before K1a
-        CU(ctx, launch_hash_dedup(ctx->stream, d_bases, dd, n, first_long, max_k_short, max_k_long, k, p.unweighted, sc, &launches));
+        CU(ctx, launch_hash_dedup(ctx->stream, d_bases, dd, n, first_long, max_k_short, max_k_long, k, filter_unweighted(flt, p.unweighted), flt, sc, &launches));
         ev_new();                                                     // [1] after K1a
+        if (want_valid) {   // which strands kept at least one k-mer
+            h_nl.resize(n); h_nh.resize(n);
+            CU(ctx, cudaMemcpyAsync(h_nl.data(), sc.nlight, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(h_nh.data(), sc.nheavy, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < n; i++) if (h_nl[i] + h_nh[i] == 0) (*slot_valid)[chunk[i].slot] = 0;
+        }
         cudaEvent_t c0 = nullptr, c1 = nullptr;
         const bool overlap = overlap_k1c() && d_ord && d_minhash;
         if (overlap) {
@@ -225,7 +258,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
             CU(ctx, launch_ordered(ctx->stream2, d_bases, dd, n, first_long, max_len_short, max_len_long, ok, S, ord_stride, sc, d_ord, d_ord_n, 1, &launches));
             cudaEventRecord(c1, ctx->stream2);
         }
-        if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n, k, H, sc, d_minhash, &launches));
+        if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n, k, H, sc, d_minhash, flt.light_weight, &launches));
         ev_new();                                                     // [2] after K1b
         if (overlap) {
             CU(ctx, cudaStreamWaitEvent(ctx->stream, c1, 0));         // the next chunk reuses the descriptors
@@ -535,10 +568,25 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
     std::vector<int64_t> rows((size_t)n_reads * per, -1);
     const int64_t n0 = s.n;
     int64_t next = n0;
+    // with a filter that can drop k-mers a strand may be left with none (ZeroNGramsFoundException): a K1a-only pass
+    // finds those before rows are assigned.  Forward strand empty => the read is skipped; only the reverse strand
+    // empty => the forward sketch alone is stored (SequenceSketchStreamer.java:123-156,225-240).
+    std::vector<uint8_t> valid((size_t)n_reads * per, 1);
+    bool bases_on_device = false;
+    if (filter_can_empty(filter_view(ctx)) && n_reads) {
+        std::vector<int64_t> ident((size_t)n_reads * per);
+        for (size_t i = 0; i < ident.size(); i++) ident[i] = (int64_t)i;
+        int rc0 = h2d_bases(ctx, bases, offsets, n_reads);
+        if (rc0) return rc0;
+        bases_on_device = true;
+        rc0 = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, both, ident, nullptr, nullptr, 0, nullptr, &valid);
+        if (rc0) return rc0;
+    }
+    auto strand_kept = [&](uint32_t r, int st) { return valid[(size_t)r * per] && valid[(size_t)r * per + st]; };
     for (uint32_t r = 0; r < n_reads; r++) {
         uint64_t len = offsets[r + 1] - offsets[r];
         if (read_status(s.p, len)) continue;
-        for (int st = 0; st < per; st++) rows[(size_t)r * per + st] = next++;
+        for (int st = 0; st < per; st++) if (strand_kept(r, st)) rows[(size_t)r * per + st] = next++;
     }
     const int64_t added = next - n0;
     if (n_added) *n_added = added;
@@ -549,6 +597,7 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
         uint64_t len = offsets[r + 1] - offsets[r];
         if (read_status(s.p, len)) continue;
         for (int st = 0; st < per; st++) {
+            if (!strand_kept(r, st)) continue;
             int32_t no = (int32_t)len - s.p.ordered_kmer_size + 1;
             int rc = store_push_meta(ctx, ids ? ids[r] : (int64_t)r + 1, st == 0, (int32_t)len, no, std::min(no, s.p.ordered_sketch_size));
             if (rc) {
@@ -560,7 +609,7 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
     }
     int rc = store_reserve(ctx, added);
     if (rc) return rc;
-    rc = h2d_bases(ctx, bases, offsets, n_reads);
+    if (!bases_on_device) rc = h2d_bases(ctx, bases, offsets, n_reads);
     if (rc) return rc;
     const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
     CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)added * S * 8, ctx->stream));
@@ -610,7 +659,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
                       &ctx->counters, &ctx->out_minhash, &ctx->out_ord, &ctx->out_ordn, &ctx->qlist, &ctx->cand, &ctx->ovl, &ctx->cand2, &ctx->ovl2, &ctx->ovf_list, &ctx->fscratch,
                       &ctx->scounters, &ctx->tmp_start, &ctx->block_sums, &ctx->q_minhash, &ctx->q_ord, &ctx->q_ordn, &ctx->q_lenk, &ctx->q_len,
                       &ctx->q_id, &ctx->eq, &ctx->store.minhash, &ctx->store.ord, &ctx->store.ord_n, &ctx->store.lenk, &ctx->store.len,
-                      &ctx->store.id, &ctx->store.slots, &ctx->store.postings};
+                      &ctx->store.id, &ctx->store.slots, &ctx->store.postings, &ctx->f_keys, &ctx->f_idf, &ctx->f_used, &ctx->f_bloom};
     for (auto b : bufs) b->release();
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -694,9 +743,12 @@ int mhapb_sketch_device(mhapb_ctx *ctx, const mhapb_sketch_params *p, const void
     if (d_minhash && slots) CU(ctx, cudaMemsetAsync(d_minhash, 0, slots * H * 4, ctx->stream));
     if (d_ord && slots) CU(ctx, cudaMemsetAsync(d_ord, 0, slots * S * 8, ctx->stream));
     if (d_ord_n && slots) CU(ctx, cudaMemsetAsync(d_ord_n, 0, slots * 4, ctx->stream));
-    if (d_status && n_reads) CU(ctx, cudaMemcpyAsync(d_status, status.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
-    rc = sketch_core(ctx, *p, (const uint8_t *)d_bases, h_offsets, n_reads, both_strands, rows, (int32_t *)d_minhash, (int32_t *)d_ord, (int)S, (int32_t *)d_ord_n);
+    std::vector<uint8_t> valid(slots, 1);
+    rc = sketch_core(ctx, *p, (const uint8_t *)d_bases, h_offsets, n_reads, both_strands, rows, (int32_t *)d_minhash, (int32_t *)d_ord, (int)S, (int32_t *)d_ord_n, &valid);
     if (rc) return rc;
+    for (uint32_t r = 0; r < n_reads; r++)
+        if (!status[r]) status[r] = !valid[(size_t)r * per] ? 1 : (per == 2 && !valid[(size_t)r * per + 1]) ? 3 : 0;
+    if (d_status && n_reads) CU(ctx, cudaMemcpyAsync(d_status, status.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return MHAPB_OK;
 }
@@ -728,10 +780,14 @@ int mhapb_sketch(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases
         CU(ctx, ctx->out_ord.ensure(slots * S * 8)); CU(ctx, cudaMemsetAsync(ctx->out_ord.p, 0, slots * S * 8, ctx->stream));
         CU(ctx, ctx->out_ordn.ensure(slots * 4)); CU(ctx, cudaMemsetAsync(ctx->out_ordn.p, 0, slots * 4, ctx->stream));
     }
+    std::vector<uint8_t> valid(slots, 1);
     rc = sketch_core(ctx, *p, ctx->bases.as<uint8_t>(), offsets, n_reads, both_strands, rows,
                      out_minhash ? ctx->out_minhash.as<int32_t>() : nullptr, want_ord ? ctx->out_ord.as<int32_t>() : nullptr, (int)S,
-                     want_ord ? ctx->out_ordn.as<int32_t>() : nullptr);
+                     want_ord ? ctx->out_ordn.as<int32_t>() : nullptr, &valid);
     if (rc) return rc;
+    if (out_status)
+        for (uint32_t r = 0; r < n_reads; r++)
+            if (!out_status[r]) out_status[r] = !valid[(size_t)r * per] ? 1 : (per == 2 && !valid[(size_t)r * per + 1]) ? 3 : 0;
     cudaEventRecord(ctx->ev[6], ctx->stream);
     if (out_minhash) CU(ctx, cudaMemcpyAsync(out_minhash, ctx->out_minhash.p, slots * H * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_ord) CU(ctx, cudaMemcpyAsync(out_ord, ctx->out_ord.p, slots * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -843,8 +899,8 @@ int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char
     if (rc) return rc;
     uint64_t total = 0; uint32_t nrec = 0;
     for (uint32_t r = 0; r < n_reads; r++) {
-        if (status[r]) continue;
-        for (int s = 0; s < per; s++) {
+        if (status[r] && status[r] != 3) continue;
+        for (int s = 0; s < (status[r] == 3 ? 1 : per); s++) {
             size_t j = (size_t)r * per + s;
             int64_t id = ids ? ids[r] : (int64_t)r + 1;
             total += (uint64_t)mhapb_dat_encode(id, s == 0, nullptr, 0, nullptr, (int32_t)H, 0, 0, nullptr, on[j], nullptr);
@@ -855,9 +911,9 @@ int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char
     if (!buf) return fail(ctx, MHAPB_ENOMEM, "malloc .dat buffer");
     uint8_t *w = buf;
     for (uint32_t r = 0; r < n_reads; r++) {
-        if (status[r]) continue;
+        if (status[r] && status[r] != 3) continue;
         const int32_t len = (int32_t)(offsets[r + 1] - offsets[r]);
-        for (int s = 0; s < per; s++) {
+        for (int s = 0; s < (status[r] == 3 ? 1 : per); s++) {
             size_t j = (size_t)r * per + s;
             int64_t id = ids ? ids[r] : (int64_t)r + 1;
             w += mhapb_dat_encode(id, s == 0, nullptr, len, mh.data() + j * H, (int32_t)H, len - p->ordered_kmer_size + 1,
@@ -1089,9 +1145,20 @@ int mhapb_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, cons
     // forward-only sketches of the valid query reads, compacted
     std::vector<int64_t> rows(n_reads, -1), qid; std::vector<uint8_t> qfwd; std::vector<int32_t> qlen, qlenk;
     int64_t nq = 0;
+    std::vector<uint8_t> valid(n_reads, 1);
+    bool bases_on_device = false;
+    if (filter_can_empty(filter_view(ctx)) && n_reads) {   // see add_reads_locked
+        std::vector<int64_t> ident(n_reads);
+        for (size_t i = 0; i < ident.size(); i++) ident[i] = (int64_t)i;
+        int rc0 = h2d_bases(ctx, bases, offsets, n_reads);
+        if (rc0) return rc0;
+        bases_on_device = true;
+        rc0 = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, 0, ident, nullptr, nullptr, 0, nullptr, &valid);
+        if (rc0) return rc0;
+    }
     for (uint32_t r = 0; r < n_reads; r++) {
         uint64_t len = offsets[r + 1] - offsets[r];
-        if (read_status(s.p, len)) continue;
+        if (read_status(s.p, len) || !valid[r]) continue;
         rows[r] = nq++;
         qid.push_back(ids ? ids[r] : (int64_t)r + 1); qfwd.push_back(1); qlen.push_back((int32_t)len);
         qlenk.push_back((int32_t)len - s.p.ordered_kmer_size + 1);
@@ -1101,7 +1168,7 @@ int mhapb_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, cons
     CU(ctx, ctx->q_ord.ensure((size_t)nq * S * 8 + 8));
     CU(ctx, ctx->q_ordn.ensure((size_t)nq * 4 + 4));
     if (nq) {
-        int rc = h2d_bases(ctx, bases, offsets, n_reads);
+        int rc = bases_on_device ? MHAPB_OK : h2d_bases(ctx, bases, offsets, n_reads);
         if (rc) return rc;
         CU(ctx, cudaMemsetAsync(ctx->q_ord.p, 0, (size_t)nq * S * 8, ctx->stream));
         rc = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, 0, rows, ctx->q_minhash.as<int32_t>(), ctx->q_ord.as<int32_t>(), (int)S, ctx->q_ordn.as<int32_t>());
@@ -1139,6 +1206,182 @@ int mhapb_minhash_equal_count(mhapb_ctx *ctx, int64_t i, int64_t j, int32_t *out
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->timing.kernel_launches += launches;
     return MHAPB_OK;
+}
+
+} // extern "C"
+
+// ---- the -f k-mer filter ----------------------------------------------------------------------
+namespace {
+
+// HashUtils.computeSequenceHashesLong(kmer, kmer.length(), 0, doReverseCompliment)[0] on the host
+uint64_t host_kmer_hash(const char *kmer, int len, int canonical)
+{
+    std::string fwd(kmer, (size_t)len);
+    const std::string *use = &fwd;
+    std::string rc;
+    if (canonical) {                                   // HashUtils.java:246-251: the smaller of k-mer and Utils.rc(k-mer)
+        rc.resize((size_t)len);
+        for (int i = 0; i < len; i++) rc[(size_t)i] = (char)complement_char(upper_char((uint8_t)kmer[len - 1 - i]));
+        if (std::lexicographical_compare(rc.begin(), rc.end(), fwd.begin(), fwd.end(),
+                                         [](char a, char b) { return (unsigned char)a < (unsigned char)b; })) use = &rc;
+    }
+    const std::string &u = *use;
+    return murmur3_128_h1_chars([&](int j) { return (uint8_t)u[(size_t)j]; }, len);
+}
+
+// Installs the filter: scaledIdf per repeat k-mer in double precision (FrequencyCounts.java:223-229,250-254,285-309),
+// an open-addressed device map, and the Bloom bit array.
+int filter_install(mhapb_ctx *ctx, const mhapb_filter_params *p, const int64_t *hashes, const double *fractions, uint64_t n,
+                   const uint64_t *bloom_words, uint64_t bloom_bits, int32_t bloom_nfun)
+{
+    if (!p) return fail(ctx, MHAPB_EINVAL, "null filter params");
+    if (p->supress_noise < 0 || p->supress_noise > 2) return fail(ctx, MHAPB_EINVAL, "The --supress-noise parameter must be in [0,2].");
+    if (p->idf_scale < 1.0) return fail(ctx, MHAPB_EINVAL, "--repeat-idf-scale must be >= 1");
+    if (n && (!hashes || !fractions)) return fail(ctx, MHAPB_EINVAL, "null filter arrays");
+    if (p->supress_noise > 0 && (!bloom_words || bloom_bits == 0 || (bloom_bits & 63) || bloom_nfun < 1))
+        return fail(ctx, MHAPB_EINVAL, "--supress-noise %d needs the Bloom filter bit array", p->supress_noise);
+    const double rw = p->repeat_weight;
+    const double offset = (rw >= 0.0 && rw < 1.0) ? rw : 0.0;                       // MhapMain.java:348-350
+    // fractionCounts: entries at or above the cutoff, a repeated k-mer keeps its last value (Map.put)
+    std::unordered_map<int64_t, double> kept;
+    double max_value = -INFINITY;
+    for (uint64_t i = 0; i < n; i++)
+        if (fractions[i] >= p->filter_cutoff) { kept[hashes[i]] = fractions[i]; if (fractions[i] > max_value) max_value = fractions[i]; }
+    const double min_idf = log(max_value / max_value - offset);                    // idf(maxValue) :228
+    const double max_idf = log(max_value / p->filter_cutoff - offset);              // idf(minValue) :229
+    const double scale = (max_idf - min_idf) / (p->idf_scale - 1.0);
+    size_t cap = 16;
+    while (cap < kept.size() * 2) cap <<= 1;
+    std::vector<uint64_t> keys(cap, 0);
+    std::vector<double> idf(cap, 0.0);
+    std::vector<uint32_t> used(cap / 32, 0u);
+    for (const auto &kv : kept) {
+        const double v = 1.0 + (log(max_value / kv.second - offset) - min_idf) / scale;   // scaledIdf :300-308
+        size_t q = (size_t)fmix64((uint64_t)kv.first) & (cap - 1);
+        while ((used[q >> 5] >> (q & 31)) & 1u) q = (q + 1) & (cap - 1);
+        used[q >> 5] |= 1u << (q & 31); keys[q] = (uint64_t)kv.first; idf[q] = v;
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    KmerFilterView v{};
+    if (!kept.empty()) {
+        CU(ctx, ctx->f_keys.ensure(cap * 8)); CU(ctx, ctx->f_idf.ensure(cap * 8)); CU(ctx, ctx->f_used.ensure(cap / 8));
+        CU(ctx, cudaMemcpy(ctx->f_keys.p, keys.data(), cap * 8, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->f_idf.p, idf.data(), cap * 8, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->f_used.p, used.data(), cap / 8, cudaMemcpyHostToDevice));
+        v.map_keys = ctx->f_keys.as<uint64_t>(); v.map_idf = ctx->f_idf.as<double>(); v.map_used = ctx->f_used.as<uint32_t>();
+        v.map_mask = (uint32_t)(cap - 1);
+    }
+    if (p->supress_noise > 0) {
+        CU(ctx, ctx->f_bloom.ensure(bloom_bits / 8));
+        CU(ctx, cudaMemcpy(ctx->f_bloom.p, bloom_words, bloom_bits / 8, cudaMemcpyHostToDevice));
+        v.bloom = ctx->f_bloom.as<uint64_t>(); v.bloom_bits = bloom_bits; v.bloom_nfun = bloom_nfun;
+    }
+    v.mode = rw < 0.0 ? 1 : (rw < 1.0 ? 2 : 3);
+    v.remove_unique = p->supress_noise;
+    v.no_tf = p->no_tf ? 1 : 0;
+    v.range = p->idf_scale;
+    v.light_weight = 1;
+    if (v.mode == 2) {                                 // weight of a once-seen k-mer outside the repeat map: round(1 * range)
+        const double r = floor(p->idf_scale + 0.5);
+        v.light_weight = r >= 1.0 ? (r > 2147483647.0 ? 2147483647u : (uint32_t)r) : 1u;
+    }
+    ctx->filter = v; ctx->filter_params = *p; ctx->filter_set = true;
+    return MHAPB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int mhapb_kmer_hash(const char *kmer, int32_t len, int canonical, int64_t *out_hash)
+{
+    if (!kmer || len < 1 || !out_hash) return MHAPB_EINVAL;
+    *out_hash = (int64_t)host_kmer_hash(kmer, len, canonical);
+    return MHAPB_OK;
+}
+
+int mhapb_filter_set(mhapb_ctx *ctx, const mhapb_filter_params *p, const int64_t *hashes, const double *fractions, uint64_t n,
+                     const uint64_t *bloom_words, uint64_t bloom_bits, int32_t bloom_num_hash_functions)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return filter_install(ctx, p, hashes, fractions, n, bloom_words, bloom_bits, bloom_num_hash_functions);
+}
+
+int mhapb_filter_clear(mhapb_ctx *ctx)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->filter = KmerFilterView{}; ctx->filter_set = false;
+    return MHAPB_OK;
+}
+
+int mhapb_filter_load_text(mhapb_ctx *ctx, const mhapb_filter_params *p, const char *text, uint64_t len, int canonical, int64_t *n_repeat)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!p || (!text && len)) return fail(ctx, MHAPB_EINVAL, "null filter text/params");
+    if (p->supress_noise < 0 || p->supress_noise > 2) return fail(ctx, MHAPB_EINVAL, "The --supress-noise parameter must be in [0,2].");
+    const char *cur = text, *end = text + len;
+    auto is_ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; };
+    // first line: "<sizeBloom> <sizeRepeat>" (FrequencyCounts.java:91-117)
+    long long size_bloom = 1;
+    {
+        const char *nl = (const char *)memchr(cur, '\n', (size_t)(end - cur));
+        const char *le = nl ? nl : end;
+        if (le > cur) {
+            std::string first(cur, le);
+            long long a = 0, b = 0;
+            if (sscanf(first.c_str(), "%lld %lld", &a, &b) < 2 || a < 0 || b < 0)
+                return fail(ctx, MHAPB_EINVAL, "K-mer filter file first line must contain estimated number of k-mers in the file (long).");
+            size_bloom = a ? a : 1;
+        }
+        cur = nl ? nl + 1 : end;
+    }
+    std::vector<uint64_t> bloom;
+    uint64_t bloom_bits = 0; int32_t nfun = 0;
+    if (p->supress_noise > 0) {
+        // Guava BloomFilter.create(funnel, expectedInsertions, 1e-5): optimalNumOfBits, optimalNumOfHashFunctions, BitArray
+        const double fpp = 1.0e-5;
+        const long long num_bits = (long long)(-(double)size_bloom * log(fpp) / (log(2.0) * log(2.0)));
+        const int nh = (int)floor((double)num_bits / (double)size_bloom * log(2.0) + 0.5);
+        nfun = nh < 1 ? 1 : nh;
+        long long words = (num_bits + 63) / 64;
+        if (words < 1) words = 1;
+        bloom.assign((size_t)words, 0ull);
+        bloom_bits = (uint64_t)words * 64;
+    }
+    std::vector<int64_t> hashes; std::vector<double> fractions;
+    while (cur < end) {
+        const char *nl = (const char *)memchr(cur, '\n', (size_t)(end - cur));
+        const char *le = nl ? nl : end;
+        const char *q = cur;
+        while (q < le && !is_ws(*q)) q++;
+        const int klen = (int)(q - cur);
+        if (klen >= 1) {
+            const uint64_t h = host_kmer_hash(cur, klen, canonical);
+            while (q < le && is_ws(*q)) q++;
+            bool skip = false;
+            if (q < le) {                               // second column: the fraction (:178-193)
+                const char *t = q;
+                while (q < le && !is_ws(*q)) q++;
+                std::string num(t, q);
+                char *ep = nullptr;
+                const double pct = strtod(num.c_str(), &ep);
+                if (ep == num.c_str() || *ep != 0) skip = true;     // NumberFormatException: the line is dropped (:204-207)
+                else if (pct >= p->filter_cutoff) { hashes.push_back((int64_t)h); fractions.push_back(pct); }
+            }
+            if (!skip && p->supress_noise > 0) {        // validMers.put(hash) (:196-200)
+                uint64_t h1, h2; bloom_hash_pair(h, &h1, &h2);
+                uint64_t c = h1;
+                for (int i = 0; i < nfun; i++) { const uint64_t bit = (c & 0x7fffffffffffffffULL) % bloom_bits; bloom[bit >> 6] |= 1ull << (bit & 63); c += h2; }
+            }
+        }
+        cur = nl ? nl + 1 : end;
+    }
+    if (n_repeat) *n_repeat = (int64_t)hashes.size();
+    return filter_install(ctx, p, hashes.data(), fractions.data(), hashes.size(), bloom.empty() ? nullptr : bloom.data(), bloom_bits, nfun);
 }
 
 } // extern "C"

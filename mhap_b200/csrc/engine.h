@@ -12,7 +12,7 @@ struct StrandDesc {
     uint32_t len;        // read length in bases
     uint32_t row;        // output row
     uint32_t rc;         // 1: sketch the reverse complement (Sequence.getReverseCompliment)
-    uint32_t pad;
+    uint32_t slot;       // caller's sketch slot (read * strands + strand), for per-strand status read-back
 };
 
 // ---- K1 ------------------------------------------------------------------------------------
@@ -37,13 +37,35 @@ struct SketchScratch {
     uint32_t *counters;  // work-queue counters
 };
 
-// K1a: hash every k-mer (MurmurHash3_x64_128 h1), de-duplicate with counts.
+// Device view of the -f k-mer filter (sketch/FrequencyCounts.java) and of the weight rule of
+// sketch/MinHashSketch.java:95-130.  mode: 0 no filter (weight = count, or 1 when unweighted),
+// 1 repeatWeight<0 with a filter (weight 1, popular k-mers dropped :101-107), 2 tf-idf (:109-124),
+// 3 repeatWeight>=1 with a filter (tf only).  The map holds scaledIdf(key) (FrequencyCounts.java:285-309)
+// precomputed on the host in double precision; absent keys get `range`.
+struct KmerFilterView {
+    const uint64_t *map_keys;   // open addressing (linear probing), empty slots hold kFilterEmpty with map_used bit clear
+    const double   *map_idf;
+    const uint32_t *map_used;   // bitmap of occupied slots
+    uint32_t map_mask;          // capacity - 1 (power of two); 0 entries => map_keys == nullptr
+    const uint64_t *bloom;      // Guava BloomFilter bit array (LockFreeBitArray words), nullptr when --supress-noise 0
+    uint64_t bloom_bits;
+    int32_t bloom_nfun;
+    int32_t mode;
+    int32_t remove_unique;      // --supress-noise
+    int32_t no_tf;
+    double  range;              // --repeat-idf-scale
+    uint32_t light_weight;      // the weight of a k-mer seen once that is not in the map: keys of this weight are "light"
+};
+
+// K1a: hash every k-mer (MurmurHash3_x64_128 h1), de-duplicate with counts, apply the weight rule.
 cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
                               int first_long /* descs [first_long, n) are long strands */, int max_kmers_short,
-                              int max_kmers_long, int k, int unweighted, const SketchScratch &sc, int *launches);
-// K1b: H-step XORShift chain per distinct k-mer, per-word signed minimum -> minhash rows.
+                              int max_kmers_long, int k, int unweighted, const KmerFilterView &filter,
+                              const SketchScratch &sc, int *launches);
+// K1b: H-step XORShift chain per distinct k-mer (light keys advance light_weight steps per word, heavy keys their
+// own weight), per-word signed minimum -> minhash rows.
 cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
-                           const SketchScratch &sc, int32_t *d_minhash, int *launches);
+                           const SketchScratch &sc, int32_t *d_minhash, uint32_t light_weight, int *launches);
 // K1c: MurmurHash3_x86_32 of every ordered k-mer, bottom-S by (signed hash, position), sorted.
 cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
                            int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,

@@ -66,6 +66,21 @@ __host__ __device__ __forceinline__ uint64_t murmur3_128_h1_chars(const C &ch, i
     return h1;
 }
 
+// Guava 19.0 BloomFilterStrategies.MURMUR128_MITZ_64 hashes a Long through Funnel (v, sink) -> sink.putLong(v):
+// MurmurHash3_x64_128 (seed 0) of the key's 8 little-endian bytes (tail-only input: one k1 lane).
+// hash1 = lower eight bytes (h1), hash2 = upper eight (h2); probe i tests bit ((h1 + i*h2) & Long.MAX_VALUE) % bitSize.
+__host__ __device__ __forceinline__ void bloom_hash_pair(uint64_t key, uint64_t *o1, uint64_t *o2)
+{
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t k1 = key * c1; k1 = rotl64(k1, 31); k1 *= c2;
+    uint64_t h1 = k1, h2 = 0;
+    h1 ^= 8; h2 ^= 8;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+    *o1 = h1; *o2 = h2;
+}
+
 // MurmurHash3_x86_32 (seed 0) over k chars as UTF-16LE.
 template <class C>
 __host__ __device__ __forceinline__ uint32_t murmur3_32_chars(const C &ch, int k)

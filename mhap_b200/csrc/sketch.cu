@@ -60,6 +60,50 @@ __device__ __forceinline__ int warp_alloc(int *counter, bool want)
 }
 
 // ---------------------------------------------------------------------------------------------
+// the -f k-mer filter on the device (sketch/FrequencyCounts.java)
+// ---------------------------------------------------------------------------------------------
+// Guava 19.0 BloomFilterStrategies.MURMUR128_MITZ_64.mightContain (hash pair: hash.cuh bloom_hash_pair)
+__device__ __forceinline__ bool bloom_might_contain(const KmerFilterView &f, uint64_t key)
+{
+    uint64_t h1, h2;
+    bloom_hash_pair(key, &h1, &h2);
+    uint64_t c = h1;
+    for (int i = 0; i < f.bloom_nfun; i++) {
+        const uint64_t bit = (c & 0x7fffffffffffffffULL) % f.bloom_bits;
+        if (!((f.bloom[bit >> 6] >> (bit & 63)) & 1ull)) return false;
+        c += h2;
+    }
+    return true;
+}
+
+// fractionCounts.get(key) turned into scaledIdf on the host; returns false when the key is not a repeat k-mer
+__device__ __forceinline__ bool filter_lookup(const KmerFilterView &f, uint64_t key, double *idf)
+{
+    if (!f.map_keys) return false;
+    uint32_t q = (uint32_t)fmix64(key) & f.map_mask;
+    for (;;) {
+        if (!((f.map_used[q >> 5] >> (q & 31)) & 1u)) return false;
+        if (f.map_keys[q] == key) { *idf = f.map_idf[q]; return true; }
+        q = (q + 1) & f.map_mask;
+    }
+}
+
+// sketch/MinHashSketch.java:95-130: the weight of a distinct k-mer seen `count` times (0 = not used)
+__device__ __forceinline__ uint32_t kmer_weight(const KmerFilterView &f, uint64_t key, uint32_t count)
+{
+    if (f.mode == 0 || f.mode == 3) return count;
+    double idf = 0.0;
+    if (f.mode == 1) return filter_lookup(f, key, &idf) ? 0u : 1u;        // :101-107 isPopular
+    // :109-124 tf-idf
+    const double tf = f.no_tf ? 1.0 : (double)count;                       // FrequencyCounts.tfWeight
+    if (f.remove_unique == 2 && f.bloom && !bloom_might_contain(f, key)) idf = 1.0;   // scaledIdf :292-293
+    else if (!filter_lookup(f, key, &idf)) idf = f.range;                 // :295-297
+    const double r = floor(tf * idf + 0.5);                               // Math.round
+    if (!(r >= 1.0)) return 1u;                                           // NaN or < 1 -> 1 (:122-123)
+    return r > 2147483647.0 ? 2147483647u : (uint32_t)r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1a: k-mer hashing + exact de-duplication with counts
 // ---------------------------------------------------------------------------------------------
 // One CTA per strand (persistent, work queue).  Distinct hashes go into an open-addressed table
@@ -71,7 +115,8 @@ __device__ __forceinline__ int warp_alloc(int *counter, bool want)
 template <bool LONG, int KC /* compile-time k, 0 = runtime */>
 __global__ void __launch_bounds__(1024)
 k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc, int s_begin, int s_end,
-             int k, int unweighted, uint32_t table_cap, uint32_t chars_cap, SketchScratch sc, uint32_t *queue)
+             int k, int unweighted, uint32_t table_cap, uint32_t chars_cap, SketchScratch sc, uint32_t *queue,
+             const KmerFilterView flt)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int s_strand, s_nlight, s_nheavy, s_special;
@@ -119,7 +164,8 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
                 uint64_t h;
                 if (LONG) h = murmur3_128_h1_chars([&](int j) { return gsrc(i + j); }, KC ? KC : k);
                 else      h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, KC ? KC : k);
-                if (h == kEmptyKey) atomicAdd(&s_special, 1);
+                if (flt.remove_unique == 1 && !bloom_might_contain(flt, h)) { /* keepKmer false (MinHashSketch.java:70-71) */ }
+                else if (h == kEmptyKey) atomicAdd(&s_special, 1);
                 else {
                     // open addressing with double hashing: the stride is a power of two picked by three hash bits (C is odd,
                     // so every stride is a full cycle); a plain load looks at the slot first and the CAS is only issued on
@@ -161,19 +207,23 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
                 else if (dupmask[i >> 5] & (1u << (i & 31))) extra = dupcnt[i];
                 if (extra) dupcnt[i] = 0;   // leave the scratch zeroed for the next strand
             }
-            int pl = warp_alloc(&s_nlight, occ && extra == 0);
-            int ph = warp_alloc(&s_nheavy, occ && extra != 0);
-            if (occ) {
-                if (extra == 0) keys[pl] = key;
-                else { keys[nk - 1 - ph] = key; wts[nk - 1 - ph] = extra + 1; }
-            }
+            // weight rule (MinHashSketch.java:95-130); keys of the launch's light weight go to the front, the rest
+            // (with their weights) to the back, weight 0 (a popular k-mer under --repeat-weight < 0) is dropped
+            uint32_t w = 0;
+            if (occ) w = kmer_weight(flt, key, extra + 1);
+            const bool light = occ && w == flt.light_weight, heavy = occ && w != 0 && w != flt.light_weight;
+            int pl = warp_alloc(&s_nlight, light);
+            int ph = warp_alloc(&s_nheavy, heavy);
+            if (light) keys[pl] = key;
+            else if (heavy) { keys[nk - 1 - ph] = key; wts[nk - 1 - ph] = w; }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             int nl = s_nlight, nh = s_nheavy;
             if (s_special > 0) {   // a k-mer whose hash equals the table's empty marker (p = 2^-64)
-                if (s_special > 1 && !unweighted) { keys[nk - 1 - nh] = kEmptyKey; wts[nk - 1 - nh] = (uint32_t)s_special; nh++; }
-                else { keys[nl] = kEmptyKey; nl++; }
+                const uint32_t w = kmer_weight(flt, kEmptyKey, unweighted ? 1u : (uint32_t)s_special);
+                if (w == flt.light_weight) { keys[nl] = kEmptyKey; nl++; }
+                else if (w != 0) { keys[nk - 1 - nh] = kEmptyKey; wts[nk - 1 - nh] = w; nh++; }
             }
             sc.nlight[s] = nl;
             sc.nheavy[s] = nh;
@@ -220,7 +270,8 @@ __device__ __forceinline__ void xorshift_step32(uint32_t &lo, uint32_t &hi)
 
 template <int B, bool WEIGHTED>
 __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ wts,
-                                                 int n, int dir /* +1 light, -1 heavy */, uint64_t *kring, uint32_t *wbuf, int lane)
+                                                 int n, int dir /* +1 light, -1 heavy */, uint64_t *kring, uint32_t *wbuf, int lane,
+                                                 uint32_t uniform_w = 1 /* WEIGHTED with wts == nullptr: every key has this weight */)
 {
     constexpr int G = B < 4 ? B : 4;   // steps per rare-path check
     static_assert(B % G == 0, "B must be a multiple of the check group");
@@ -234,7 +285,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
         {
             int e = t0 + lane;
             uint64_t mk = 0; uint32_t mw = 1;
-            if (e < n) { mk = keys[(long long)dir * e]; if (WEIGHTED) mw = wts[(long long)dir * e]; }
+            if (e < n) { mk = keys[(long long)dir * e]; if (WEIGHTED) mw = wts ? wts[(long long)dir * e] : uniform_w; }
             kring[e & 63] = mk;
             if (WEIGHTED) wbuf[lane] = mw;
         }
@@ -308,7 +359,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
 template <int B>
 __global__ void __launch_bounds__(256)
 k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
-          int32_t *__restrict__ minhash, uint32_t *queue)
+          int32_t *__restrict__ minhash, uint32_t *queue, uint32_t light_w)
 {
     __shared__ uint64_t s_kbuf[8][64];
     __shared__ uint32_t s_wbuf[8][32];
@@ -325,7 +376,8 @@ k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, Sket
         for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
         const uint64_t *keys = sc.keys + d.koff;
         const int nl = sc.nlight[s], nh = sc.nheavy[s];
-        minhash_pipeline<B, false>(m, keys, nullptr, nl, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        if (light_w == 1) minhash_pipeline<B, false>(m, keys, nullptr, nl, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        else              minhash_pipeline<B, true>(m, keys, nullptr, nl, +1, s_kbuf[wib], s_wbuf[wib], lane, light_w);
         if (nh > 0)
             minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
         int32_t *row = minhash + (size_t)d.row * H;
@@ -580,9 +632,10 @@ __device__ __forceinline__ uint32_t bs_prefix_filter(const uint32_t (&R)[64], ui
 
 struct BsShared { uint32_t *hi, *lo, *out, *depth; };   // [Hpad] each, indexed by word
 
-template <bool PAIRED>
+// MULTI: every key advances light_w (> 1) steps per word, each of them compared (a uniform tf-idf weight, MinHashSketch.java:138)
+template <bool MULTI>
 __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
-                                                  uint32_t *scratch /* [64] */, int lane)
+                                                  uint32_t *scratch /* [64] */, int lane, int light_w)
 {
     uint32_t R[64];
     for (int r0 = 0; r0 < nb; r0 += 32) {
@@ -611,45 +664,14 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
         // the word loop carries a shared-window address and a countdown instead of (base + 4*wd, wd < H): written as C
         // the compiler re-derives the base from %tid every iteration (three S2R and six integer ops per word step)
         uint32_t daddr = (uint32_t)__cvta_generic_to_shared(st.depth);
+        int rep = light_w;           // MULTI: steps left in the current word
 #pragma unroll 1
-        for (int left = H; left > 0; left--, daddr += 4) {
+        for (int left = H; left > 0;) {
             bs_step(R);
             // chains whose sign-biased value has its top `depth` bits all zero (warp-uniform depth)
             uint32_t cand;
             const int wd = H - left;
-            if constexpr (!PAIRED) {
-            uint32_t o = 0;
-            switch (st.depth[wd]) {
-            case 26: o |= R[38];
-            case 25: o |= R[39];
-            case 24: o |= R[40];
-            case 23: o |= R[41];
-            case 22: o |= R[42];
-            case 21: o |= R[43];
-            case 20: o |= R[44];
-            case 19: o |= R[45];
-            case 18: o |= R[46];
-            case 17: o |= R[47];
-            case 16: o |= R[48];
-            case 15: o |= R[49];
-            case 14: o |= R[50];
-            case 13: o |= R[51];
-            case 12: o |= R[52];
-            case 11: o |= R[53];
-            case 10: o |= R[54];
-            case 9: o |= R[55];
-            case 8: o |= R[56];
-            case 7: o |= R[57];
-            case 6: o |= R[58];
-            case 5: o |= R[59];
-            case 4: o |= R[60];
-            case 3: o |= R[61];
-            case 2: o |= R[62];
-            case 1: o |= ~R[63];
-            default: break;
-            }
-            cand = ~o;
-            } else {
+            {
                 uint32_t depth;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(depth) : "r"(daddr) : "memory");
                 cand = bs_prefix_filter(R, depth);
@@ -704,14 +726,19 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
                 __syncwarp();
             }
             }
+            if constexpr (MULTI) {
+                if (--rep > 0) continue;
+                rep = light_w;
+            }
+            left--; daddr += 4;
         }
     }
 }
 
-template <int B, bool PAIRED>
+template <int B, bool MULTI>
 __global__ void __launch_bounds__(128, B <= 16 ? 5 : (B <= 32 ? 3 : 1))
 k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
-              int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys)
+              int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys, int light_w)
 {
     // per warp: state [4][B*32] | scratch [64] ; static: key ring + weights for the scalar pipeline
     extern __shared__ __align__(16) uint32_t s_dyn[];
@@ -738,7 +765,8 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
         LaneMins<B> m;
 #pragma unroll
         for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
-        minhash_pipeline<B, false>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        if constexpr (!MULTI) minhash_pipeline<B, false>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        else                  minhash_pipeline<B, true>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane, (uint32_t)light_w);
         if (nh > 0)
             minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
         int32_t *row = minhash + (size_t)d.row * H;
@@ -751,7 +779,7 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
                 st.depth[word] = bs_depth_of((uint32_t)m.hi[b]);
             }
             __syncwarp();
-            bs_phase_lockstep<PAIRED>(st, H, keys + n_sc, nb, scratch, lane);
+            bs_phase_lockstep<MULTI>(st, H, keys + n_sc, nb, scratch, lane, light_w);
             __syncwarp();
             for (int word = lane; word < H; word += 32) row[word] = (int32_t)st.out[word];
             __syncwarp();
@@ -1014,7 +1042,7 @@ static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
                               int first_long, int max_kmers_short, int max_kmers_long, int k, int unweighted,
-                              const SketchScratch &sc, int *launches)
+                              const KmerFilterView &filter, const SketchScratch &sc, int *launches)
 {
     cudaError_t e;
     if (first_long > 0) {
@@ -1028,7 +1056,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         if (smem <= 113 * 1024) grid *= 2;
         if (grid > first_long) grid = first_long;
         // dupcnt rows are strided by the *launch's* cap so both variants can share the buffer
-        kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, 0, first_long, k, unweighted, cap, chars_cap, sc, sc.counters + 0);
+        kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, 0, first_long, k, unweighted, cap, chars_cap, sc, sc.counters + 0, filter);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -1036,7 +1064,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         uint32_t cap = dedup_table_slots((uint32_t)max_kmers_long);
         int grid = hash_dedup_grid();
         if (grid > n_strands - first_long) grid = n_strands - first_long;
-        k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, first_long, n_strands, k, unweighted, cap, 0, sc, sc.counters + 1);
+        k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, first_long, n_strands, k, unweighted, cap, 0, sc, sc.counters + 1, filter);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -1054,16 +1082,15 @@ static int k1b_variant()
 
 template <int B>
 static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
-                                    const SketchScratch &sc, int32_t *d_minhash)
+                                    const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w)
 {
     cudaError_t e;
     int per_sm = 0;
-    if (k1b_variant() == 2 && B <= 32) {
+    // the two A/B variants (MHAPB_K1B) only implement light weight 1; a uniform tf-idf weight takes the default kernels
+    const int variant = light_w == 1 ? k1b_variant() : 2;
+    if (variant == 2 && B <= 32) {
         const size_t smem = (size_t)4 * (4 * B * 32 + 64) * 4;
-        // MHAPB_BS_FILTER=single keeps the one-plane-per-LOP3 prefix filter for A/B runs; default: two planes per LOP3
-        static int paired = -1;
-        if (paired < 0) { const char *ev = getenv("MHAPB_BS_FILTER"); paired = (ev && ev[0] == 's') ? 0 : 1; }
-        auto kern = paired ? k_minhash_bs2<B, true> : k_minhash_bs2<B, false>;
+        auto kern = light_w == 1 ? k_minhash_bs2<B, false> : k_minhash_bs2<B, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
@@ -1074,10 +1101,10 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         if (grid > need) grid = need;
         static int scalar_keys2 = -1;
         if (scalar_keys2 < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys2 = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys2 < 0) scalar_keys2 = 0; }
-        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys2);
+        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys2, (int)light_w);
         return cudaGetLastError();
     }
-    if (k1b_variant() == 1 && B <= 32) {
+    if (variant == 1 && B <= 32) {
         const size_t smem = (size_t)4 * (4 * B * 32 + 64 * kBsStage + 64) * 4;
         e = cudaFuncSetAttribute(k_minhash_bs<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1098,26 +1125,26 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
     int grid = sm_count() * per_sm;
     int need = (n_strands + 7) / 8;
     if (grid > need) grid = need;
-    k_minhash<B><<<grid, 256, 0, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2);
+    k_minhash<B><<<grid, 256, 0, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, light_w);
     return cudaGetLastError();
 }
 
 cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
-                           const SketchScratch &sc, int32_t *d_minhash, int *launches)
+                           const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, int *launches)
 {
     if (n_strands <= 0) return cudaSuccess;
     (*launches)++;
     const int b = (H + 31) / 32;
-    if (b <= 1) return launch_minhash_b<1>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 2) return launch_minhash_b<2>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 4) return launch_minhash_b<4>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 8) return launch_minhash_b<8>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 12) return launch_minhash_b<12>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 16) return launch_minhash_b<16>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 24) return launch_minhash_b<24>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 32) return launch_minhash_b<32>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    if (b <= 48) return launch_minhash_b<48>(st, d_desc, n_strands, k, H, sc, d_minhash);
-    return launch_minhash_b<64>(st, d_desc, n_strands, k, H, sc, d_minhash);
+    if (b <= 1) return launch_minhash_b<1>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 2) return launch_minhash_b<2>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 4) return launch_minhash_b<4>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 8) return launch_minhash_b<8>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 12) return launch_minhash_b<12>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 16) return launch_minhash_b<16>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 24) return launch_minhash_b<24>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 32) return launch_minhash_b<32>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 48) return launch_minhash_b<48>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    return launch_minhash_b<64>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
 }
 
 cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,

@@ -6,8 +6,9 @@
 //   -s <fasta|dat>                 self overlap                      (MhapMain.computeMain :452-477)
 //   -s <fasta|dat> -q <file|dir>   store vs query files              (:478-541), --no-self
 //   -p <fasta|dir> -q <outdir>     FASTA -> .dat sketch files        (:384-451)
-// Not supported (outside the path): -f filter files (and --filter-threshold, --supress-noise,
-// --no-tf, --repeat-idf-scale, which only act through a filter), --store-full-id, gz/bz2 input.
+//   -f <filter file> [--filter-threshold --repeat-idf-scale --supress-noise --no-tf]   k-mer filter / tf-idf
+//                                  weights (main/MhapMain.java:340-372, sketch/FrequencyCounts.java), plain text only
+// Not supported (outside the path): --store-full-id, gz/bz2 input.
 // Paths cited are relative to /root/reference/src/main/java/edu/umd/marbl/mhap/.
 #include "../../include/mhap_b200.h"
 
@@ -41,8 +42,9 @@ struct Options {
     std::string s, q, p, f;
     int k = 16, num_hashes = 512, num_min_matches = 3, num_threads = 1, ordered_kmer = 12, ordered_sketch = 1536;
     int min_store_length = 0, min_olap_length = 116, settings = 0, device = 0;
-    double threshold = 0.78, max_shift = 0.2, repeat_weight = 0.9;
-    bool no_self = false, store_full_id = false, no_rc = false;
+    double threshold = 0.78, max_shift = 0.2, repeat_weight = 0.9, filter_threshold = 1.0e-5, repeat_idf_scale = 3.0;
+    int supress_noise = 0;
+    bool no_self = false, store_full_id = false, no_rc = false, no_tf = false;
     std::map<std::string, bool> set;
 };
 
@@ -74,8 +76,10 @@ Options parse(int argc, char **argv)
         else if (a == "--no-self") o.no_self = true;
         else if (a == "--no-rc") o.no_rc = true;   // main/MhapMain.java: does not stop rc sketches being stored (MinHashSearch.java:80)
         else if (a == "--store-full-id") o.store_full_id = true;
-        else if (a == "--filter-threshold" || a == "--repeat-idf-scale" || a == "--supress-noise") need(i);
-        else if (a == "--no-tf") {}
+        else if (a == "--filter-threshold") o.filter_threshold = atof(need(i));
+        else if (a == "--repeat-idf-scale") o.repeat_idf_scale = atof(need(i));
+        else if (a == "--supress-noise") o.supress_noise = atoi(need(i));
+        else if (a == "--no-tf") o.no_tf = true;
         else if (a == "-h" || a == "--help" || a == "--version") { printf("%s\n", mhapb_version()); exit(0); }
         else { printf("Unknown option %s\n", a.c_str()); exit(1); }
     }
@@ -104,7 +108,8 @@ Options parse(int argc, char **argv)
     if (o.min_store_length < 0) { printf("The minimum read length stored must be >=0.\n"); exit(1); }
     if (o.max_shift < -1.0) { printf("The minimum shift must be greater than -1.\n"); exit(1); }
     if (o.threshold < 0.0 || o.threshold > 1.0) { printf("The second stage filter threshold must be 0<=threshold<=1.0.\n"); exit(1); }
-    if (!o.f.empty()) { printf("-f k-mer filter files are not supported by mhap-b200 (outside the accelerated path).\n"); exit(1); }
+    if (o.repeat_idf_scale < 1.0) { printf("The --repeat-idf-scale parameter must be >=1.0.\n"); exit(1); }               // :272-276
+    if (o.supress_noise < 0 || o.supress_noise > 2) { printf("The --supress-noise parameter must be in [0,2].\n"); exit(1); }   // :293-297
     if (o.store_full_id) { printf("--store-full-id is not supported by mhap-b200 (numeric ids only).\n"); exit(1); }
     return o;
 }
@@ -221,6 +226,19 @@ int main(int argc, char **argv)
     mhapb_ctx *ctx = nullptr;
     if (mhapb_create(o.device, &ctx)) die(mhapb_last_error(nullptr));
     mhapb_sketch_params p{o.k, o.num_hashes, o.ordered_kmer, o.ordered_sketch, o.repeat_weight < 0.0 ? 1 : 0, o.min_olap_length};
+
+    if (!o.f.empty()) {   // main/MhapMain.java:340-372: read the k-mer filter set
+        const double t0 = now_s();
+        fprintf(stderr, "Reading in filter file %s.\n", o.f.c_str());
+        if (ends_with(o.f, ".gz") || ends_with(o.f, ".bz2")) die("compressed filter files are not supported by mhap-b200: " + o.f);
+        std::vector<uint8_t> text = read_file(o.f);
+        mhapb_filter_params fp{o.filter_threshold, o.repeat_weight, o.repeat_idf_scale, o.supress_noise, o.no_tf ? 1 : 0};
+        int64_t n_repeat = 0;
+        if (mhapb_filter_load_text(ctx, &fp, (const char *)text.data(), text.size(), o.no_rc ? 0 : 1, &n_repeat))
+            die(std::string("Could not parse k-mer filter file. ") + mhapb_last_error(ctx));
+        fprintf(stderr, "Time (s) to read filter file: %g\n", now_s() - t0);
+        fprintf(stderr, "Read in k-mer filter with %lld repeat k-mers.\n", (long long)n_repeat);
+    }
 
     if (!o.p.empty()) {   // main/MhapMain.java:384-451
         fprintf(stderr, "Processing FASTA files for binary compression...\n");

@@ -22,6 +22,7 @@ EXPORTS = [
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
     "mhapb_search_query_sketches", "mhapb_search_sketches_device", "mhapb_format_match", "mhapb_minhash_equal_count",
+    "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
 ]
 
 
@@ -42,6 +43,12 @@ class SearchParams(C.Structure):
     _fields_ = [("num_min_matches", C.c_int32), ("min_store_length", C.c_int32), ("max_shift", C.c_double),
                 ("accept_score", C.c_double), ("keep_all", C.c_int32), ("reserved", C.c_int32),
                 ("query_first", C.c_int64), ("query_count", C.c_int64)]
+
+
+class FilterParams(C.Structure):
+    """mhapb_filter_params: the FrequencyCounts constructor arguments (sketch/FrequencyCounts.java:63)."""
+    _fields_ = [("filter_cutoff", C.c_double), ("repeat_weight", C.c_double), ("idf_scale", C.c_double),
+                ("supress_noise", C.c_int32), ("no_tf", C.c_int32)]
 
 
 class Hit(C.Structure):
@@ -113,12 +120,26 @@ def load():
     L.mhapb_search_sketches_device.argtypes = [vp, P(SearchParams), C.c_int, vp, vp, vp, vp, vp, vp, vp, i32, u32, P(vp), P(u64), P(Stats)]
     L.mhapb_format_match.argtypes = [P(Hit), C.c_char_p, C.c_size_t]
     L.mhapb_minhash_equal_count.argtypes = [vp, i64, i64, P(i32)]
+    L.mhapb_kmer_hash.argtypes = [C.c_char_p, i32, C.c_int, P(i64)]
+    L.mhapb_filter_set.argtypes = [vp, P(FilterParams), vp, vp, u64, vp, u64, i32]
+    L.mhapb_filter_load_text.argtypes = [vp, P(FilterParams), C.c_char_p, u64, C.c_int, P(i64)]
+    L.mhapb_filter_clear.argtypes = [vp]
     _lib = L
     return L
 
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def kmer_hash(kmer, canonical=True) -> int:
+    """mhapb_kmer_hash: the key a filter-file k-mer is stored under (HashUtils.computeSequenceHashesLong)."""
+    b = kmer if isinstance(kmer, (bytes, bytearray)) else kmer.encode("latin-1")
+    out = C.c_int64()
+    rc = load().mhapb_kmer_hash(b, len(b), int(canonical), C.byref(out))
+    if rc:
+        raise MhapError(rc, "mhapb_kmer_hash")
+    return int(out.value)
 
 
 def pack_reads(reads):
@@ -173,6 +194,28 @@ class Engine:
         v = C.c_double()
         self._ck(self.L.mhapb_xorshift_peak(self.h, C.byref(v)))
         return v.value
+
+    # ---- the -f k-mer filter (FrequencyCounts) ----
+    def filter_load_text(self, text, repeat_weight=0.9, filter_cutoff=1.0e-5, idf_scale=3.0, supress_noise=0, no_tf=False,
+                         canonical=True) -> int:
+        """Parse the text of a -f filter file and install it; returns the number of repeat k-mers kept."""
+        t = text if isinstance(text, (bytes, bytearray)) else text.encode("latin-1")
+        fp = FilterParams(filter_cutoff, repeat_weight, idf_scale, supress_noise, int(no_tf))
+        n = C.c_int64()
+        self._ck(self.L.mhapb_filter_load_text(self.h, C.byref(fp), t, len(t), int(canonical), C.byref(n)))
+        return int(n.value)
+
+    def filter_set(self, hashes, fractions, repeat_weight=0.9, filter_cutoff=1.0e-5, idf_scale=3.0, supress_noise=0, no_tf=False,
+                   bloom_words=None, bloom_bits=0, bloom_nfun=0):
+        h = np.ascontiguousarray(hashes, dtype=np.int64)
+        f = np.ascontiguousarray(fractions, dtype=np.float64)
+        bw = None if bloom_words is None else np.ascontiguousarray(bloom_words, dtype=np.uint64)
+        fp = FilterParams(filter_cutoff, repeat_weight, idf_scale, supress_noise, int(no_tf))
+        self._ck(self.L.mhapb_filter_set(self.h, C.byref(fp), _ptr(h) if h.size else None, _ptr(f) if f.size else None, h.size,
+                                         _ptr(bw), bloom_bits, bloom_nfun))
+
+    def filter_clear(self):
+        self._ck(self.L.mhapb_filter_clear(self.h))
 
     # ---- K1 ----
     def sketch(self, bases, offsets, params: SketchParams, both_strands=True, want_ord=True):

@@ -156,7 +156,7 @@ class FrequencyCounts:  # sketch/FrequencyCounts.java:63-320
                 continue
             kmer = tok[0]
             if canonical:                                                  # HashUtils.java:246-251
-                r = rc(kmer) if kmer == kmer.upper() else "".join(_COMP.get(c, c) for c in reversed(kmer))
+                r = rc(kmer)                                               # Utils.rc upper-cases
                 if r < kmer:
                     kmer = r
             h = _s64(murmur3_x64_128(_utf16(kmer), 0)[0])

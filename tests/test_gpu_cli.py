@@ -117,6 +117,29 @@ def test_dat_round_trip_equals_fasta_path(tmp_path):
     assert via_dat == _oracle_lines(exp_hits) and len(via_dat) > 20
 
 
+@pytest.mark.parametrize("extra,kw", [([], {}), (["--supress-noise", "2", "--repeat-idf-scale", "4"], dict(supress_noise=2, idf_scale=4.0)),
+                                      (["--repeat-weight", "-1"], dict(repeat_weight=-1.0))])
+def test_self_overlap_with_kmer_filter_file(tmp_path, extra, kw):
+    # -f: main/MhapMain.java:340-372 + sketch/FrequencyCounts.java (what Canu runs: tf-idf weights from a repeat k-mer list)
+    reads = _reads(120, 2000, 6)
+    fa = tmp_path / "store.fasta"
+    _write_fasta(fa, reads)
+    rng = random.Random(2)
+    kmers = sorted({r[i:i + 16].decode().upper() for r in reads[:60] for i in range(0, max(0, len(r) - 16), 11)})
+    text = "\n".join([f"{len(kmers)} {len(kmers)}"] + [f"{km}\t{rng.choice([5e-6, 4e-5, 1e-3, 0.02])}" for km in kmers]) + "\n"
+    ff = tmp_path / "repeats.txt"
+    ff.write_text(text)
+    got, err = _run(["-s", str(fa), "-f", str(ff), "--num-hashes", "256"] + extra)
+    rw = kw.get("repeat_weight", 0.9)
+    f = orc.KmerFilter(text, **kw)
+    st = orc.Store(num_hashes=256, unweighted=rw < 0)
+    st.set_filter(f, rw)
+    st.add_reads(*orc.pack_reads([r.upper() for r in reads]), threads=8)
+    res = st.search_self(threads=8)
+    assert got == _oracle_lines(res.hits) and len(got) > 20
+    assert f"Read in k-mer filter with {len(f)} repeat k-mers." in err
+
+
 def test_bad_arguments_exit_like_the_reference(tmp_path):
     p = subprocess.run([CLI], capture_output=True, text=True)
     assert p.returncode == 1 and "Please set the -s or the -p options." in p.stdout
