@@ -149,7 +149,7 @@ int mhapb_kmer_hash(const char *kmer, int32_t len, int canonical, int64_t *out_h
 int mhapb_filter_set(mhapb_ctx *ctx, const mhapb_filter_params *p, const int64_t *hashes, const double *fractions, uint64_t n,
                      const uint64_t *bloom_words, uint64_t bloom_bits, int32_t bloom_num_hash_functions);
 /* Same from the text of a filter file ("<sizeBloom> <sizeRepeat>" then "<k-mer> <fraction> ..." lines): the parsing
- * half of the FrequencyCounts constructor.  n_repeat (optional) = entries at or above the cutoff. */
+ * half of the FrequencyCounts constructor.  n_repeat (optional) = distinct k-mers at or above the cutoff (fractionCounts.size()). */
 int mhapb_filter_load_text(mhapb_ctx *ctx, const mhapb_filter_params *p, const char *text, uint64_t len, int canonical, int64_t *n_repeat);
 int mhapb_filter_clear(mhapb_ctx *ctx);
 

@@ -1232,7 +1232,7 @@ uint64_t host_kmer_hash(const char *kmer, int len, int canonical)
 // Installs the filter: scaledIdf per repeat k-mer in double precision (FrequencyCounts.java:223-229,250-254,285-309),
 // an open-addressed device map, and the Bloom bit array.
 int filter_install(mhapb_ctx *ctx, const mhapb_filter_params *p, const int64_t *hashes, const double *fractions, uint64_t n,
-                   const uint64_t *bloom_words, uint64_t bloom_bits, int32_t bloom_nfun)
+                   const uint64_t *bloom_words, uint64_t bloom_bits, int32_t bloom_nfun, int64_t *n_kept = nullptr)
 {
     if (!p) return fail(ctx, MHAPB_EINVAL, "null filter params");
     if (p->supress_noise < 0 || p->supress_noise > 2) return fail(ctx, MHAPB_EINVAL, "The --supress-noise parameter must be in [0,2].");
@@ -1247,10 +1247,11 @@ int filter_install(mhapb_ctx *ctx, const mhapb_filter_params *p, const int64_t *
     double max_value = -INFINITY;
     for (uint64_t i = 0; i < n; i++)
         if (fractions[i] >= p->filter_cutoff) { kept[hashes[i]] = fractions[i]; if (fractions[i] > max_value) max_value = fractions[i]; }
+    if (n_kept) *n_kept = (int64_t)kept.size();
     const double min_idf = log(max_value / max_value - offset);                    // idf(maxValue) :228
     const double max_idf = log(max_value / p->filter_cutoff - offset);              // idf(minValue) :229
     const double scale = (max_idf - min_idf) / (p->idf_scale - 1.0);
-    size_t cap = 16;
+    size_t cap = 64;
     while (cap < kept.size() * 2) cap <<= 1;
     std::vector<uint64_t> keys(cap, 0);
     std::vector<double> idf(cap, 0.0);
@@ -1380,8 +1381,7 @@ int mhapb_filter_load_text(mhapb_ctx *ctx, const mhapb_filter_params *p, const c
         }
         cur = nl ? nl + 1 : end;
     }
-    if (n_repeat) *n_repeat = (int64_t)hashes.size();
-    return filter_install(ctx, p, hashes.data(), fractions.data(), hashes.size(), bloom.empty() ? nullptr : bloom.data(), bloom_bits, nfun);
+    return filter_install(ctx, p, hashes.data(), fractions.data(), hashes.size(), bloom.empty() ? nullptr : bloom.data(), bloom_bits, nfun, n_repeat);
 }
 
 } // extern "C"
