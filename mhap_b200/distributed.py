@@ -1,4 +1,4 @@
-"""Multi-GPU self-overlap: shard reads, sketch + index locally, all-gather sketch blocks, query everything.
+"""Multi-GPU self-overlap and store-vs-query: shard reads, sketch + index locally, all-gather sketch blocks, query everything.
 
 The reference is one JVM ("Distributed communication backend: none"); its users
 partition by hand.  Here the path shards naturally with ONE exchange step:
@@ -11,6 +11,11 @@ partition by hand.  Here the path shards naturally with ONE exchange step:
      id rules (MinHashSearch.java:200,215-225), so each overlap (query, target) is found exactly once,
      on the rank that owns the target; the order-independent counters (MhapMain.java:572-590) are
      additive over target shards and are summed with an all-reduce.
+
+Store-vs-query mode (`-s store -q query`, AbstractMatchSearch.findMatches(streamer) :203-285; BASELINE configs[3]) shards
+the same way: every rank indexes its shard of the STORE, sketches its shard of the QUERY file (forward strand only),
+the query blocks are all-gathered and every rank runs all queries against its local index without the self-search id
+rules; a (query, target) pair is again found exactly once, on the target's rank.
 
 The compute is behind a small backend protocol so the host logic can be exercised with gloo on CPU
 (tests use an oracle-backed stand-in; the product backend is GpuBackend over the C ABI).
@@ -89,12 +94,30 @@ def sharded_self_overlap(backend, bases, offsets, ids, dist=None):
     block = backend.store_shard(bases, offsets, ids)          # sketch + store + index the local shard
     gblock, counts = all_gather_blocks(block, dist)           # the one exchange step
     hits, stats = backend.search_all(gblock)                  # all forward sketches vs the local index
+    stats = _reduce_stats(stats, gblock.ids.device, dist)
+    return hits, stats, dict(counts=counts, n_store=gblock.n)
+
+
+def _reduce_stats(stats, dev, dist):
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         keys = [k for k in sorted(stats) if k != "sequences_searched"]
-        t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device=gblock.ids.device)
+        t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
         stats = dict(stats, **{k: int(v) for k, v in zip(keys, t.tolist())})   # every rank searched every query once
-    return hits, stats, dict(counts=counts, n_store=gblock.n)
+    return stats
+
+
+def sharded_query_overlap(backend, store_reads, query_reads, dist=None):
+    """One rank's part of a sharded store-vs-query run.  store_reads / query_reads = (bases, offsets, ids) of THIS
+    rank's shard of the store file and of the query file.
+
+    Returns (hits whose target lives on this rank, job-wide stats dict, info dict)."""
+    block = backend.store_shard(*store_reads)                 # sketch + store + index the local store shard
+    qblock = backend.sketch_queries(*query_reads)             # forward-only sketches of the local query shard
+    gq, counts = all_gather_blocks(qblock, dist)              # the one exchange step
+    hits, stats = backend.search_all(gq, to_self=False)       # all queries vs the local index
+    stats = _reduce_stats(stats, gq.ids.device, dist)
+    return hits, stats, dict(query_counts=counts, n_queries=gq.n, n_store_local=block.n)
 
 
 class _DevArray:
@@ -157,8 +180,34 @@ class GpuBackend:
                            seq_len_kmers=to(meta["seq_len_kmers"], np.int32), ord_n=view(d_on, (ns,)),
                            minhash=view(d_mh, (ns, H)), ord=view(d_od, (ns, S, 2)))
 
-    def search_all(self, g: SketchBlock):
+    def sketch_queries(self, bases, offsets, ids) -> SketchBlock:
+        """Forward-only sketches of a query shard (SequenceSketchStreamer with fwdOnly, AbstractMatchSearch.java:214),
+        left on the device for the all-gather."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.size - 1
+        k, ok = self.p.kmer_size, self.p.ordered_kmer_size
+        H, S = self.p.num_hashes, self.p.ordered_sketch_size
+        ids = np.arange(1, n + 1, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        self.upload(np.ascontiguousarray(bases, dtype=np.uint8))
+        mh = torch.empty((n, H), dtype=torch.int32, device=self.dev)
+        od = torch.empty((n, S, 2), dtype=torch.int32, device=self.dev)
+        on = torch.empty(n, dtype=torch.int32, device=self.dev)
+        st = torch.empty(n, dtype=torch.int32, device=self.dev)
+        torch.cuda.current_stream(self.dev).synchronize()
+        if n:
+            self.e.sketch_device(self.d_bases.data_ptr(), offsets, self.p, False, mh.data_ptr(), od.data_ptr(), on.data_ptr(), st.data_ptr())
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        keep_np = st.cpu().numpy() == 0 if n else np.zeros(0, bool)     # status 0: long enough and (with a -f filter) not emptied
+        v = np.nonzero(keep_np)[0]
+        if v.size != n:
+            keep = torch.from_numpy(keep_np).to(self.dev)
+            mh, od, on = mh[keep].contiguous(), od[keep].contiguous(), on[keep].contiguous()
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.dev)
+        return SketchBlock(ids=to(ids[v], np.int64), is_fwd=to(np.ones(v.size, np.uint8), np.uint8), seq_len=to(lens[v], np.int32),
+                           seq_len_kmers=to(lens[v] - ok + 1, np.int32), ord_n=on, minhash=mh, ord=od)
+
+    def search_all(self, g: SketchBlock, to_self: bool = True):
         torch.cuda.synchronize(self.dev)
-        return self.e.search_sketches_device(self.sp, True, g.ids.cpu().numpy(), g.is_fwd.cpu().numpy(), g.seq_len.cpu().numpy(),
+        return self.e.search_sketches_device(self.sp, to_self, g.ids.cpu().numpy(), g.is_fwd.cpu().numpy(), g.seq_len.cpu().numpy(),
                                              g.seq_len_kmers.cpu().numpy(), g.minhash.data_ptr(), g.ord.data_ptr(),
                                              g.ord_n.data_ptr(), int(g.ord.shape[1]))

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mhap_b200.distributed import SketchBlock, all_gather_blocks, shard_range, sharded_self_overlap
+from mhap_b200.distributed import SketchBlock, all_gather_blocks, shard_range, sharded_query_overlap, sharded_self_overlap
 from oracle import oracle as orc
 
 H, S = 64, 200
@@ -26,6 +26,15 @@ class OracleBackend:
         st = orc.Store(num_hashes=H, ordered_size=S)
         st.add_reads(bases, offsets, ids=ids)
         self.store = st
+        return self._block(st)
+
+    def sketch_queries(self, bases, offsets, ids):
+        qs = orc.Store(num_hashes=H, ordered_size=S)
+        qs.add_reads(bases, offsets, ids=ids, both_strands=False)
+        return self._block(qs)
+
+    @staticmethod
+    def _block(st):
         rows = [st.get(i) for i in range(len(st))]
         n = len(rows)
         od = np.zeros((n, S, 2), np.int32)
@@ -38,7 +47,7 @@ class OracleBackend:
                            ord_n=t(np.array([r["ord"].shape[0] for r in rows], np.int32)),
                            minhash=t(np.stack([r["minhash"] for r in rows]) if n else np.zeros((0, H), np.int32)), ord=t(od))
 
-    def search_all(self, g):
+    def search_all(self, g, to_self=True):
         qs = orc.Store(num_hashes=H, ordered_size=S)
         for i in range(g.n):
             qs.add_sketch(int(g.ids[i]), bool(g.is_fwd[i]), int(g.seq_len[i]), g.minhash[i].numpy(), int(g.seq_len_kmers[i]),
@@ -46,13 +55,15 @@ class OracleBackend:
         if len(self.store) == 0:
             return np.zeros(0, orc.HIT_DTYPE), dict(elements_processed=0, sequences_hit=0, fully_compared=0, matches_processed=0,
                                                    sequences_searched=int(g.is_fwd.sum()))
-        r = self.store.search_query(qs, keep_all=True, to_self=True)
+        r = self.store.search_query(qs, keep_all=True, to_self=to_self)
         return r.hits, r.stats
 
 
-def _reads(n, L, seed):
+def _reads(n, L, seed, genome_seed=None):
     rng = np.random.default_rng(seed)
     g = rng.integers(0, 4, size=6000)
+    if genome_seed is not None:          # reads of another file drawn from the same genome (store vs query)
+        g = np.random.default_rng(genome_seed).integers(0, 4, size=6000)
     out = []
     for i in range(n):
         ln = L if i % 7 else 90          # some reads below min-olap are skipped (ragged shard sizes)
@@ -76,6 +87,22 @@ def _worker(rank, world, port, n_reads, q):
     bases, offs = orc.pack_reads(reads[first:first + cnt])
     ids = np.arange(first + 1, first + cnt + 1, dtype=np.int64)
     hits, stats, info = sharded_self_overlap(OracleBackend(), bases, offs, ids, dist)
+    q.put((rank, sorted(_key(h) for h in hits), stats, info))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _worker_query(rank, world, port, n_store, n_query, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    store, query = _reads(n_store, 500, 5, genome_seed=99), _reads(n_query, 500, 6, genome_seed=99)
+    f, c = shard_range(n_store, rank, world)
+    sb, so = orc.pack_reads(store[f:f + c])
+    sids = np.arange(f + 1, f + c + 1, dtype=np.int64)
+    f2, c2 = shard_range(n_query, rank, world)
+    qb, qo = orc.pack_reads(query[f2:f2 + c2])
+    qids = np.arange(f2 + 1, f2 + c2 + 1, dtype=np.int64) + n_store      # main/MhapMain.java:537 id offset of the query file
+    hits, stats, info = sharded_query_overlap(OracleBackend(), (sb, so, sids), (qb, qo, qids), dist)
     q.put((rank, sorted(_key(h) for h in hits), stats, info))
     dist.barrier()
     dist.destroy_process_group()
@@ -115,6 +142,35 @@ def test_sharded_self_overlap_equals_single_process(world):
     for rank, hits, _, _ in res:
         for k in hits:
             assert owners.setdefault(k[1], rank) == rank
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_store_vs_query_equals_single_process(world):
+    # BASELINE configs[3] shape (-s store -q query) at oracle scale: the query file's sketches are all-gathered,
+    # every rank searches its shard of the store
+    n_store, n_query = 37, 23
+    store, query = _reads(n_store, 500, 5, genome_seed=99), _reads(n_query, 500, 6, genome_seed=99)
+    st = orc.Store(num_hashes=H, ordered_size=S)
+    st.add_reads(*orc.pack_reads(store))
+    qs = orc.Store(num_hashes=H, ordered_size=S)
+    qs.add_reads(*orc.pack_reads(query), ids=np.arange(1, n_query + 1, dtype=np.int64) + n_store, both_strands=False)
+    ref = st.search_query(qs, keep_all=True)
+    assert len(ref.hits) > 20
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_query, args=(r, world, port, n_store, n_query, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(k for _, hits, _, _ in res for k in hits) == sorted(_key(h) for h in ref.hits)
+    for rank, hits, stats, info in res:
+        assert stats == ref.stats
+        assert info["n_queries"] == len(qs) and sum(info["query_counts"]) == len(qs)
 
 
 def test_shard_range_covers_everything():

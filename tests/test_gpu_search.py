@@ -184,3 +184,29 @@ def test_large_ordered_sketch_4096():
     bases, offs = synth.dataset(60, 9000, seed=31, err=0.05)
     reads = [bytes(bases[int(offs[i]):int(offs[i + 1])]) for i in range(60)]
     _run_self(reads, H=64, S=4096, m=2, thr=0.6)
+
+
+def test_gpu_backend_sharded_paths_single_rank():
+    # the product backend of mhap_b200/distributed.py (world size 1: no collective) against the oracle, both modes
+    from mhap_b200.distributed import GpuBackend, sharded_query_overlap, sharded_self_overlap
+    g = synth.genome(31, 40000)
+    sb, so = synth.reads(g, 1, 0, 300, 1500, 0.06)
+    qb, qo = synth.reads(g, 2, 0, 120, 1500, 0.06)
+    qo = qo.copy(); qo[5:] -= 1400; qb = np.concatenate([qb[:int(qo[5])], qb[int(qo[5]) + 1400:]])   # query 4 is 100 bp: skipped
+    p = native.SketchParams(16, 128, 12, 400, 0, 116)
+    sp = native.SearchParams(3, 0, 0.2, 0.78, 1, 0, 0, -1)
+    be = GpuBackend(engine(), p, sp)
+    sids = np.arange(1, 301, dtype=np.int64)
+    qids = np.arange(1, 121, dtype=np.int64) + 300
+    ost = orc.Store(num_hashes=128, ordered_size=400)
+    ost.add_reads(sb, so, ids=sids, threads=4)
+    oq = orc.Store(num_hashes=128, ordered_size=400)
+    oq.add_reads(qb, qo, ids=qids, both_strands=False, threads=4)
+    hits, stats, info = sharded_query_overlap(be, (sb, so, sids), (qb, qo, qids))
+    res = ost.search_query(oq, keep_all=True, threads=4)
+    assert info["n_queries"] == len(oq) == 119
+    assert_same_hits(hits, res.hits, stats, res.stats)
+    assert len(hits) > 50
+    hits, stats, info = sharded_self_overlap(be, sb, so, sids)
+    res = ost.search_self(keep_all=True, threads=4)
+    assert_same_hits(hits, res.hits, stats, res.stats)
