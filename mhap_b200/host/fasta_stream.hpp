@@ -1,0 +1,222 @@
+// fasta_stream.hpp -- streaming FASTA producer for the host driver.
+//
+// Replaces impl/FastaData.java:125-204 (enqueueNextSequenceInFile) as a pipeline: at >= 1 Gbases/s of K1 a
+// single-threaded getline parser is the wall-clock bottleneck, so
+//   reader thread  : reads the file (plain or .gz through zlib) in large text chunks cut at record starts ("\n>"),
+//   parser threads : turn a chunk into a batch -- sequence lines concatenated into a PINNED buffer
+//                    (mhapb_host_alloc, so the H2D copy of mhapb_store_add_reads is a straight DMA) + offsets,
+//   consumer       : takes batches in file order (ids are file positions, FastaData.java:181,190-192) and calls the
+//                    library, so parsing batch i+1 overlaps H2D + K1 of batch i.
+// Semantics kept from the reference: records start with '>', the header text is ignored (numeric ids), sequence lines
+// are concatenated, '\r' is dropped, a first line that is not a header is "Next sequence does not start with >. Invalid
+// format.", and an EMPTY record ends the file (enqueueNextSequenceInFile returns false on a zero-length sequence).
+// Upper-casing (FastaData.java:194) happens on the GPU.  .bz2 is not supported (no bzlib header in this image).
+#pragma once
+#include "../../include/mhap_b200.h"
+
+#include <zlib.h>
+
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace mhapb_host {
+
+struct FastaBatch {
+    char *bases = nullptr;            // pinned, cap bytes
+    size_t cap = 0, len = 0;
+    std::vector<uint64_t> offsets;    // n+1
+    bool ended = false;               // an empty record was met: nothing after this batch is read
+    std::string error;                // non-empty: the reference's exception text
+    uint64_t seq = 0;
+    std::vector<char> text;           // the chunk this batch is parsed from (owned here so pools stay paired)
+    size_t text_len = 0;
+    bool first_chunk = false;
+    uint32_t n_reads() const { return offsets.empty() ? 0u : (uint32_t)(offsets.size() - 1); }
+};
+
+class FastaStream {
+public:
+    FastaStream(const std::string &path, int parser_threads, size_t chunk_bytes)
+        : path_(path), chunk_(chunk_bytes < (1u << 16) ? (1u << 16) : chunk_bytes)
+    {
+        const size_t n = path.size();
+        gz_ = n > 3 && path.compare(n - 3, 3, ".gz") == 0;
+        if (gz_) { gzf_ = gzopen(path.c_str(), "rb"); if (gzf_) gzbuffer(gzf_, 1u << 20); }
+        else fp_ = fopen(path.c_str(), "rb");
+        if (!gzf_ && !fp_) { open_failed_ = true; return; }
+        if (parser_threads < 1) parser_threads = 1;
+        const int pool = parser_threads + 2;
+        for (int i = 0; i < pool; i++) free_.push_back(new FastaBatch());
+        reader_ = std::thread([this] { read_loop(); });
+        for (int i = 0; i < parser_threads; i++) parsers_.emplace_back([this] { parse_loop(); });
+    }
+    ~FastaStream()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        if (reader_.joinable()) reader_.join();
+        for (auto &t : parsers_) t.join();
+        auto drop = [](FastaBatch *b) { if (b->bases) mhapb_host_free(b->bases); delete b; };
+        for (auto *b : free_) drop(b);
+        for (auto &kv : done_) drop(kv.second);
+        for (auto *b : work_) drop(b);
+        if (held_) drop(held_);
+        if (gzf_) gzclose(gzf_);
+        if (fp_) fclose(fp_);
+    }
+    bool open_failed() const { return open_failed_; }
+
+    // Next batch in file order, or nullptr at the end of the file (or after an empty record).  The previous batch
+    // is recycled by this call.
+    FastaBatch *next()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (held_) { held_->len = 0; held_->offsets.clear(); held_->ended = false; held_->error.clear(); free_.push_back(held_); held_ = nullptr; cv_.notify_all(); }
+        if (finished_) return nullptr;
+        cv_.wait(lk, [this] { return done_.count(next_seq_) || (eof_ && next_seq_ >= eof_seq_); });
+        auto it = done_.find(next_seq_);
+        if (it == done_.end()) { finished_ = true; return nullptr; }
+        held_ = it->second;
+        done_.erase(it);
+        next_seq_++;
+        if (held_->ended || !held_->error.empty()) { finished_ = true; stop_ = true; cv_.notify_all(); }
+        return held_;
+    }
+
+private:
+    size_t read_some(char *dst, size_t want)
+    {
+        if (gz_) { int r = gzread(gzf_, dst, (unsigned)std::min<size_t>(want, 1u << 30)); return r > 0 ? (size_t)r : 0; }
+        return fread(dst, 1, want, fp_);
+    }
+
+    // Fill chunks that end just before a record start; the tail after the last "\n>" is carried to the next chunk.
+    void read_loop()
+    {
+        std::vector<char> carry;
+        uint64_t seq = 0;
+        bool at_eof = false;
+        while (!at_eof) {
+            FastaBatch *b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !free_.empty(); });
+                if (stop_) break;
+                b = free_.back(); free_.pop_back();
+            }
+            std::vector<char> &t = b->text;
+            if (t.size() < chunk_ + carry.size()) t.resize(chunk_ + carry.size());
+            size_t len = carry.size();
+            if (len) memcpy(t.data(), carry.data(), len);
+            carry.clear();
+            size_t cut = 0;
+            for (;;) {
+                const size_t got = read_some(t.data() + len, t.size() - len);
+                len += got;
+                if (got == 0) { at_eof = true; cut = len; break; }
+                if (len < t.size()) continue;                       // short read: keep filling
+                // full buffer: cut at the last record start
+                size_t p = len;
+                while (p > 1) { const void *q = memrchr(t.data(), '>', p - 1); if (!q) { p = 0; break; } p = (size_t)((const char *)q - t.data()); if (p > 0 && t[p - 1] == '\n') break; }
+                if (p > 1) { cut = p; break; }
+                t.resize(t.size() * 2);                             // one record larger than the chunk: grow and go on
+            }
+            if (!at_eof) carry.assign(t.begin() + (long)cut, t.begin() + (long)len);
+            b->text_len = cut; b->seq = seq; b->first_chunk = seq == 0;
+            seq++;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                work_.push_back(b);
+            }
+            cv_.notify_all();
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            eof_ = true; eof_seq_ = seq;
+        }
+        cv_.notify_all();
+    }
+
+    void parse_loop()
+    {
+        for (;;) {
+            FastaBatch *b = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !work_.empty() || (eof_ && work_.empty()); });
+                if (work_.empty()) { if (stop_ || eof_) return; continue; }
+                b = work_.front(); work_.pop_front();
+            }
+            parse(*b);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                done_[b->seq] = b;
+            }
+            cv_.notify_all();
+        }
+    }
+
+    static void parse(FastaBatch &b)
+    {
+        const char *p = b.text.data(), *end = p + b.text_len;
+        if (b.cap < b.text_len + 64) {
+            if (b.bases) mhapb_host_free(b.bases);
+            void *q = nullptr;
+            b.cap = b.text_len + b.text_len / 8 + 64;
+            if (mhapb_host_alloc(b.cap, &q)) { b.error = "cudaHostAlloc failed for a FASTA batch"; b.bases = nullptr; b.cap = 0; return; }
+            b.bases = (char *)q;
+        }
+        b.len = 0; b.offsets.clear(); b.offsets.push_back(0); b.ended = false; b.error.clear();
+        if (p == end) return;
+        if (*p != '>') {
+            // only the first line of the file can fail this test (a chunk always starts at a record start)
+            if (b.first_chunk) b.error = "Next sequence does not start with >. Invalid format.";
+            return;
+        }
+        while (p < end) {
+            // header line
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            p = nl ? nl + 1 : end;
+            const size_t start = b.len;
+            while (p < end && *p != '>') {
+                nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+                const char *le = nl ? nl : end;
+                size_t n = (size_t)(le - p);
+                if (n && p[n - 1] == '\r') n--;
+                memcpy(b.bases + b.len, p, n);
+                b.len += n;
+                p = nl ? nl + 1 : end;
+            }
+            if (b.len == start) { b.ended = true; return; }     // empty record: the reference stops reading here
+            b.offsets.push_back(b.len);
+        }
+    }
+
+    std::string path_;
+    size_t chunk_;
+    bool gz_ = false, open_failed_ = false;
+    gzFile gzf_ = nullptr;
+    FILE *fp_ = nullptr;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<FastaBatch *> free_;
+    std::deque<FastaBatch *> work_;
+    std::map<uint64_t, FastaBatch *> done_;
+    FastaBatch *held_ = nullptr;
+    uint64_t next_seq_ = 0, eof_seq_ = 0;
+    bool eof_ = false, stop_ = false, finished_ = false;
+    std::thread reader_;
+    std::vector<std::thread> parsers_;
+};
+
+} // namespace mhapb_host

@@ -8,9 +8,11 @@
 //   -p <fasta|dir> -q <outdir>     FASTA -> .dat sketch files        (:384-451)
 //   -f <filter file> [--filter-threshold --repeat-idf-scale --supress-noise --no-tf]   k-mer filter / tf-idf
 //                                  weights (main/MhapMain.java:340-372, sketch/FrequencyCounts.java), plain text only
-// Not supported (outside the path): --store-full-id, gz/bz2 input.
+// FASTA input (plain or .gz) is streamed: a reader thread + --num-threads parser threads fill pinned batches while the
+// GPU works on the previous one (fasta_stream.hpp).  Not supported: --store-full-id, .bz2 input.
 // Paths cited are relative to /root/reference/src/main/java/edu/umd/marbl/mhap/.
 #include "../../include/mhap_b200.h"
+#include "fasta_stream.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -135,36 +137,31 @@ std::vector<std::string> list_files(const std::string &path)
     return out;
 }
 
-struct Reads {
-    std::string bases; std::vector<uint64_t> offsets{0}; std::vector<int64_t> ids;
-};
-
-// impl/FastaData.java:125-204: records start with '>', sequence lines are concatenated, ids are 1-based
-// positions of the non-empty records (+offset); an empty record ends the file like the reference's
-// enqueueNextSequenceInFile returning false.  Upper-casing (:194) happens on the GPU.
-Reads read_fasta(const std::string &path, int64_t offset)
+// impl/FastaData.java:125-204 through the streaming producer: fn(batch, ids) is called once per batch in file order;
+// ids are the 1-based positions of the records in the file (+offset).  Returns the number of records read.
+template <class F>
+int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int threads, F fn)
 {
-    if (ends_with(path, ".gz") || ends_with(path, ".bz2")) die("compressed FASTA is not supported by mhap-b200: " + path);
-    std::ifstream in(path, std::ios::binary);
-    if (!in) die("Could not open " + path);
-    Reads r;
-    std::string line;
+    if (ends_with(path, ".bz2")) die("bzip2 FASTA is not supported by mhap-b200: " + path);
+    struct stat st;
+    size_t chunk = 128u << 20;
+    if (const char *e = getenv("MHAPB_FASTA_CHUNK_KB")) chunk = (size_t)std::max(64, atoi(e)) << 10;   // batch size (text bytes)
+    if (!ends_with(path, ".gz") && stat(path.c_str(), &st) == 0 && (size_t)st.st_size + 4096 < chunk) chunk = (size_t)st.st_size + 4096;
+    mhapb_host::FastaStream fs(path, std::max(1, std::min(threads, 8)), chunk);
+    if (fs.open_failed()) die("Could not open " + path);
     int64_t n = 0;
-    bool have = (bool)std::getline(in, line);
-    while (have) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty() || line[0] != '>') die("Next sequence does not start with >. Invalid format.");
-        size_t start = r.bases.size();
-        while ((have = (bool)std::getline(in, line))) {
-            if (!line.empty() && line.back() == '\r') line.pop_back();
-            if (!line.empty() && line[0] == '>') break;
-            r.bases += line;
+    std::vector<int64_t> ids;
+    while (mhapb_host::FastaBatch *b = fs.next()) {
+        if (!b->error.empty()) die(b->error);
+        const uint32_t nb = b->n_reads();
+        if (nb) {
+            ids.resize(nb);
+            for (uint32_t i = 0; i < nb; i++) ids[i] = n + i + 1 + offset;
+            fn(*b, ids);
+            n += nb;
         }
-        if (r.bases.size() == start) break;   // empty record: the reference stops reading here
-        r.offsets.push_back(r.bases.size());
-        r.ids.push_back(++n + offset);
     }
-    return r;
+    return n;
 }
 
 std::vector<uint8_t> read_file(const std::string &path)
@@ -245,17 +242,21 @@ int main(int argc, char **argv)
         if (!is_dir(o.q)) die("Target directory doesn't exit.");
         for (const std::string &pf : list_files(o.p)) {
             const double t0 = now_s();
-            Reads r = read_fasta(pf, 0);
-            uint8_t *blob = nullptr; uint64_t len = 0; uint32_t nrec = 0;
-            ck(ctx, mhapb_sketch_to_dat(ctx, &p, r.bases.data(), r.offsets.data(), r.ids.data(), (uint32_t)r.ids.size(), 1, &blob, &len, &nrec));
             std::string name = pf.substr(pf.find_last_of('/') == std::string::npos ? 0 : pf.find_last_of('/') + 1);
+            if (ends_with(name, ".gz")) name = name.substr(0, name.size() - 3);
             size_t dot = name.find_last_of('.');
             if (dot != std::string::npos && dot > 0) name = name.substr(0, dot);
             std::string outp = o.q + "/" + name + ".dat";
             std::ofstream out(outp, std::ios::binary);
             if (!out) die("Could not open " + outp);
-            out.write((const char *)blob, (std::streamsize)len);
-            mhapb_free(blob);
+            uint32_t nrec = 0;
+            for_each_fasta_batch(pf, 0, o.num_threads, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
+                uint8_t *blob = nullptr; uint64_t len = 0; uint32_t nr = 0;
+                ck(ctx, mhapb_sketch_to_dat(ctx, &p, b.bases, b.offsets.data(), ids.data(), b.n_reads(), 1, &blob, &len, &nr));
+                out.write((const char *)blob, (std::streamsize)len);
+                mhapb_free(blob);
+                nrec += nr;
+            });
             fprintf(stderr, "Processed %u sequences (fwd and rev).\n", nrec);
             fprintf(stderr, "Read, hashed, and stored file %s to %s.\n", pf.c_str(), outp.c_str());
             fprintf(stderr, "Time (s): %g\n", now_s() - t0);
@@ -276,9 +277,12 @@ int main(int argc, char **argv)
         ck(ctx, mhapb_store_add_sketches(ctx, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.ord.data(), d.ordn.data(), d.max_ord, d.n));
         n_sketches = d.n;
     } else {
-        Reads r = read_fasta(o.s, 0);
         ck(ctx, mhapb_store_reset(ctx, &p));
-        ck(ctx, mhapb_store_add_reads(ctx, r.bases.data(), r.offsets.data(), r.ids.data(), (uint32_t)r.ids.size(), 1, &n_sketches));
+        for_each_fasta_batch(o.s, 0, o.num_threads, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
+            int64_t added = 0;
+            ck(ctx, mhapb_store_add_reads(ctx, b.bases, b.offsets.data(), ids.data(), b.n_reads(), 1, &added));
+            n_sketches += added;
+        });
     }
     if (n_sketches > 0) ck(ctx, mhapb_index_build(ctx));
     fprintf(stderr, "Stored %lld sequences in the index.\n", (long long)n_sketches);
@@ -314,9 +318,12 @@ int main(int argc, char **argv)
                 processed = st.sequences_searched;
                 from_sub = seq_number_processed;
             } else {
-                Reads r = read_fasta(cf, seq_number_processed);
-                ck(ctx, mhapb_search_query_reads(ctx, &sp, r.bases.data(), r.offsets.data(), r.ids.data(), (uint32_t)r.ids.size(), &hits, &n, &st));
-                processed = st.sequences_searched;
+                for_each_fasta_batch(cf, seq_number_processed, o.num_threads, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
+                    mhapb_hit *bh = nullptr; uint64_t bn = 0; mhapb_stats bst{};
+                    ck(ctx, mhapb_search_query_reads(ctx, &sp, b.bases, b.offsets.data(), ids.data(), b.n_reads(), &bh, &bn, &bst));
+                    emit(bh, bn, bst, tot);
+                    processed += bst.sequences_searched;
+                });
             }
             if (hits) emit(hits, n, st, tot, from_sub);
             seq_number_processed += processed;   // :537 counts the sketched (forward) query sequences

@@ -37,8 +37,8 @@ def _reads(n, L, seed, err=0.06, genome_seed=77):
     return out
 
 
-def _run(args):
-    p = subprocess.run([CLI] + args, capture_output=True, text=True, timeout=600)
+def _run(args, env=None):
+    p = subprocess.run([CLI] + args, capture_output=True, text=True, timeout=600, env=None if env is None else dict(os.environ, **env))
     assert p.returncode == 0, p.stderr[-2000:]
     return sorted(l for l in p.stdout.splitlines() if l.strip()), p.stderr
 
@@ -138,6 +138,31 @@ def test_self_overlap_with_kmer_filter_file(tmp_path, extra, kw):
     res = st.search_self(threads=8)
     assert got == _oracle_lines(res.hits) and len(got) > 20
     assert f"Read in k-mer filter with {len(f)} repeat k-mers." in err
+
+
+def test_streamed_batches_and_gzip_input_equal_the_single_batch_run(tmp_path):
+    # the FASTA producer cuts the file into batches at record starts (64 KB here: ~6 batches per file); ids, the store, the
+    # query offsets and the .dat files must not depend on where the cuts fall.  Also: .gz input through zlib.
+    import gzip
+    store, query = _reads(160, 2000, 11), _reads(90, 2000, 12)
+    fa, qa = tmp_path / "store.fasta", tmp_path / "query.fasta"
+    _write_fasta(fa, store)
+    _write_fasta(qa, query)
+    gz = tmp_path / "store_gz.fasta.gz"
+    with open(fa, "rb") as f, gzip.open(gz, "wb") as g:
+        g.write(f.read())
+    args = ["--num-hashes", "256", "--num-threads", "3"]
+    one, err1 = _run(["-s", str(fa), "-q", str(qa)] + args)
+    many, err2 = _run(["-s", str(fa), "-q", str(qa)] + args, env={"MHAPB_FASTA_CHUNK_KB": "64"})
+    zipped, _ = _run(["-s", str(gz), "-q", str(qa)] + args, env={"MHAPB_FASTA_CHUNK_KB": "64"})
+    assert one == many == zipped and len(one) > 100
+    pick = lambda e: [l for l in e.splitlines() if l.startswith(("Stored", "Processed", "Total matches"))]
+    assert pick(err1) == pick(err2)
+    d1, d2 = tmp_path / "d1", tmp_path / "d2"
+    d1.mkdir(); d2.mkdir()
+    _run(["-p", str(fa), "-q", str(d1)] + args)
+    _run(["-p", str(gz), "-q", str(d2)] + args, env={"MHAPB_FASTA_CHUNK_KB": "64"})
+    assert (d1 / "store.dat").read_bytes() == (d2 / "store_gz.dat").read_bytes()
 
 
 def test_bad_arguments_exit_like_the_reference(tmp_path):
