@@ -16,8 +16,10 @@
 
 #include <zlib.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -35,8 +37,9 @@ struct FastaBatch {
     bool ended = false;               // an empty record was met: nothing after this batch is read
     std::string error;                // non-empty: the reference's exception text
     uint64_t seq = 0;
-    std::vector<char> text;           // the chunk this batch is parsed from (owned here so pools stay paired)
-    size_t text_len = 0;
+    char *text = nullptr;             // the chunk this batch is parsed from (owned here so pools stay paired)
+    size_t text_cap = 0, text_len = 0;
+    double t_read = 0, t_parse = 0, t_alloc = 0;   // seconds, for MHAPB_FASTA_TRACE
     bool first_chunk = false;
     uint32_t n_reads() const { return offsets.empty() ? 0u : (uint32_t)(offsets.size() - 1); }
 };
@@ -52,7 +55,9 @@ public:
         else fp_ = fopen(path.c_str(), "rb");
         if (!gzf_ && !fp_) { open_failed_ = true; return; }
         if (parser_threads < 1) parser_threads = 1;
-        const int pool = parser_threads + 2;
+        // batches in flight: one being read, one per parser, one with the consumer -- but no more than 4, so that the
+        // pinned buffers are reused instead of page-locking the whole file once
+        const int pool = std::min(parser_threads + 2, 4);
         for (int i = 0; i < pool; i++) free_.push_back(new FastaBatch());
         reader_ = std::thread([this] { read_loop(); });
         for (int i = 0; i < parser_threads; i++) parsers_.emplace_back([this] { parse_loop(); });
@@ -66,7 +71,7 @@ public:
         cv_.notify_all();
         if (reader_.joinable()) reader_.join();
         for (auto &t : parsers_) t.join();
-        auto drop = [](FastaBatch *b) { if (b->bases) mhapb_host_free(b->bases); delete b; };
+        auto drop = [](FastaBatch *b) { if (b->bases) mhapb_host_free(b->bases); free(b->text); delete b; };
         for (auto *b : free_) drop(b);
         for (auto &kv : done_) drop(kv.second);
         for (auto *b : work_) drop(b);
@@ -114,24 +119,32 @@ private:
                 if (stop_) break;
                 b = free_.back(); free_.pop_back();
             }
-            std::vector<char> &t = b->text;
-            if (t.size() < chunk_ + carry.size()) t.resize(chunk_ + carry.size());
+            const auto t0 = std::chrono::steady_clock::now();
+            auto ensure = [&](size_t want) {
+                if (b->text_cap >= want) return;
+                b->text = (char *)realloc(b->text, want);     // no zero fill: every byte below `len` is written by the read
+                b->text_cap = want;
+            };
+            ensure(chunk_ + carry.size());
+            char *t = b->text;
             size_t len = carry.size();
-            if (len) memcpy(t.data(), carry.data(), len);
+            if (len) memcpy(t, carry.data(), len);
             carry.clear();
             size_t cut = 0;
             for (;;) {
-                const size_t got = read_some(t.data() + len, t.size() - len);
+                const size_t got = read_some(t + len, b->text_cap - len);
                 len += got;
                 if (got == 0) { at_eof = true; cut = len; break; }
-                if (len < t.size()) continue;                       // short read: keep filling
+                if (len < b->text_cap) continue;                    // short read: keep filling
                 // full buffer: cut at the last record start
                 size_t p = len;
-                while (p > 1) { const void *q = memrchr(t.data(), '>', p - 1); if (!q) { p = 0; break; } p = (size_t)((const char *)q - t.data()); if (p > 0 && t[p - 1] == '\n') break; }
+                while (p > 1) { const void *q = memrchr(t, '>', p - 1); if (!q) { p = 0; break; } p = (size_t)((const char *)q - t); if (p > 0 && t[p - 1] == '\n') break; }
                 if (p > 1) { cut = p; break; }
-                t.resize(t.size() * 2);                             // one record larger than the chunk: grow and go on
+                ensure(b->text_cap * 2);                            // one record larger than the chunk: grow and go on
+                t = b->text;
             }
-            if (!at_eof) carry.assign(t.begin() + (long)cut, t.begin() + (long)len);
+            if (!at_eof) carry.assign(t + cut, t + len);
+            b->t_read = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             b->text_len = cut; b->seq = seq; b->first_chunk = seq == 0;
             seq++;
             {
@@ -168,13 +181,23 @@ private:
 
     static void parse(FastaBatch &b)
     {
-        const char *p = b.text.data(), *end = p + b.text_len;
+        const auto t00 = std::chrono::steady_clock::now();
+        parse_impl(b);
+        b.t_parse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t00).count();
+    }
+
+    static void parse_impl(FastaBatch &b)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const char *p = b.text, *end = p + b.text_len;
+        b.t_alloc = 0;
         if (b.cap < b.text_len + 64) {
             if (b.bases) mhapb_host_free(b.bases);
             void *q = nullptr;
             b.cap = b.text_len + b.text_len / 8 + 64;
             if (mhapb_host_alloc(b.cap, &q)) { b.error = "cudaHostAlloc failed for a FASTA batch"; b.bases = nullptr; b.cap = 0; return; }
             b.bases = (char *)q;
+            b.t_alloc = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
         b.len = 0; b.offsets.clear(); b.offsets.push_back(0); b.ended = false; b.error.clear();
         if (p == end) return;

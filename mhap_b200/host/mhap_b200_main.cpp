@@ -151,7 +151,12 @@ int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int thread
     if (fs.open_failed()) die("Could not open " + path);
     int64_t n = 0;
     std::vector<int64_t> ids;
-    while (mhapb_host::FastaBatch *b = fs.next()) {
+    const bool trace = getenv("MHAPB_FASTA_TRACE") != nullptr;
+    for (;;) {
+        const double tw = now_s();
+        mhapb_host::FastaBatch *b = fs.next();
+        if (!b) break;
+        const double t0 = now_s();
         if (!b->error.empty()) die(b->error);
         const uint32_t nb = b->n_reads();
         if (nb) {
@@ -160,6 +165,8 @@ int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int thread
             fn(*b, ids);
             n += nb;
         }
+        if (trace) fprintf(stderr, "[fasta] batch %llu: %u reads, %.1f MB text; read %.3f s, parse %.3f s (pinned alloc %.3f s), waited %.3f s, library call %.3f s\n",
+                           (unsigned long long)b->seq, nb, b->text_len / 1048576.0, b->t_read, b->t_parse, b->t_alloc, t0 - tw, now_s() - t0);
     }
     return n;
 }
