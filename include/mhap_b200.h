@@ -230,6 +230,9 @@ int mhapb_store_add_sketches_device(mhapb_ctx *ctx, const int64_t *ids, const ui
                                     const int32_t *seq_len, const int32_t *seq_len_kmers,
                                     const void *d_minhash, const void *d_ord, const int32_t *ord_n,
                                     uint32_t n);
+/* Capacity hint (total sketches the store is expected to hold), like the size argument of the reference's hash maps
+ * (impl/MinHashSearch.java:83-90): batches appended later do not have to grow-and-copy the sketch blocks. */
+int mhapb_store_reserve(mhapb_ctx *ctx, int64_t n_sketches);
 int64_t mhapb_store_size(mhapb_ctx *ctx);                          /* AbstractMatchSearch.size() */
 /* Copy stored sketch idx back to the host (getStoredSequenceHash, AbstractMatchSearch.java:314). */
 int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, int32_t *seq_len,

@@ -1004,6 +1004,17 @@ int mhapb_store_add_sketches_device(mhapb_ctx *ctx, const int64_t *ids, const ui
     return add_sketches_common(ctx, ids, is_fwd, seq_len, seq_len_kmers, d_minhash, d_ord, ord_n, ctx->store.p.ordered_sketch_size, n, cudaMemcpyDeviceToDevice);
 }
 
+int mhapb_store_reserve(mhapb_ctx *ctx, int64_t n_sketches)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (!s.configured) return fail(ctx, MHAPB_ESTATE, "mhapb_store_reset must be called first");
+    if (n_sketches <= s.n) return MHAPB_OK;
+    return store_reserve(ctx, n_sketches - s.n);
+}
+
 int64_t mhapb_store_size(mhapb_ctx *ctx)
 {
     if (!ctx) return MHAPB_EINVAL;

@@ -125,22 +125,27 @@ private:
                 b->text = (char *)realloc(b->text, want);     // no zero fill: every byte below `len` is written by the read
                 b->text_cap = want;
             };
-            ensure(chunk_ + carry.size());
+            // the first chunks are small (1/8, 1/4, 1/2 of the chunk size) so that the GPU starts early
+            size_t target = chunk_;
+            if (seq < 3) target = std::max<size_t>(1u << 16, chunk_ >> (3 - seq));
+            size_t limit = target + carry.size();
+            ensure(limit);
             char *t = b->text;
             size_t len = carry.size();
             if (len) memcpy(t, carry.data(), len);
             carry.clear();
             size_t cut = 0;
             for (;;) {
-                const size_t got = read_some(t + len, b->text_cap - len);
+                const size_t got = read_some(t + len, limit - len);
                 len += got;
                 if (got == 0) { at_eof = true; cut = len; break; }
-                if (len < b->text_cap) continue;                    // short read: keep filling
+                if (len < limit) continue;                          // short read: keep filling
                 // full buffer: cut at the last record start
                 size_t p = len;
                 while (p > 1) { const void *q = memrchr(t, '>', p - 1); if (!q) { p = 0; break; } p = (size_t)((const char *)q - t); if (p > 0 && t[p - 1] == '\n') break; }
                 if (p > 1) { cut = p; break; }
-                ensure(b->text_cap * 2);                            // one record larger than the chunk: grow and go on
+                limit *= 2;                                         // one record larger than the chunk: grow and go on
+                ensure(limit);
                 t = b->text;
             }
             if (!at_eof) carry.assign(t + cut, t + len);

@@ -285,7 +285,14 @@ int main(int argc, char **argv)
         n_sketches = d.n;
     } else {
         ck(ctx, mhapb_store_reset(ctx, &p));
+        struct stat fst;
+        const double file_bytes = (!ends_with(o.s, ".gz") && stat(o.s.c_str(), &fst) == 0) ? (double)fst.st_size : 0.0;
         for_each_fasta_batch(o.s, 0, o.num_threads, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
+            if (b.seq == 0 && file_bytes > 0 && b.text_len > 0 && (double)b.text_len < file_bytes) {
+                // size the store once from the first batch's record density instead of growing it batch by batch
+                const double est_reads = file_bytes / (double)b.text_len * b.n_reads() * 1.03 + 64;
+                ck(ctx, mhapb_store_reserve(ctx, (int64_t)(2 * est_reads)));
+            }
             int64_t added = 0;
             ck(ctx, mhapb_store_add_reads(ctx, b.bases, b.offsets.data(), ids.data(), b.n_reads(), 1, &added));
             n_sketches += added;

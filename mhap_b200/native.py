@@ -22,7 +22,7 @@ EXPORTS = [
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
     "mhapb_search_query_sketches", "mhapb_search_sketches_device", "mhapb_format_match", "mhapb_minhash_equal_count",
-    "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
+    "mhapb_store_reserve", "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
 ]
 
 
@@ -111,6 +111,7 @@ def load():
     L.mhapb_store_add_sketches.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, u32]
     L.mhapb_store_add_sketches_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32]
     L.mhapb_store_size.argtypes = [vp]; L.mhapb_store_size.restype = i64
+    L.mhapb_store_reserve.argtypes = [vp, i64]
     L.mhapb_store_get.argtypes = [vp, i64, P(i64), P(i32), P(i32), P(i32), vp, vp, P(i32)]
     L.mhapb_store_device_ptrs.argtypes = [vp, P(vp), P(vp), P(vp), P(i64), P(i32), P(i32)]
     L.mhapb_index_build.argtypes = [vp]
@@ -283,6 +284,9 @@ class Engine:
 
     def store_size(self) -> int:
         return int(self.L.mhapb_store_size(self.h))
+
+    def store_reserve(self, n_sketches: int):
+        self._ck(self.L.mhapb_store_reserve(self.h, int(n_sketches)))
 
     def store_get(self, idx: int, H: int, S: int) -> dict:
         id_ = C.c_int64(); fwd = C.c_int32(); sl = C.c_int32(); slk = C.c_int32(); on = C.c_int32()
