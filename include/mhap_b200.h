@@ -230,6 +230,10 @@ int mhapb_store_add_sketches_device(mhapb_ctx *ctx, const int64_t *ids, const ui
                                     const int32_t *seq_len, const int32_t *seq_len_kmers,
                                     const void *d_minhash, const void *d_ord, const int32_t *ord_n,
                                     uint32_t n);
+/* Scratch hint for callers that feed reads in batches (the streaming FASTA producer of the host driver): pre-sizes the
+ * per-call device scratch (copy of the reads, k-mer key/weight scratch, strand descriptors) for calls of up to max_bases
+ * characters in max_reads reads, so that growing batch sizes do not re-allocate it.  Purely an optimisation. */
+int mhapb_sketch_reserve(mhapb_ctx *ctx, const mhapb_sketch_params *p, uint64_t max_bases, uint32_t max_reads, int both_strands);
 /* Capacity hint (total sketches the store is expected to hold), like the size argument of the reference's hash maps
  * (impl/MinHashSearch.java:83-90): batches appended later do not have to grow-and-copy the sketch blocks. */
 int mhapb_store_reserve(mhapb_ctx *ctx, int64_t n_sketches);

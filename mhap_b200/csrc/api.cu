@@ -1004,6 +1004,24 @@ int mhapb_store_add_sketches_device(mhapb_ctx *ctx, const int64_t *ids, const ui
     return add_sketches_common(ctx, ids, is_fwd, seq_len, seq_len_kmers, d_minhash, d_ord, ord_n, ctx->store.p.ordered_sketch_size, n, cudaMemcpyDeviceToDevice);
 }
 
+int mhapb_sketch_reserve(mhapb_ctx *ctx, const mhapb_sketch_params *p, uint64_t max_bases, uint32_t max_reads, int both_strands)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = check_sketch_params(ctx, p);
+    if (rc) return rc;
+    const uint64_t per = both_strands ? 2 : 1;
+    const uint64_t kmers = std::min<uint64_t>(max_bases * per, 256ull << 20);   // sketch_core's chunk cap
+    CU(ctx, ctx->bases.ensure((size_t)max_bases + 64));
+    CU(ctx, ctx->keys.ensure((size_t)kmers * 8));
+    CU(ctx, ctx->wts.ensure((size_t)kmers * 4));
+    CU(ctx, ctx->desc.ensure((size_t)max_reads * per * sizeof(StrandDesc)));
+    CU(ctx, ctx->nlight.ensure((size_t)max_reads * per * 4));
+    CU(ctx, ctx->nheavy.ensure((size_t)max_reads * per * 4));
+    return MHAPB_OK;
+}
+
 int mhapb_store_reserve(mhapb_ctx *ctx, int64_t n_sketches)
 {
     if (!ctx) return MHAPB_EINVAL;

@@ -22,7 +22,7 @@ EXPORTS = [
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
     "mhapb_search_query_sketches", "mhapb_search_sketches_device", "mhapb_format_match", "mhapb_minhash_equal_count",
-    "mhapb_store_reserve", "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
+    "mhapb_store_reserve", "mhapb_sketch_reserve", "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
 ]
 
 
@@ -112,6 +112,7 @@ def load():
     L.mhapb_store_add_sketches_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32]
     L.mhapb_store_size.argtypes = [vp]; L.mhapb_store_size.restype = i64
     L.mhapb_store_reserve.argtypes = [vp, i64]
+    L.mhapb_sketch_reserve.argtypes = [vp, P(SketchParams), u64, u32, C.c_int]
     L.mhapb_store_get.argtypes = [vp, i64, P(i64), P(i32), P(i32), P(i32), vp, vp, P(i32)]
     L.mhapb_store_device_ptrs.argtypes = [vp, P(vp), P(vp), P(vp), P(i64), P(i32), P(i32)]
     L.mhapb_index_build.argtypes = [vp]

@@ -29,7 +29,7 @@ with open(fa, "wb") as f:
 t_write = time.time() - t0
 out = os.path.join(d, "out.ovl")
 res = {}
-for label, env in (("streamed", {}), ("single_batch", {"MHAPB_FASTA_CHUNK_KB": str(4 << 20)})):
+for label, env in (("warmup", {}), ("streamed", {}), ("single_batch", {"MHAPB_FASTA_CHUNK_KB": str(4 << 20)})):
     t0 = time.time()
     with open(out, "wb") as fo:
         p = subprocess.run([os.path.join(ROOT, "mhap_b200", "mhap-b200"), "-s", fa, "--num-hashes", "512", "--num-threads", str(a.threads)],
