@@ -11,6 +11,7 @@
 #include "engine.h"
 #include "hash.cuh"
 #include "bs_step.cuh"
+#include "bs_filter.cuh"
 
 #include <cstdlib>
 
@@ -568,74 +569,24 @@ __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__re
 // That removes the 64 shuffles per hop, the pipeline fill/drain (31 of 311 hops for a 10 kbp strand) and the
 // per-lane tap select (the OR over the top planes is a fall-through switch on a uniform value, 1-bit
 // granularity).  Flagged chains are resolved one at a time against the shared exact state as before.
-constexpr int kBsMaxDepth = 26;
+struct BsShared { uint32_t *hi, *lo, *out, *depth; };   // [Hpad] each, indexed by word; depth holds the filter code (bs_filter.cuh)
 
-__device__ __forceinline__ uint32_t bs_depth_of(uint32_t hi_signed)
+// shared-window accesses by 32-bit address (the lock-step word loop carries one such address; everything the rare path
+// touches is at a constant offset from it, so nothing has to be re-derived from %tid inside the loop)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+template <int OFF>   // immediate offset: one address register serves all sixteen stores of a publish
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
-    const uint32_t tu = hi_signed ^ 0x80000000u;     // sign-biased high word of the word's current minimum
-    const int F = tu ? __clz(tu) : 32;               // x < min  =>  the top F biased bits of x are zero
-    return (uint32_t)min(F, kBsMaxDepth);
+    asm volatile("st.shared.v4.u32 [%0+%5], {%1, %2, %3, %4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w), "n"(OFF) : "memory");
 }
-
-// Prefix filter of the lock-step kernel: bit c of the result is set when chain c's sign-biased value has its top
-// `depth` bits all zero.  depth is warp-uniform, 0..kBsMaxDepth.  Written in PTX
-// so that it is ONE indexed branch (brx.idx -> BRX through a table) into one of two pure fall-through chains that
-// OR two planes per LOP3 -- even depths pair (63,62),(61,60),.., odd depths pair (62,61),(60,59),.. and fold plane 63
-// into the last LOP3 -- so depth d costs ceil(d/2)+1 LOP3.  (The C++ switch of the same shape is compiled to a
-// compare/branch tree: ~12 extra alu-pipe instructions per word step.)
-__device__ __forceinline__ uint32_t bs_prefix_filter(const uint32_t (&R)[64], uint32_t depth)
-{
-    uint32_t cand;
-    asm volatile(
-        "{\n\t"
-        ".reg .u32 o;\n\t"
-        "bsf_tbl: .branchtargets bsf_d0, bsf_d1, bsf_d2, bsf_d3, bsf_d4, bsf_d5, bsf_d6, bsf_d7, bsf_d8, bsf_d9, bsf_d10, bsf_d11, bsf_d12, bsf_d13, bsf_d14, bsf_d15, bsf_d16, bsf_d17, bsf_d18, bsf_d19, bsf_d20, bsf_d21, bsf_d22, bsf_d23, bsf_d24, bsf_d25, bsf_d26;\n\t"
-        "mov.u32 o, 0;\n\t"
-        "brx.idx.uni %1, bsf_tbl;\n\t"
-        "bsf_d26: lop3.b32 o, %3, %4, o, 0xFE;\n\t"   // R38 | R39
-        "bsf_d24: lop3.b32 o, %5, %6, o, 0xFE;\n\t"   // R40 | R41
-        "bsf_d22: lop3.b32 o, %7, %8, o, 0xFE;\n\t"   // R42 | R43
-        "bsf_d20: lop3.b32 o, %9, %10, o, 0xFE;\n\t"   // R44 | R45
-        "bsf_d18: lop3.b32 o, %11, %12, o, 0xFE;\n\t"   // R46 | R47
-        "bsf_d16: lop3.b32 o, %13, %14, o, 0xFE;\n\t"   // R48 | R49
-        "bsf_d14: lop3.b32 o, %15, %16, o, 0xFE;\n\t"   // R50 | R51
-        "bsf_d12: lop3.b32 o, %17, %18, o, 0xFE;\n\t"   // R52 | R53
-        "bsf_d10: lop3.b32 o, %19, %20, o, 0xFE;\n\t"   // R54 | R55
-        "bsf_d8: lop3.b32 o, %21, %22, o, 0xFE;\n\t"   // R56 | R57
-        "bsf_d6: lop3.b32 o, %23, %24, o, 0xFE;\n\t"   // R58 | R59
-        "bsf_d4: lop3.b32 o, %25, %26, o, 0xFE;\n\t"   // R60 | R61
-        "bsf_d2: lop3.b32 o, %27, %28, o, 0xFB;\n\t"   // R62 | ~R63
-        "bsf_d0: not.b32 %0, o;\n\t"   // depth 0 (minimum still Long.MAX_VALUE): every chain is a candidate
-        "bra.uni bsf_end;\n\t"
-        "bsf_d25: lop3.b32 o, %4, %5, o, 0xFE;\n\t"   // R39 | R40
-        "bsf_d23: lop3.b32 o, %6, %7, o, 0xFE;\n\t"   // R41 | R42
-        "bsf_d21: lop3.b32 o, %8, %9, o, 0xFE;\n\t"   // R43 | R44
-        "bsf_d19: lop3.b32 o, %10, %11, o, 0xFE;\n\t"   // R45 | R46
-        "bsf_d17: lop3.b32 o, %12, %13, o, 0xFE;\n\t"   // R47 | R48
-        "bsf_d15: lop3.b32 o, %14, %15, o, 0xFE;\n\t"   // R49 | R50
-        "bsf_d13: lop3.b32 o, %16, %17, o, 0xFE;\n\t"   // R51 | R52
-        "bsf_d11: lop3.b32 o, %18, %19, o, 0xFE;\n\t"   // R53 | R54
-        "bsf_d9: lop3.b32 o, %20, %21, o, 0xFE;\n\t"   // R55 | R56
-        "bsf_d7: lop3.b32 o, %22, %23, o, 0xFE;\n\t"   // R57 | R58
-        "bsf_d5: lop3.b32 o, %24, %25, o, 0xFE;\n\t"   // R59 | R60
-        "bsf_d3: lop3.b32 o, %26, %27, o, 0xFE;\n\t"   // R61 | R62
-        "bsf_d1: lop3.b32 %0, o, %28, 0, 0x0C;\n\t"   // ~o & R63
-        "bsf_end:\n\t"
-        "}"
-        : "=r"(cand)
-        : "r"(depth), "r"(0),
-          "r"(R[38]), "r"(R[39]), "r"(R[40]), "r"(R[41]), "r"(R[42]), "r"(R[43]), "r"(R[44]), "r"(R[45]), "r"(R[46]), "r"(R[47]),
-          "r"(R[48]), "r"(R[49]), "r"(R[50]), "r"(R[51]), "r"(R[52]), "r"(R[53]), "r"(R[54]), "r"(R[55]), "r"(R[56]), "r"(R[57]),
-          "r"(R[58]), "r"(R[59]), "r"(R[60]), "r"(R[61]), "r"(R[62]), "r"(R[63]));
-    return cand;
-}
-
-struct BsShared { uint32_t *hi, *lo, *out, *depth; };   // [Hpad] each, indexed by word
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u32_off(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory"); return v; }
 
 // MULTI: every key advances light_w (> 1) steps per word, each of them compared (a uniform tf-idf weight, MinHashSketch.java:138)
 template <bool MULTI>
 __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
-                                                  uint32_t *scratch /* [64] */, int lane, int light_w)
+                                                  uint32_t hpb /* bytes between the per-word arrays hi|lo|out|depth|scratch */, int lane, int light_w)
 {
     uint32_t R[64];
     for (int r0 = 0; r0 < nb; r0 += 32) {
@@ -664,6 +615,7 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
         // the word loop carries a shared-window address and a countdown instead of (base + 4*wd, wd < H): written as C
         // the compiler re-derives the base from %tid every iteration (three S2R and six integer ops per word step)
         uint32_t daddr = (uint32_t)__cvta_generic_to_shared(st.depth);
+        asm volatile("" : "+r"(daddr));   // opaque: otherwise daddr - 4*wd is folded back into the %tid expression
         int rep = light_w;           // MULTI: steps left in the current word
 #pragma unroll 1
         for (int left = H; left > 0;) {
@@ -671,54 +623,43 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
             // chains whose sign-biased value has its top `depth` bits all zero (warp-uniform depth)
             uint32_t cand;
             const int wd = H - left;
-            {
-                uint32_t depth;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(depth) : "r"(daddr) : "memory");
-                cand = bs_prefix_filter(R, depth);
-            }
+            cand = bs_prefix_filter(R, lds_u32(daddr));
             if (__any_sync(kFull, cand != 0)) {
             if (!valid) cand = 0;
             unsigned evm = __ballot_sync(kFull, cand != 0);
+            // per-word state of this word: hi | lo | out | code at daddr - 3,2,1,0 * hpb; the warp's scratch after the code array
+            const uint32_t sbase = daddr - 4u * (uint32_t)wd + hpb;
             while (evm) {                               // warp-uniform
                 const int L = __ffs(evm) - 1;
                 evm &= evm - 1;
-                // high planes first: about half of the flagged chains are rejected on the high word alone
+                // the filter compares the top depth+3 bits exactly, so ~9 of 10 flagged chains are real updates: the lane
+                // publishes all 64 planes at once and every flagged chain is re-assembled with two ballots
                 if (lane == L) {
-#pragma unroll
-                    for (int i = 0; i < 32; i++) scratch[32 + i] = R[32 + i];
+                    sts_v4<0>(sbase, R[0], R[1], R[2], R[3]);       sts_v4<16>(sbase, R[4], R[5], R[6], R[7]);
+                    sts_v4<32>(sbase, R[8], R[9], R[10], R[11]);    sts_v4<48>(sbase, R[12], R[13], R[14], R[15]);
+                    sts_v4<64>(sbase, R[16], R[17], R[18], R[19]);  sts_v4<80>(sbase, R[20], R[21], R[22], R[23]);
+                    sts_v4<96>(sbase, R[24], R[25], R[26], R[27]);  sts_v4<112>(sbase, R[28], R[29], R[30], R[31]);
+                    sts_v4<128>(sbase, R[32], R[33], R[34], R[35]); sts_v4<144>(sbase, R[36], R[37], R[38], R[39]);
+                    sts_v4<160>(sbase, R[40], R[41], R[42], R[43]); sts_v4<176>(sbase, R[44], R[45], R[46], R[47]);
+                    sts_v4<192>(sbase, R[48], R[49], R[50], R[51]); sts_v4<208>(sbase, R[52], R[53], R[54], R[55]);
+                    sts_v4<224>(sbase, R[56], R[57], R[58], R[59]); sts_v4<240>(sbase, R[60], R[61], R[62], R[63]);
                 }
                 __syncwarp();
-                const uint32_t p_hi = scratch[32 + lane];
+                const uint32_t p_lo = lds_u32_off<0>(sbase + 4u * lane), p_hi = lds_u32_off<128>(sbase + 4u * lane);
                 uint32_t cm = __shfl_sync(kFull, cand, L);
-                const int32_t bh0 = (int32_t)st.hi[wd];
-                uint32_t keep = 0;
-                for (uint32_t c2 = cm; c2; c2 &= c2 - 1) {
-                    const int sb = __ffs(c2) - 1;
-                    const uint32_t xh = __ballot_sync(kFull, (p_hi >> sb) & 1u);
-                    if ((int32_t)xh <= bh0) keep |= 1u << sb;
-                }
-                cm = keep;
-                if (cm) {
-                    if (lane == L) {
-#pragma unroll
-                        for (int i = 0; i < 32; i++) scratch[i] = R[i];
-                    }
-                    __syncwarp();
-                }
-                const uint32_t p_lo = cm ? scratch[lane] : 0u;
                 while (cm) {                            // warp-uniform
                     const int sb = __ffs(cm) - 1;
                     cm &= cm - 1;
                     const uint32_t xh = __ballot_sync(kFull, (p_hi >> sb) & 1u);
                     const uint32_t xl = __ballot_sync(kFull, (p_lo >> sb) & 1u);
-                    const int32_t bh = (int32_t)st.hi[wd];
-                    if ((int32_t)xh < bh || ((int32_t)xh == bh && xl < st.lo[wd])) {   // MinHashSketch.java:144, uniform
+                    const int32_t bh = (int32_t)lds_u32(daddr - 3u * hpb);
+                    if ((int32_t)xh < bh || ((int32_t)xh == bh && xl < lds_u32(daddr - 2u * hpb))) {   // MinHashSketch.java:144, uniform
                         __syncwarp();
                         if (lane == L) {
                             const uint64_t key = keys[(size_t)(r0 + L) * 32 + (31 - sb)];
-                            st.hi[wd] = xh; st.lo[wd] = xl;
-                            st.out[wd] = (wd & 1) ? (uint32_t)(key >> 32) : (uint32_t)key;   // :146-149
-                            st.depth[wd] = bs_depth_of(xh);
+                            sts_u32(daddr - 3u * hpb, xh); sts_u32(daddr - 2u * hpb, xl);
+                            sts_u32(daddr - hpb, (wd & 1) ? (uint32_t)(key >> 32) : (uint32_t)key);   // :146-149
+                            sts_u32(daddr, bs_code_of(xh));
                         }
                         __syncwarp();
                     }
@@ -776,10 +717,10 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
             for (int b = 0; b < B; b++) {
                 const int word = lane * B + b;
                 st.hi[word] = (uint32_t)m.hi[b]; st.lo[word] = m.lo[b]; st.out[word] = (uint32_t)m.out[b];
-                st.depth[word] = bs_depth_of((uint32_t)m.hi[b]);
+                st.depth[word] = bs_code_of((uint32_t)m.hi[b]);
             }
             __syncwarp();
-            bs_phase_lockstep<MULTI>(st, H, keys + n_sc, nb, scratch, lane, light_w);
+            bs_phase_lockstep<MULTI>(st, H, keys + n_sc, nb, (uint32_t)HP * 4u, lane, light_w);
             __syncwarp();
             for (int word = lane; word < H; word += 32) row[word] = (int32_t)st.out[word];
             __syncwarp();
