@@ -38,9 +38,9 @@ ALG_BYTES_PER_BASE = {  # (ceil(L/4)+8 in + strands*(4H + 8*min(
 
 
 # DRAM traffic of one K1b launch per read, from the ncu --set full capture of k_minhash_bs2<16>
-# (profiles/r1q_k_minhash_bs2_ncu_summary.txt, one launch = 12 500 reads x 10 kbp: dram__bytes_read 1.8560 GB +
+# (profiles/r1r_k_minhash_bs2_ncu_summary.txt, one launch = 12 500 reads x 10 kbp: dram__bytes_read 1.8560 GB +
 # dram__bytes_write 0.0497 GB): the 8-byte k-mer keys it streams in, the min-hash rows it writes
-K1B_DRAM_BYTES_PER_READ = (1.855984e9 + 49.676288e6) / 12500.0
+K1B_DRAM_BYTES_PER_READ = (1.854622e9 + 47.591424e6) / 12500.0
 
 
 def alg_bytes_per_read(L, H, S, ok=12, strands=2):
@@ -320,7 +320,7 @@ def _main(args, real_stdout):
         "counters": stats, "n_store": last["n_store"],
         "roofline": {"kernel": "k_minhash (K1b)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                     "traffic": K1B_DRAM_BYTES_PER_READ * n_local / n_chunks, "traffic_source": "ncu --set full, profiles/r1q_k_minhash_bs2_ncu_summary.txt: dram read+write of one launch / its reads",
+                     "traffic": K1B_DRAM_BYTES_PER_READ * n_local / n_chunks, "traffic_source": "ncu --set full, profiles/r1r_k_minhash_bs2_ncu_summary.txt: dram read+write of one launch / its reads",
                      "alg_bytes_per_launch": alg_bytes / n_chunks, "launches_per_step": n_chunks,
                      "note": "K1b is integer-issue bound, not HBM bound (about 2*H XORShift-min steps per base against ~3 bytes); see int_issue"},
         "int_issue": {"kernel": "k_minhash (K1b)", "achieved_steps_per_s": steps_per_s, "peak_steps_per_s": peak_steps,
