@@ -12,6 +12,10 @@ final class MhapB200 {
                                           java.nio.ByteBuffer bases, long[] offsets, long[] ids, int n, long[] stats);
     static native byte[] sketchToDat(long h, java.nio.ByteBuffer bases, long[] offsets, long[] ids, int n, boolean both);
     static native long storeSize(long h);
+    /** FrequencyCounts -> device filter: the text of the -f file is parsed by the library (mhapb_filter_load_text). */
+    static native long filterLoadText(long h, byte[] text, double filterCutoff, double repeatWeight, double idfScale,
+                                      int supressNoise, boolean noTf, boolean canonical);
+    static native void filterClear(long h);
 }
 
 /** Drop-in for MinHashSearch: same constructor arguments, same getters MhapMain.outputFinalStat reads. */

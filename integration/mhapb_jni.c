@@ -51,3 +51,21 @@ JNIEXPORT jbyteArray JNICALL Java_edu_umd_marbl_mhap_impl_MhapB200_searchSelf(JN
 }
 /* searchQueryReads, sketchToDat, storeSize, destroy: same pattern over
  * mhapb_search_query_reads, mhapb_sketch_to_dat, mhapb_store_size, mhapb_destroy. */
+
+/* main/MhapMain.java:340-372: the -f k-mer filter.  text = the (decompressed) bytes of the filter file. */
+JNIEXPORT jlong JNICALL Java_edu_umd_marbl_mhap_impl_MhapB200_filterLoadText(JNIEnv *env, jclass c, jlong h, jbyteArray text,
+        jdouble filterCutoff, jdouble repeatWeight, jdouble idfScale, jint supressNoise, jboolean noTf, jboolean canonical) {
+    mhapb_ctx *ctx = (mhapb_ctx *)(intptr_t)h;
+    mhapb_filter_params p = { filterCutoff, repeatWeight, idfScale, supressNoise, noTf ? 1 : 0 };
+    jsize n = (*env)->GetArrayLength(env, text);
+    jbyte *b = (*env)->GetByteArrayElements(env, text, NULL);
+    int64_t n_repeat = 0;
+    int rc = mhapb_filter_load_text(ctx, &p, (const char *)b, (uint64_t)n, canonical ? 1 : 0, &n_repeat);
+    (*env)->ReleaseByteArrayElements(env, text, b, JNI_ABORT);
+    if (rc) { throw_mhap(env, ctx); return 0; }
+    return n_repeat;
+}
+
+JNIEXPORT void JNICALL Java_edu_umd_marbl_mhap_impl_MhapB200_filterClear(JNIEnv *env, jclass c, jlong h) {
+    mhapb_filter_clear((mhapb_ctx *)(intptr_t)h);
+}

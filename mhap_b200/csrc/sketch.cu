@@ -409,7 +409,7 @@ k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, Sket
 // The first kBsScalarKeys keys of a strand (where a running minimum changes most often: the expected
 // number of updates of word w after t keys is the harmonic sum) and the keys with weight > 1 go through
 // the scalar pipeline first; so do strands too short to fill bundles.
-constexpr int kBsScalarKeys = 768;
+constexpr int kBsScalarKeys = 512;   // floor; whole-set rounding in k_minhash_bs2 adds up to 1023 (10 kbp strands: 769)
 constexpr int kBsTaps = 9;
 constexpr int kBsStage = 16;   // bundles transposed per staging round (lanes 0..15 transpose one each)
 __device__ __constant__ int c_bs_tap_bits[kBsTaps] = {0, 4, 8, 10, 12, 14, 16, 18, 20};
@@ -701,7 +701,11 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
         const int nk = (int)d.len - k + 1;
         const uint64_t *keys = sc.keys + d.koff;
         const int nl = sc.nlight[s], nh = sc.nheavy[s];
-        const int nb = nl > scalar_keys ? (nl - scalar_keys) / 32 : 0;   // full bundles, taken from the end
+        // full bundles, taken from the end; at least scalar_keys keys stay scalar, and when more than one warp-wide set
+        // of 32 bundles is available only whole sets are taken (a partial set costs a whole set's plane steps), so
+        // between scalar_keys and scalar_keys + 1023 keys go through the scalar pipeline
+        int nb = nl > scalar_keys ? (nl - scalar_keys) / 32 : 0;
+        if (nb >= 32) nb &= ~31;
         const int n_sc = nl - 32 * nb;
         LaneMins<B> m;
 #pragma unroll

@@ -1,13 +1,14 @@
 """-m gpu: K2 parity -- index build, probe + hit counting, second-stage filter, through the C ABI,
 against the CPU oracle: identical hit sets (all integers + score), identical printed lines, identical
 order-independent counters."""
+import ctypes as C
 import random
 
 import numpy as np
 import pytest
 
 from mhap_b200 import native, synth
-from tests.gpu_common import assert_same_hits, engine, nasty_seq, rand_seq
+from tests.gpu_common import assert_same_hits, engine, hit_key, nasty_seq, rand_seq
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -210,3 +211,22 @@ def test_gpu_backend_sharded_paths_single_rank():
     hits, stats, info = sharded_self_overlap(be, sb, so, sids)
     res = ost.search_self(keep_all=True, threads=4)
     assert_same_hits(hits, res.hits, stats, res.stats)
+
+
+def test_capacity_hints_change_nothing():
+    # mhapb_store_reserve / mhapb_sketch_reserve are pure optimisations (the streaming FASTA producer uses them)
+    bases, offs = synth.dataset(400, 1500, seed=21, err=0.06)
+    p = native.SketchParams(16, 128, 12, 300, 0, 116)
+    sp = native.SearchParams(3, 0, 0.2, 0.78, 0, 0, 0, -1)
+    e = engine()
+    e.store_reset(p)
+    e.store_add_reads(bases, offs)
+    h0, s0 = e.search_self(sp)
+    e.store_reset(p)
+    e.store_reserve(2000)
+    e._ck(e.L.mhapb_sketch_reserve(e.h, C.byref(p), 1 << 20, 1000, 1))
+    half = 200
+    e.store_add_reads(bases[: int(offs[half])], offs[: half + 1])
+    e.store_add_reads(bases[int(offs[half]):], offs[half:] - offs[half], ids=np.arange(half + 1, 401, dtype=np.int64))
+    h1, s1 = e.search_self(sp)
+    assert s0 == s1 and sorted(map(hit_key, h0)) == sorted(map(hit_key, h1)) and len(h0) > 100
