@@ -226,9 +226,10 @@ def _main(args, real_stdout):
 
     def device_step(resident=True, record=False):
         t_a = time.perf_counter()
-        block = be.store_shard(bases, offsets, ids, resident=resident)      # K1 + K2a on the local shard
+        block = be.store_shard(bases, offsets, ids, resident=resident, build_index=False)      # K1 on the local shard
+        # the one exchange step; K2a (index build over the rank's own min-hashes) runs behind the collectives
+        gblock, counts = all_gather_blocks(block, dist if world > 1 else None, overlap=be.index_build)
         tm = eng.timing()
-        gblock, counts = all_gather_blocks(block, dist if world > 1 else None)
         torch.cuda.synchronize()
         t_b = time.perf_counter()
         hits, stats = be.search_all(gblock)                                  # K2b + K2c: all forward sketches vs local index

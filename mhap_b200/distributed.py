@@ -61,9 +61,14 @@ def _pad_rows(t: torch.Tensor, rows: int) -> torch.Tensor:
     return out
 
 
-def all_gather_blocks(block: SketchBlock, dist=None) -> tuple[SketchBlock, list[int]]:
-    """All-gather the shard blocks in rank order.  Returns (global block, per-rank counts)."""
+def all_gather_blocks(block: SketchBlock, dist=None, overlap=None) -> tuple[SketchBlock, list[int]]:
+    """All-gather the shard blocks in rank order.  Returns (global block, per-rank counts).
+
+    overlap: optional callable run while the collectives are in flight (the local index build: it only reads the
+    rank's own min-hashes, so it hides behind the gather of the 14 KB-per-sketch blocks)."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        if overlap is not None:
+            overlap()
         return block, [block.n]
     world = dist.get_world_size()
     dev = block.minhash.device
@@ -73,17 +78,26 @@ def all_gather_blocks(block: SketchBlock, dist=None) -> tuple[SketchBlock, list[
     counts = [int(c) for c in counts_t.tolist()]
     mx = max(counts)
 
-    def gather(t: torch.Tensor) -> torch.Tensor:
+    pending = []
+
+    def gather(t: torch.Tensor):
         padded = _pad_rows(t, mx)
         out = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(out, padded)
+        pending.append((dist.all_gather_into_tensor(out, padded, async_op=True), padded))   # keep `padded` alive
+        return out
+
+    def trim(out: torch.Tensor) -> torch.Tensor:
         if all(c == mx for c in counts):
             return out
         return torch.cat([out[r * mx: r * mx + counts[r]] for r in range(world)], 0)
 
-    g = SketchBlock(ids=gather(block.ids), is_fwd=gather(block.is_fwd), seq_len=gather(block.seq_len),
-                    seq_len_kmers=gather(block.seq_len_kmers), ord_n=gather(block.ord_n),
-                    minhash=gather(block.minhash), ord=gather(block.ord))
+    raw = dict(ord=gather(block.ord), minhash=gather(block.minhash), ids=gather(block.ids), is_fwd=gather(block.is_fwd),
+               seq_len=gather(block.seq_len), seq_len_kmers=gather(block.seq_len_kmers), ord_n=gather(block.ord_n))
+    if overlap is not None:
+        overlap()
+    for w, _ in pending:
+        w.wait()
+    g = SketchBlock(**{k: trim(v) for k, v in raw.items()})
     return g, counts
 
 
@@ -91,8 +105,8 @@ def sharded_self_overlap(backend, bases, offsets, ids, dist=None):
     """One rank's part of a sharded self-overlap.  `bases/offsets/ids` are THIS rank's reads.
 
     Returns (hits whose target lives on this rank, job-wide stats dict, info dict)."""
-    block = backend.store_shard(bases, offsets, ids)          # sketch + store + index the local shard
-    gblock, counts = all_gather_blocks(block, dist)           # the one exchange step
+    block = backend.store_shard(bases, offsets, ids, build_index=False)      # sketch + store the local shard
+    gblock, counts = all_gather_blocks(block, dist, overlap=backend.index_build)   # the one exchange step, K2a behind it
     hits, stats = backend.search_all(gblock)                  # all forward sketches vs the local index
     stats = _reduce_stats(stats, gblock.ids.device, dist)
     return hits, stats, dict(counts=counts, n_store=gblock.n)
@@ -144,7 +158,10 @@ class GpuBackend:
         self.d_bases[: t.numel()].copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
 
-    def store_shard(self, bases, offsets, ids, resident=False) -> SketchBlock:
+    def index_build(self):
+        self.e.index_build()
+
+    def store_shard(self, bases, offsets, ids, resident=False, build_index=True) -> SketchBlock:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = offsets.size - 1
         k, ok = self.p.kmer_size, self.p.ordered_kmer_size
@@ -173,7 +190,8 @@ class GpuBackend:
                                              mh.data_ptr(), od.data_ptr(), on.cpu().numpy())
         d_mh, d_od, d_on, ns, H, S = self.e.store_device_ptrs()
         assert ns == 2 * v.size
-        self.e.index_build()
+        if build_index:
+            self.e.index_build()
         to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.dev)
         view = lambda ptr, shape: torch.as_tensor(_DevArray(ptr, shape, "<i4"), device=self.dev) if ns else torch.empty(shape, dtype=torch.int32, device=self.dev)
         return SketchBlock(ids=to(meta["ids"], np.int64), is_fwd=to(meta["is_fwd"], np.uint8), seq_len=to(meta["seq_len"], np.int32),

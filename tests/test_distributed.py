@@ -22,11 +22,15 @@ class OracleBackend:
     def __init__(self):
         self.store = None
 
-    def store_shard(self, bases, offsets, ids):
+    def store_shard(self, bases, offsets, ids, build_index=True):
         st = orc.Store(num_hashes=H, ordered_size=S)
         st.add_reads(bases, offsets, ids=ids)
         self.store = st
+        self.indexed = build_index
         return self._block(st)
+
+    def index_build(self):
+        self.indexed = True
 
     def sketch_queries(self, bases, offsets, ids):
         qs = orc.Store(num_hashes=H, ordered_size=S)
@@ -48,6 +52,7 @@ class OracleBackend:
                            minhash=t(np.stack([r["minhash"] for r in rows]) if n else np.zeros((0, H), np.int32)), ord=t(od))
 
     def search_all(self, g, to_self=True):
+        assert self.indexed, "search before the index build"
         qs = orc.Store(num_hashes=H, ordered_size=S)
         for i in range(g.n):
             qs.add_sketch(int(g.ids[i]), bool(g.is_fwd[i]), int(g.seq_len[i]), g.minhash[i].numpy(), int(g.seq_len_kmers[i]),
