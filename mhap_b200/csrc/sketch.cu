@@ -820,11 +820,50 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
         const int no = (int)d.len - ok + 1;
         if (!LONG) { stage_chars(chars, bases + d.base_off, d.len, d.rc); __syncthreads(); }
         const CharsGlobal gsrc{bases + d.base_off, d.len, d.rc};
-        for (int i = threadIdx.x; i < no; i += blockDim.x) {
-            uint32_t h;
-            if (LONG) h = murmur3_32_chars([&](int j) { return gsrc(i + j); }, KC ? KC : ok);
-            else      h = murmur3_32_chars([&](int j) { return chars[i + j]; }, KC ? KC : ok);
-            oh[i] = h ^ 0x80000000u;   // signed order -> unsigned order
+        if constexpr (!LONG && KC > 0 && (KC & 1) == 0) {
+            // MurmurHash3_x86_32 block b of k-mer i is the pair of chars (i+2b, i+2b+1), and its mixed value
+            // rotl(P*c1,15)*c2 depends on the pair alone -- the same pair serves KC/2 overlapping k-mers.  Every thread
+            // hashes a RUN of consecutive k-mers with a sliding window of KC mixed pairs in registers: one new pair
+            // mix (and one char load) per k-mer instead of KC/2 mixes and KC loads.
+            const int run = (no + (int)blockDim.x - 1) / (int)blockDim.x;
+            const int i0 = (int)threadIdx.x * run, i1 = min(no, i0 + run);
+            if (i0 < i1) {
+                auto mixp = [](uint32_t p) { p *= 0xcc9e2d51u; p = rotl32(p, 15); return p * 0x1b873593u; };
+                uint32_t W[KC];                          // W[(u+q) % KC] = mix(pair(i+q)) while hashing k-mer i = base+u
+                uint32_t cprev = chars[i0];
+#pragma unroll
+                for (int q = 0; q < KC - 1; q++) {       // pairs i0 .. i0+KC-2 all lie inside k-mer i0
+                    const uint32_t cn = chars[i0 + q + 1];
+                    W[q] = mixp(cprev | (cn << 16));
+                    cprev = cn;
+                }
+                for (int base = i0; base < i1; base += KC) {
+#pragma unroll
+                    for (int u = 0; u < KC; u++) {
+                        const int i = base + u;
+                        if (i < i1) {
+                            uint32_t h = 0;
+#pragma unroll
+                            for (int b = 0; b < KC / 2; b++) { h ^= W[(u + 2 * b) % KC]; h = rotl32(h, 13); h = h * 5 + 0xe6546b64u; }
+                            h ^= (uint32_t)(2 * KC);
+                            h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+                            oh[i] = h ^ 0x80000000u;     // signed order -> unsigned order
+                            // slide: pair (i+KC-1, i+KC) is the last pair of k-mer i+1 (cprev = char i+KC-1; the staged
+                            // buffer is padded, a read past the strand only feeds k-mers that do not exist)
+                            const uint32_t cn = chars[i + KC];
+                            W[(u + KC - 1) % KC] = mixp(cprev | (cn << 16));
+                            cprev = cn;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < no; i += blockDim.x) {
+                uint32_t h;
+                if (LONG) h = murmur3_32_chars([&](int j) { return gsrc(i + j); }, KC ? KC : ok);
+                else      h = murmur3_32_chars([&](int j) { return chars[i + j]; }, KC ? KC : ok);
+                oh[i] = h ^ 0x80000000u;   // signed order -> unsigned order
+            }
         }
         __syncthreads();
 
