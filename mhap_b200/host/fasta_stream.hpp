@@ -34,6 +34,7 @@ struct FastaBatch {
     char *bases = nullptr;            // pinned, cap bytes
     size_t cap = 0, len = 0;
     std::vector<uint64_t> offsets;    // n+1
+    std::vector<std::string> headers; // first token of every header line, only when the stream was asked to keep them
     bool ended = false;               // an empty record was met: nothing after this batch is read
     std::string error;                // non-empty: the reference's exception text
     uint64_t seq = 0;
@@ -46,8 +47,8 @@ struct FastaBatch {
 
 class FastaStream {
 public:
-    FastaStream(const std::string &path, int parser_threads, size_t chunk_bytes)
-        : path_(path), chunk_(chunk_bytes < (1u << 16) ? (1u << 16) : chunk_bytes)
+    FastaStream(const std::string &path, int parser_threads, size_t chunk_bytes, bool keep_headers = false)
+        : path_(path), chunk_(chunk_bytes < (1u << 16) ? (1u << 16) : chunk_bytes), keep_headers_(keep_headers)
     {
         const size_t n = path.size();
         gz_ = n > 3 && path.compare(n - 3, 3, ".gz") == 0;
@@ -86,7 +87,7 @@ public:
     FastaBatch *next()
     {
         std::unique_lock<std::mutex> lk(mu_);
-        if (held_) { held_->len = 0; held_->offsets.clear(); held_->ended = false; held_->error.clear(); free_.push_back(held_); held_ = nullptr; cv_.notify_all(); }
+        if (held_) { held_->len = 0; held_->offsets.clear(); held_->headers.clear(); held_->ended = false; held_->error.clear(); free_.push_back(held_); held_ = nullptr; cv_.notify_all(); }
         if (finished_) return nullptr;
         cv_.wait(lk, [this] { return done_.count(next_seq_) || (eof_ && next_seq_ >= eof_seq_); });
         auto it = done_.find(next_seq_);
@@ -175,7 +176,7 @@ private:
                 if (work_.empty()) { if (stop_ || eof_) return; continue; }
                 b = work_.front(); work_.pop_front();
             }
-            parse(*b);
+            parse(*b, keep_headers_);
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 done_[b->seq] = b;
@@ -184,14 +185,14 @@ private:
         }
     }
 
-    static void parse(FastaBatch &b)
+    static void parse(FastaBatch &b, bool keep_headers)
     {
         const auto t00 = std::chrono::steady_clock::now();
-        parse_impl(b);
+        parse_impl(b, keep_headers);
         b.t_parse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t00).count();
     }
 
-    static void parse_impl(FastaBatch &b)
+    static void parse_impl(FastaBatch &b, bool keep_headers)
     {
         const auto t0 = std::chrono::steady_clock::now();
         const char *p = b.text, *end = p + b.text_len;
@@ -204,7 +205,7 @@ private:
             b.bases = (char *)q;
             b.t_alloc = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
-        b.len = 0; b.offsets.clear(); b.offsets.push_back(0); b.ended = false; b.error.clear();
+        b.len = 0; b.offsets.clear(); b.offsets.push_back(0); b.headers.clear(); b.ended = false; b.error.clear();
         if (p == end) return;
         if (*p != '>') {
             // only the first line of the file can fail this test (a chunk always starts at a record start)
@@ -212,8 +213,9 @@ private:
             return;
         }
         while (p < end) {
-            // header line
+            // header line; --store-full-id keeps line.substring(1).split("[\\s,]+", 2)[0] (FastaData.java:155-156)
             const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            const char *hs = p + 1, *he = nl ? nl : end;
             p = nl ? nl + 1 : end;
             const size_t start = b.len;
             while (p < end && *p != '>') {
@@ -227,12 +229,17 @@ private:
             }
             if (b.len == start) { b.ended = true; return; }     // empty record: the reference stops reading here
             b.offsets.push_back(b.len);
+            if (keep_headers) {
+                const char *q = hs;
+                while (q < he && !(*q == ' ' || *q == '\t' || *q == '\r' || *q == '\f' || *q == '\v' || *q == ',')) q++;
+                b.headers.emplace_back(hs, (size_t)(q - hs));
+            }
         }
     }
 
     std::string path_;
     size_t chunk_;
-    bool gz_ = false, open_failed_ = false;
+    bool gz_ = false, open_failed_ = false, keep_headers_ = false;
     gzFile gzf_ = nullptr;
     FILE *fp_ = nullptr;
     std::mutex mu_;

@@ -9,7 +9,9 @@
 //   -f <filter file> [--filter-threshold --repeat-idf-scale --supress-noise --no-tf]   k-mer filter / tf-idf
 //                                  weights (main/MhapMain.java:340-372, sketch/FrequencyCounts.java), plain text only
 // FASTA input (plain or .gz) is streamed: a reader thread + --num-threads parser threads fill pinned batches while the
-// GPU works on the previous one (fasta_stream.hpp).  Not supported: --store-full-id, .bz2 input.
+// GPU works on the previous one (fasta_stream.hpp).  --store-full-id prints the first token of the FASTA headers instead of
+// the file positions (impl/FastaData.java:155-156, impl/SequenceId.java; ignored for .dat input like the reference).
+// Not supported: .bz2 input.
 // Paths cited are relative to /root/reference/src/main/java/edu/umd/marbl/mhap/.
 #include "../../include/mhap_b200.h"
 #include "fasta_stream.hpp"
@@ -112,7 +114,6 @@ Options parse(int argc, char **argv)
     if (o.threshold < 0.0 || o.threshold > 1.0) { printf("The second stage filter threshold must be 0<=threshold<=1.0.\n"); exit(1); }
     if (o.repeat_idf_scale < 1.0) { printf("The --repeat-idf-scale parameter must be >=1.0.\n"); exit(1); }               // :272-276
     if (o.supress_noise < 0 || o.supress_noise > 2) { printf("The --supress-noise parameter must be in [0,2].\n"); exit(1); }   // :293-297
-    if (o.store_full_id) { printf("--store-full-id is not supported by mhap-b200 (numeric ids only).\n"); exit(1); }
     return o;
 }
 
@@ -149,12 +150,16 @@ size_t fasta_chunk_bytes(const std::string &path)
     return chunk;
 }
 
+// --store-full-id: header string of every sequence id seen so far (id = 1-based position + offset, SequenceId.getHeader())
+std::vector<std::string> g_names;
+bool g_full_ids = false;
+
 template <class F>
 int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int threads, F fn)
 {
     if (ends_with(path, ".bz2")) die("bzip2 FASTA is not supported by mhap-b200: " + path);
     const size_t chunk = fasta_chunk_bytes(path);
-    mhapb_host::FastaStream fs(path, std::max(1, std::min(threads, 8)), chunk);
+    mhapb_host::FastaStream fs(path, std::max(1, std::min(threads, 8)), chunk, g_full_ids);
     if (fs.open_failed()) die("Could not open " + path);
     int64_t n = 0;
     std::vector<int64_t> ids;
@@ -169,6 +174,10 @@ int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int thread
         if (nb) {
             ids.resize(nb);
             for (uint32_t i = 0; i < nb; i++) ids[i] = n + i + 1 + offset;
+            if (g_full_ids) {
+                if (g_names.size() < (size_t)(n + nb + offset)) g_names.resize((size_t)(n + nb + offset));
+                for (uint32_t i = 0; i < nb; i++) g_names[(size_t)(ids[i] - 1)] = b->headers[i];
+            }
             fn(*b, ids);
             n += nb;
         }
@@ -220,7 +229,19 @@ void emit(mhapb_hit *hits, uint64_t n, const mhapb_stats &st, Totals &tot, int64
 {
     // AbstractMatchSearch.outputResults :316-338: one MatchResult.toString() per line on stdout
     char line[256];
-    for (uint64_t i = 0; i < n; i++) { hits[i].from_id -= from_sub; mhapb_format_match(&hits[i], line, sizeof line); puts(line); }
+    for (uint64_t i = 0; i < n; i++) {
+        hits[i].from_id -= from_sub;
+        mhapb_format_match(&hits[i], line, sizeof line);
+        const int64_t a = hits[i].from_id, b = hits[i].to_id;
+        if (g_full_ids && !from_sub) {
+            // MatchResult.toString prints fromId.getHeader() / toId.getHeader(): the FASTA names where the ids came from
+            // FASTA files, the decimal ids for sketches read from .dat records
+            auto name = [&](int64_t id) { return (id >= 1 && (size_t)id <= g_names.size() && !g_names[(size_t)id - 1].empty()) ? g_names[(size_t)id - 1] : std::to_string(id); };
+            const char *rest = strchr(line, ' ');
+            rest = rest ? strchr(rest + 1, ' ') : nullptr;
+            printf("%s %s%s\n", name(a).c_str(), name(b).c_str(), rest ? rest : "");
+        } else puts(line);
+    }
     fflush(stdout);
     mhapb_free(hits);
     tot.st.elements_processed += st.elements_processed; tot.st.sequences_hit += st.sequences_hit;
@@ -233,6 +254,7 @@ void emit(mhapb_hit *hits, uint64_t n, const mhapb_stats &st, Totals &tot, int64
 int main(int argc, char **argv)
 {
     Options o = parse(argc, argv);
+    g_full_ids = o.store_full_id;
     const double t_total = now_s();
     mhapb_ctx *ctx = nullptr;
     if (mhapb_create(o.device, &ctx)) die(mhapb_last_error(nullptr));

@@ -11,7 +11,8 @@ extern "C" void mhapb_host_free(void *p) { free(p); }
 int main(int argc, char **argv)
 {
     if (argc < 4) return 2;
-    mhapb_host::FastaStream fs(argv[1], atoi(argv[2]), (size_t)atoll(argv[3]));
+    const bool headers = argc > 4;
+    mhapb_host::FastaStream fs(argv[1], atoi(argv[2]), (size_t)atoll(argv[3]), headers);
     if (fs.open_failed()) { printf("ERROR open\n"); return 1; }
     long long n = 0; int ended = 0;
     while (mhapb_host::FastaBatch *b = fs.next()) {
@@ -19,7 +20,8 @@ int main(int argc, char **argv)
         for (uint32_t i = 0; i < b->n_reads(); i++) {
             unsigned long long h = 1469598103934665603ull;
             for (uint64_t j = b->offsets[i]; j < b->offsets[i + 1]; j++) { h ^= (unsigned char)b->bases[j]; h *= 1099511628211ull; }
-            printf("%lld %llu %llu\n", n++, (unsigned long long)(b->offsets[i + 1] - b->offsets[i]), h);
+            if (headers) printf("%lld %llu %llu [%s]\n", n++, (unsigned long long)(b->offsets[i + 1] - b->offsets[i]), h, b->headers[i].c_str());
+            else printf("%lld %llu %llu\n", n++, (unsigned long long)(b->offsets[i + 1] - b->offsets[i]), h);
         }
         ended |= b->ended;
     }

@@ -25,11 +25,14 @@ def reference_parse(text: bytes):
         lines.pop()
     lines = [l[:-1] if l.endswith(b"\r") else l for l in lines]
     recs, i = [], 0
+    HEADERS.clear()
     if not lines:
         return recs, False, None
     while i < len(lines):
         if not lines[i] or lines[i][:1] != b">":
             return recs, False, "Next sequence does not start with >. Invalid format."
+        import re
+        HEADERS.append(re.split(rb"[\s,]+", lines[i][1:], maxsplit=1)[0])      # FastaData.java:155-156
         i += 1
         seq = b""
         while i < len(lines) and lines[i][:1] != b">":
@@ -41,6 +44,9 @@ def reference_parse(text: bytes):
     return recs, False, None
 
 
+HEADERS = []
+
+
 def fnv(b):
     h = 1469598103934665603
     for c in b:
@@ -48,8 +54,8 @@ def fnv(b):
     return h
 
 
-def run(harness, path, threads, chunk):
-    out = subprocess.run([harness, path, str(threads), str(chunk)], capture_output=True, text=True, timeout=120).stdout.splitlines()
+def run(harness, path, threads, chunk, headers=False):
+    out = subprocess.run([harness, path, str(threads), str(chunk)] + (["h"] if headers else []), capture_output=True, text=True, timeout=120).stdout.splitlines()
     return out
 
 
@@ -68,6 +74,9 @@ def check(harness, tmp_path, text, name="x.fa", configs=((1, 1 << 16), (3, 1 << 
             continue
         assert out[-1] == f"END {len(recs)} {int(ended)}", (threads, chunk, out[-1])
         assert out[:-1] == [f"{i} {len(r)} {fnv(r)}" for i, r in enumerate(recs)], (threads, chunk)
+    if not err:
+        out = run(harness, str(p), 2, 1 << 16, headers=True)
+        assert out[:-1] == [f"{i} {len(r)} {fnv(r)} [{HEADERS[i].decode()}]" for i, r in enumerate(recs)]
 
 
 def make(rng, n, lo, hi, width=70, crlf=False, weird=True):
@@ -76,7 +85,7 @@ def make(rng, n, lo, hi, width=70, crlf=False, weird=True):
     for i in range(n):
         L = rng.randint(lo, hi)
         s = bytes(rng.choice(b"ACGTacgtN") for _ in range(L))
-        parts.append(b">read_%d some > text" % i + nl)
+        parts.append((b">read_%d some > text" % i if i % 3 else b">r%d,x y" % i) + nl)
         for j in range(0, L, width):
             line = s[j:j + width]
             if weird and rng.random() < 0.02 and len(line) > 2:

@@ -165,6 +165,23 @@ def test_streamed_batches_and_gzip_input_equal_the_single_batch_run(tmp_path):
     assert (d1 / "store.dat").read_bytes() == (d2 / "store_gz.dat").read_bytes()
 
 
+def test_store_full_id_prints_fasta_names(tmp_path):
+    # --store-full-id (main/MhapMain.java:301-304, impl/FastaData.java:155-156): the first token of the header line replaces the
+    # file position in both id columns; query ids continue after the store's
+    store, query = _reads(100, 2000, 21), _reads(60, 2000, 22)
+    fa, qa = tmp_path / "store.fasta", tmp_path / "query.fasta"
+    _write_fasta(fa, store)        # headers ">read_<i> some description"
+    _write_fasta(qa, query)
+    num, _ = _run(["-s", str(fa), "-q", str(qa), "--num-hashes", "256"])
+    named, _ = _run(["-s", str(fa), "-q", str(qa), "--num-hashes", "256", "--store-full-id"], env={"MHAPB_FASTA_CHUNK_KB": "64"})
+    names = {i + 1: f"read_{i}" for i in range(100)}
+    names.update({101 + i: f"read_{i}" for i in range(60)})
+    def rename(line):
+        f = line.split(" ")
+        return " ".join([names[int(f[0])], names[int(f[1])]] + f[2:])
+    assert sorted(map(rename, num)) == named and len(named) > 50
+
+
 def test_bad_arguments_exit_like_the_reference(tmp_path):
     p = subprocess.run([CLI], capture_output=True, text=True)
     assert p.returncode == 1 and "Please set the -s or the -p options." in p.stdout
