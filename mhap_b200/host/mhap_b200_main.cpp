@@ -150,12 +150,14 @@ size_t fasta_chunk_bytes(const std::string &path)
     return chunk;
 }
 
-// --store-full-id: header string of every sequence id seen so far (id = 1-based position + offset, SequenceId.getHeader())
-std::vector<std::string> g_names;
+// --store-full-id: SequenceId.getHeader() of the sequences of one FASTA file, indexed by position in the file.  Kept per
+// file, not per id: the ids of a query file start at the number of STORED sequences (main/MhapMain.java:462,537), which can
+// overlap the file positions of the store when short reads were skipped.
+typedef std::vector<std::string> Names;
 bool g_full_ids = false;
 
 template <class F>
-int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int threads, F fn)
+int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int threads, Names *names, F fn)
 {
     if (ends_with(path, ".bz2")) die("bzip2 FASTA is not supported by mhap-b200: " + path);
     const size_t chunk = fasta_chunk_bytes(path);
@@ -174,10 +176,7 @@ int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int thread
         if (nb) {
             ids.resize(nb);
             for (uint32_t i = 0; i < nb; i++) ids[i] = n + i + 1 + offset;
-            if (g_full_ids) {
-                if (g_names.size() < (size_t)(n + nb + offset)) g_names.resize((size_t)(n + nb + offset));
-                for (uint32_t i = 0; i < nb; i++) g_names[(size_t)(ids[i] - 1)] = b->headers[i];
-            }
+            if (g_full_ids && names) names->insert(names->end(), b->headers.begin(), b->headers.end());
             fn(*b, ids);
             n += nb;
         }
@@ -225,21 +224,24 @@ struct Totals { mhapb_stats st{}; };
 
 // from_sub: sketches read from a .dat file print the header string stored in the record, i.e. the
 // file-local id without the run's offset (impl/SequenceId.java:102-108, SequenceSketch.java:75)
-void emit(mhapb_hit *hits, uint64_t n, const mhapb_stats &st, Totals &tot, int64_t from_sub = 0)
+void emit(mhapb_hit *hits, uint64_t n, const mhapb_stats &st, Totals &tot, int64_t from_sub = 0,
+          const Names *from_names = nullptr, int64_t from_offset = 0, const Names *to_names = nullptr)
 {
     // AbstractMatchSearch.outputResults :316-338: one MatchResult.toString() per line on stdout
     char line[256];
+    auto name = [](const Names *t, int64_t pos, int64_t id) {
+        return (t && pos >= 0 && (size_t)pos < t->size()) ? (*t)[(size_t)pos] : std::to_string(id);
+    };
     for (uint64_t i = 0; i < n; i++) {
         hits[i].from_id -= from_sub;
         mhapb_format_match(&hits[i], line, sizeof line);
-        const int64_t a = hits[i].from_id, b = hits[i].to_id;
-        if (g_full_ids && !from_sub) {
-            // MatchResult.toString prints fromId.getHeader() / toId.getHeader(): the FASTA names where the ids came from
+        if (g_full_ids && (from_names || to_names)) {
+            // MatchResult.toString prints fromId.getHeader() / toId.getHeader(): the FASTA names where the sequences came from
             // FASTA files, the decimal ids for sketches read from .dat records
-            auto name = [&](int64_t id) { return (id >= 1 && (size_t)id <= g_names.size() && !g_names[(size_t)id - 1].empty()) ? g_names[(size_t)id - 1] : std::to_string(id); };
             const char *rest = strchr(line, ' ');
             rest = rest ? strchr(rest + 1, ' ') : nullptr;
-            printf("%s %s%s\n", name(a).c_str(), name(b).c_str(), rest ? rest : "");
+            printf("%s %s%s\n", name(from_names, hits[i].from_id - 1 - from_offset, hits[i].from_id).c_str(),
+                   name(to_names, hits[i].to_id - 1, hits[i].to_id).c_str(), rest ? rest : "");
         } else puts(line);
     }
     fflush(stdout);
@@ -286,7 +288,7 @@ int main(int argc, char **argv)
             std::ofstream out(outp, std::ios::binary);
             if (!out) die("Could not open " + outp);
             uint32_t nrec = 0;
-            for_each_fasta_batch(pf, 0, o.num_threads, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
+            for_each_fasta_batch(pf, 0, o.num_threads, nullptr, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
                 uint8_t *blob = nullptr; uint64_t len = 0; uint32_t nr = 0;
                 ck(ctx, mhapb_sketch_to_dat(ctx, &p, b.bases, b.offsets.data(), ids.data(), b.n_reads(), 1, &blob, &len, &nr));
                 out.write((const char *)blob, (std::streamsize)len);
@@ -305,6 +307,7 @@ int main(int argc, char **argv)
     fprintf(stderr, "Processing files for storage in reverse index...\n");
     const double t_proc = now_s();
     int64_t n_sketches = 0;
+    Names store_names;   // empty for .dat stores: ids print as numbers
     if (ends_with(o.s, ".dat")) {
         DatSketches d = read_dat(o.s, 0);
         if (d.n && d.H != o.num_hashes) die("Number of MinHashes of the sequence does not match current settings.");   // MinHashSearch.java:105
@@ -320,7 +323,7 @@ int main(int argc, char **argv)
         }
         struct stat fst;
         const double file_bytes = (!ends_with(o.s, ".gz") && stat(o.s.c_str(), &fst) == 0) ? (double)fst.st_size : 0.0;
-        for_each_fasta_batch(o.s, 0, o.num_threads, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
+        for_each_fasta_batch(o.s, 0, o.num_threads, &store_names, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
             if (b.seq == 0 && file_bytes > 0 && b.text_len > 0 && (double)b.text_len < file_bytes) {
                 // size the store once from the first batch's record density instead of growing it batch by batch
                 const double est_reads = file_bytes / (double)b.text_len * b.n_reads() * 1.03 + 64;
@@ -345,7 +348,7 @@ int main(int argc, char **argv)
         if (n_sketches > 0) {
             mhapb_hit *hits = nullptr; uint64_t n = 0; mhapb_stats st{};
             ck(ctx, mhapb_search_self(ctx, &sp, &hits, &n, &st));
-            emit(hits, n, st, tot);
+            emit(hits, n, st, tot, 0, store_names.empty() ? nullptr : &store_names, 0, store_names.empty() ? nullptr : &store_names);
         }
         fprintf(stderr, "Time (s) to score and output to self: %g\n", now_s() - t0);
     };
@@ -365,10 +368,11 @@ int main(int argc, char **argv)
                 processed = st.sequences_searched;
                 from_sub = seq_number_processed;
             } else {
-                for_each_fasta_batch(cf, seq_number_processed, o.num_threads, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
+                Names query_names;
+                for_each_fasta_batch(cf, seq_number_processed, o.num_threads, &query_names, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
                     mhapb_hit *bh = nullptr; uint64_t bn = 0; mhapb_stats bst{};
                     ck(ctx, mhapb_search_query_reads(ctx, &sp, b.bases, b.offsets.data(), ids.data(), b.n_reads(), &bh, &bn, &bst));
-                    emit(bh, bn, bst, tot);
+                    emit(bh, bn, bst, tot, 0, &query_names, seq_number_processed, store_names.empty() ? nullptr : &store_names);
                     processed += bst.sequences_searched;
                 });
             }
