@@ -424,16 +424,6 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
             CU(ctx, ctx->ovl.ensure((size_t)nc * sizeof(OverlapOut)));
             CU(ctx, ctx->ovf_list.ensure((size_t)nc * 4 + 16));
             CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 64, ctx->stream));
-            // more queries than local sketches (multi-GPU: all ranks' queries against this rank's shard): a query then has
-            // fewer than one candidate here on average and consecutive candidates share no sketch -- reorder by target
-            const Candidate *cand_in = ctx->cand.as<Candidate>();
-            if ((int64_t)nq > s.n) {
-                const size_t tb = sort_candidates_tmp_bytes(nc);
-                CU(ctx, ctx->fscratch.ensure(tb));
-                CU(ctx, ctx->cand2.ensure(nc * sizeof(Candidate)));
-                CU(ctx, launch_sort_candidates_by_target(ctx->stream, cand_in, nc, (uint32_t)s.n, ctx->fscratch.p, tb, ctx->cand2.as<Candidate>(), &launches));
-                CU(ctx, cudaMemcpyAsync(ctx->cand.p, ctx->cand2.p, nc * sizeof(Candidate), cudaMemcpyDeviceToDevice, ctx->stream));
-            }
             FilterArgs f{};
             f.cand = ctx->cand.as<Candidate>(); f.n_cand = nc;
             f.q_ord = q.d_ord; f.q_ord_n = q.d_ordn; f.q_lenk = q.d_lenk; f.q_stride = q.ord_stride;

@@ -129,14 +129,6 @@ cudaError_t launch_filter_warp(cudaStream_t st, FilterArgs a, int *launches);
 cudaError_t launch_compact_hits(cudaStream_t st, const Candidate *cand, const OverlapOut *ovl, uint64_t n, double jmin, int keep_all,
                                 Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *d_count, int *launches);
 
-// Reorders candidates by target (stable: within a target the probe's order is kept) into cand_out.  Used when the queries
-// outnumber the local sketches (multi-GPU: every rank sees all ranks' queries), where consecutive candidates otherwise share
-// neither sketch; sorted by target, the candidates of one target reuse its ordered sketch from L2.
-// d_tmp: scratch of at least sort_candidates_tmp_bytes(n) bytes.
-size_t sort_candidates_tmp_bytes(uint64_t n);
-cudaError_t launch_sort_candidates_by_target(cudaStream_t st, const Candidate *cand, uint64_t n, uint32_t n_targets, void *d_tmp,
-                                             size_t tmp_bytes, Candidate *cand_out, int *launches);
-
 cudaError_t launch_equal_count(cudaStream_t st, const int32_t *a, const int32_t *b, int H, int32_t *d_out, int *launches);
 
 } // namespace mhapb

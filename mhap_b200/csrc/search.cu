@@ -10,8 +10,6 @@
 // HBM / L2 random-access bound integer work; no tensor cores.
 #include "engine.h"
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <cstdlib>
 
@@ -886,47 +884,6 @@ cudaError_t launch_equal_count(cudaStream_t st, const int32_t *a, const int32_t 
     if (e != cudaSuccess) return e;
     k_equal_count<<<1, 128, 0, st>>>(a, b, H, d_out);
     (*launches)++;
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// candidate reordering by target (see engine.h)
-// ---------------------------------------------------------------------------------------------
-__global__ void k_cand_keys(const Candidate *__restrict__ cand, uint64_t n, uint32_t *keys, uint32_t *vals)
-{
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) { keys[i] = cand[i].t; vals[i] = (uint32_t)i; }
-}
-__global__ void k_cand_gather(const Candidate *__restrict__ cand, const uint32_t *__restrict__ vals, uint64_t n, Candidate *out)
-{
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = cand[vals[i]];
-}
-
-static size_t cub_sort_bytes(uint64_t n)
-{
-    size_t b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
-    return (b + 255) & ~(size_t)255;
-}
-size_t sort_candidates_tmp_bytes(uint64_t n) { return cub_sort_bytes(n) + 4 * ((n * 4 + 255) & ~(uint64_t)255); }
-
-cudaError_t launch_sort_candidates_by_target(cudaStream_t st, const Candidate *cand, uint64_t n, uint32_t n_targets, void *d_tmp,
-                                             size_t tmp_bytes, Candidate *cand_out, int *launches)
-{
-    if (n == 0) return cudaSuccess;
-    if (n > 0x7fffffffull) return cudaErrorInvalidValue;
-    const size_t arr = (n * 4 + 255) & ~(uint64_t)255, cb = cub_sort_bytes(n);
-    if (tmp_bytes < cb + 4 * arr) return cudaErrorInvalidValue;
-    uint8_t *p = (uint8_t *)d_tmp;
-    uint32_t *k0 = (uint32_t *)p, *v0 = (uint32_t *)(p + arr), *k1 = (uint32_t *)(p + 2 * arr), *v1 = (uint32_t *)(p + 3 * arr);
-    void *ctmp = p + 4 * arr;
-    const int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-    k_cand_keys<<<grid, 256, 0, st>>>(cand, n, k0, v0);
-    int bits = 1; while ((1ull << bits) < (uint64_t)n_targets && bits < 32) bits++;
-    size_t cbb = cb;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(ctmp, cbb, k0, k1, v0, v1, (int)n, 0, bits, st);
-    if (e != cudaSuccess) return e;
-    k_cand_gather<<<grid, 256, 0, st>>>(cand, v1, n, cand_out);
-    (*launches) += 2;
     return cudaGetLastError();
 }
 
