@@ -230,3 +230,23 @@ def test_capacity_hints_change_nothing():
     e.store_add_reads(bases[int(offs[half]):], offs[half:] - offs[half], ids=np.arange(half + 1, 401, dtype=np.int64))
     h1, s1 = e.search_self(sp)
     assert s0 == s1 and sorted(map(hit_key, h0)) == sorted(map(hit_key, h1)) and len(h0) > 100
+
+
+def test_more_queries_than_stored_sketches():
+    # the multi-GPU shape seen from one rank: all ranks' queries against one rank's (small) shard
+    g = synth.genome(41, 30000)
+    sb, so = synth.reads(g, 3, 0, 60, 2000, 0.05)
+    qb, qo = synth.reads(g, 4, 0, 500, 2000, 0.05)
+    p = native.SketchParams(16, 128, 12, 500, 0, 116)
+    e = engine()
+    e.store_reset(p)
+    e.store_add_reads(sb, so)
+    qids = np.arange(1, 501, dtype=np.int64) + 60
+    hits, stats = e.search_query_reads(native.SearchParams(3, 0, 0.2, 0.78, 1, 0, 0, -1), qb, qo, ids=qids)
+    ost = orc.Store(num_hashes=128, ordered_size=500)
+    ost.add_reads(sb, so, threads=4)
+    oq = orc.Store(num_hashes=128, ordered_size=500)
+    oq.add_reads(qb, qo, ids=qids, both_strands=False, threads=4)
+    res = ost.search_query(oq, keep_all=True, threads=4)
+    assert_same_hits(hits, res.hits, stats, res.stats)
+    assert len(hits) > 500
