@@ -10,10 +10,12 @@
 // Semantics kept from the reference: records start with '>', the header text is ignored (numeric ids), sequence lines
 // are concatenated, '\r' is dropped, a first line that is not a header is "Next sequence does not start with >. Invalid
 // format.", and an EMPTY record ends the file (enqueueNextSequenceInFile returns false on a zero-length sequence).
-// Upper-casing (FastaData.java:194) happens on the GPU.  .bz2 is not supported (no bzlib header in this image).
+// Upper-casing (FastaData.java:194) happens on the GPU.  .bz2 goes through libbz2's high-level API, bound with dlopen
+// (the image ships libbz2.so.1.0 but no bzlib.h; the three prototypes used are part of its stable C ABI).
 #pragma once
 #include "../../include/mhap_b200.h"
 
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <chrono>
@@ -52,9 +54,20 @@ public:
     {
         const size_t n = path.size();
         gz_ = n > 3 && path.compare(n - 3, 3, ".gz") == 0;
+        bz_ = n > 4 && path.compare(n - 4, 4, ".bz2") == 0;
         if (gz_) { gzf_ = gzopen(path.c_str(), "rb"); if (gzf_) gzbuffer(gzf_, 1u << 20); }
+        else if (bz_) {
+            // BZFILE *BZ2_bzopen(const char *path, const char *mode); int BZ2_bzread(BZFILE *, void *, int); void BZ2_bzclose(BZFILE *)
+            for (const char *lib : {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so"}) if ((bzlib_ = dlopen(lib, RTLD_NOW))) break;
+            if (bzlib_) {
+                bz_open_ = (void *(*)(const char *, const char *))dlsym(bzlib_, "BZ2_bzopen");
+                bz_read_ = (int (*)(void *, void *, int))dlsym(bzlib_, "BZ2_bzread");
+                bz_close_ = (void (*)(void *))dlsym(bzlib_, "BZ2_bzclose");
+                if (bz_open_ && bz_read_ && bz_close_) bzf_ = bz_open_(path.c_str(), "rb");
+            }
+        }
         else fp_ = fopen(path.c_str(), "rb");
-        if (!gzf_ && !fp_) { open_failed_ = true; return; }
+        if (!gzf_ && !fp_ && !bzf_) { open_failed_ = true; return; }
         if (parser_threads < 1) parser_threads = 1;
         // batches in flight: one being read, one per parser, one with the consumer -- but no more than 4, so that the
         // pinned buffers are reused instead of page-locking the whole file once
@@ -78,6 +91,8 @@ public:
         for (auto *b : work_) drop(b);
         if (held_) drop(held_);
         if (gzf_) gzclose(gzf_);
+        if (bzf_) bz_close_(bzf_);
+        if (bzlib_) dlclose(bzlib_);
         if (fp_) fclose(fp_);
     }
     bool open_failed() const { return open_failed_; }
@@ -103,6 +118,7 @@ private:
     size_t read_some(char *dst, size_t want)
     {
         if (gz_) { int r = gzread(gzf_, dst, (unsigned)std::min<size_t>(want, 1u << 30)); return r > 0 ? (size_t)r : 0; }
+        if (bz_) { int r = bz_read_(bzf_, dst, (int)std::min<size_t>(want, 1u << 30)); return r > 0 ? (size_t)r : 0; }
         return fread(dst, 1, want, fp_);
     }
 
@@ -239,7 +255,11 @@ private:
 
     std::string path_;
     size_t chunk_;
-    bool gz_ = false, open_failed_ = false, keep_headers_ = false;
+    bool gz_ = false, bz_ = false, open_failed_ = false, keep_headers_ = false;
+    void *bzlib_ = nullptr, *bzf_ = nullptr;
+    void *(*bz_open_)(const char *, const char *) = nullptr;
+    int (*bz_read_)(void *, void *, int) = nullptr;
+    void (*bz_close_)(void *) = nullptr;
     gzFile gzf_ = nullptr;
     FILE *fp_ = nullptr;
     std::mutex mu_;

@@ -7,11 +7,10 @@
 //   -s <fasta|dat> -q <file|dir>   store vs query files              (:478-541), --no-self
 //   -p <fasta|dir> -q <outdir>     FASTA -> .dat sketch files        (:384-451)
 //   -f <filter file> [--filter-threshold --repeat-idf-scale --supress-noise --no-tf]   k-mer filter / tf-idf
-//                                  weights (main/MhapMain.java:340-372, sketch/FrequencyCounts.java), plain text only
-// FASTA input (plain or .gz) is streamed: a reader thread + --num-threads parser threads fill pinned batches while the
+//                                  weights (main/MhapMain.java:340-372, sketch/FrequencyCounts.java); plain, .gz or .bz2
+// FASTA input (plain, .gz or .bz2) is streamed: a reader thread + --num-threads parser threads fill pinned batches while the
 // GPU works on the previous one (fasta_stream.hpp).  --store-full-id prints the first token of the FASTA headers instead of
 // the file positions (impl/FastaData.java:155-156, impl/SequenceId.java; ignored for .dat input like the reference).
-// Not supported: .bz2 input.
 // Paths cited are relative to /root/reference/src/main/java/edu/umd/marbl/mhap/.
 #include "../../include/mhap_b200.h"
 #include "fasta_stream.hpp"
@@ -146,7 +145,7 @@ size_t fasta_chunk_bytes(const std::string &path)
     struct stat st;
     size_t chunk = 64u << 20;
     if (const char *e = getenv("MHAPB_FASTA_CHUNK_KB")) chunk = (size_t)std::max(64, atoi(e)) << 10;
-    if (!ends_with(path, ".gz") && stat(path.c_str(), &st) == 0 && (size_t)st.st_size + 4096 < chunk) chunk = (size_t)st.st_size + 4096;
+    if (!ends_with(path, ".gz") && !ends_with(path, ".bz2") && stat(path.c_str(), &st) == 0 && (size_t)st.st_size + 4096 < chunk) chunk = (size_t)st.st_size + 4096;
     return chunk;
 }
 
@@ -159,7 +158,6 @@ bool g_full_ids = false;
 template <class F>
 int64_t for_each_fasta_batch(const std::string &path, int64_t offset, int threads, Names *names, F fn)
 {
-    if (ends_with(path, ".bz2")) die("bzip2 FASTA is not supported by mhap-b200: " + path);
     const size_t chunk = fasta_chunk_bytes(path);
     mhapb_host::FastaStream fs(path, std::max(1, std::min(threads, 8)), chunk, g_full_ids);
     if (fs.open_failed()) die("Could not open " + path);
@@ -194,6 +192,33 @@ std::vector<uint8_t> read_file(const std::string &path)
     in.seekg(0);
     in.read((char *)buf.data(), (std::streamsize)buf.size());
     return buf;
+}
+
+// utils/Utils.java getFile: plain, .gz or .bz2 text (the -f filter file)
+std::vector<uint8_t> read_text_any(const std::string &path)
+{
+    if (!ends_with(path, ".gz") && !ends_with(path, ".bz2")) return read_file(path);
+    std::vector<uint8_t> out;
+    std::vector<uint8_t> buf(1u << 20);
+    if (ends_with(path, ".gz")) {
+        gzFile f = gzopen(path.c_str(), "rb");
+        if (!f) die("Could not open " + path);
+        for (int r; (r = gzread(f, buf.data(), (unsigned)buf.size())) > 0;) out.insert(out.end(), buf.begin(), buf.begin() + r);
+        gzclose(f);
+        return out;
+    }
+    void *lib = nullptr;
+    for (const char *l : {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so"}) if ((lib = dlopen(l, RTLD_NOW))) break;
+    if (!lib) die("libbz2 not found, cannot read " + path);
+    auto bzopen = (void *(*)(const char *, const char *))dlsym(lib, "BZ2_bzopen");
+    auto bzread = (int (*)(void *, void *, int))dlsym(lib, "BZ2_bzread");
+    auto bzclose = (void (*)(void *))dlsym(lib, "BZ2_bzclose");
+    void *f = (bzopen && bzread && bzclose) ? bzopen(path.c_str(), "rb") : nullptr;
+    if (!f) die("Could not open " + path);
+    for (int r; (r = bzread(f, buf.data(), (int)buf.size())) > 0;) out.insert(out.end(), buf.begin(), buf.begin() + r);
+    bzclose(f);
+    dlclose(lib);
+    return out;
 }
 
 struct DatSketches {
@@ -265,8 +290,7 @@ int main(int argc, char **argv)
     if (!o.f.empty()) {   // main/MhapMain.java:340-372: read the k-mer filter set
         const double t0 = now_s();
         fprintf(stderr, "Reading in filter file %s.\n", o.f.c_str());
-        if (ends_with(o.f, ".gz") || ends_with(o.f, ".bz2")) die("compressed filter files are not supported by mhap-b200: " + o.f);
-        std::vector<uint8_t> text = read_file(o.f);
+        std::vector<uint8_t> text = read_text_any(o.f);
         mhapb_filter_params fp{o.filter_threshold, o.repeat_weight, o.repeat_idf_scale, o.supress_noise, o.no_tf ? 1 : 0};
         int64_t n_repeat = 0;
         if (mhapb_filter_load_text(ctx, &fp, (const char *)text.data(), text.size(), o.no_rc ? 0 : 1, &n_repeat))
@@ -282,6 +306,7 @@ int main(int argc, char **argv)
             const double t0 = now_s();
             std::string name = pf.substr(pf.find_last_of('/') == std::string::npos ? 0 : pf.find_last_of('/') + 1);
             if (ends_with(name, ".gz")) name = name.substr(0, name.size() - 3);
+            else if (ends_with(name, ".bz2")) name = name.substr(0, name.size() - 4);
             size_t dot = name.find_last_of('.');
             if (dot != std::string::npos && dot > 0) name = name.substr(0, dot);
             std::string outp = o.q + "/" + name + ".dat";
@@ -322,7 +347,7 @@ int main(int argc, char **argv)
             ck(ctx, mhapb_sketch_reserve(ctx, &p, chunk, (uint32_t)std::min<size_t>(chunk / 500 + 64, 1u << 24), 1));
         }
         struct stat fst;
-        const double file_bytes = (!ends_with(o.s, ".gz") && stat(o.s.c_str(), &fst) == 0) ? (double)fst.st_size : 0.0;
+        const double file_bytes = (!ends_with(o.s, ".gz") && !ends_with(o.s, ".bz2") && stat(o.s.c_str(), &fst) == 0) ? (double)fst.st_size : 0.0;
         for_each_fasta_batch(o.s, 0, o.num_threads, &store_names, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
             if (b.seq == 0 && file_bytes > 0 && b.text_len > 0 && (double)b.text_len < file_bytes) {
                 // size the store once from the first batch's record density instead of growing it batch by batch

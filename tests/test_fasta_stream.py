@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def harness(tmp_path_factory):
     out = tmp_path_factory.mktemp("fs") / "fasta_stream_test"
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", str(out), os.path.join(ROOT, "tests", "cpp", "fasta_stream_test.cpp"), "-lz"])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", str(out), os.path.join(ROOT, "tests", "cpp", "fasta_stream_test.cpp"), "-lz", "-ldl"])
     return str(out)
 
 
@@ -64,6 +64,9 @@ def check(harness, tmp_path, text, name="x.fa", configs=((1, 1 << 16), (3, 1 << 
     if name.endswith(".gz"):
         with gzip.open(p, "wb") as f:
             f.write(text)
+    elif name.endswith(".bz2"):
+        import bz2
+        p.write_bytes(bz2.compress(text))
     else:
         p.write_bytes(text)
     recs, ended, err = reference_parse(text)
@@ -109,6 +112,7 @@ def test_record_larger_than_chunk_and_gzip(harness, tmp_path):
     text = make(rng, 5, 100, 200) + make(rng, 1, 400000, 400000, weird=False) + make(rng, 20, 100, 5000)
     check(harness, tmp_path, text, name="big.fa")
     check(harness, tmp_path, text, name="big.fa.gz", configs=((2, 1 << 16), (1, 1 << 20)))
+    check(harness, tmp_path, text, name="big.fa.bz2", configs=((2, 1 << 16), (1, 1 << 20)))
 
 
 def test_empty_record_ends_the_file_and_bad_first_line(harness, tmp_path):

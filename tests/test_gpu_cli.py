@@ -127,8 +127,14 @@ def test_self_overlap_with_kmer_filter_file(tmp_path, extra, kw):
     rng = random.Random(2)
     kmers = sorted({r[i:i + 16].decode().upper() for r in reads[:60] for i in range(0, max(0, len(r) - 16), 11)})
     text = "\n".join([f"{len(kmers)} {len(kmers)}"] + [f"{km}\t{rng.choice([5e-6, 4e-5, 1e-3, 0.02])}" for km in kmers]) + "\n"
-    ff = tmp_path / "repeats.txt"
-    ff.write_text(text)
+    if extra:                                    # compressed filter files go through the same reader (utils/Utils.java getFile)
+        import gzip
+        ff = tmp_path / "repeats.txt.gz"
+        with gzip.open(ff, "wt") as g:
+            g.write(text)
+    else:
+        ff = tmp_path / "repeats.txt"
+        ff.write_text(text)
     got, err = _run(["-s", str(fa), "-f", str(ff), "--num-hashes", "256"] + extra)
     rw = kw.get("repeat_weight", 0.9)
     f = orc.KmerFilter(text, **kw)
