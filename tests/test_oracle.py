@@ -229,3 +229,17 @@ def test_dat_record_layout():
     assert struct.unpack(">iii", q[24:36]) == (89, 12, 2)
     assert struct.unpack(">4i", q[36:52]) == (-5, 7, 6, 0)
     assert len(q) == 52
+
+
+def test_pin_cases_self_consistent():
+    # tests/golden/pin_*.txt are the cases integration/PinOracle.java feeds to the REAL reference on a box with a JDK
+    # (tests/golden/check_against_jvm.py diffs its output against the oracle).  Here: the committed expectation is what the
+    # oracle says today, so the files a maintainer would diff against cannot drift silently.
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("check_against_jvm", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "check_against_jvm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lines, text, out = mod.oracle_output()
+    assert open(mod.CASES).read().splitlines() == lines
+    assert open(mod.FILTER).read() == text
+    assert open(mod.EXPECTED).read().splitlines() == out
