@@ -243,3 +243,19 @@ def test_pin_cases_self_consistent():
     assert open(mod.CASES).read().splitlines() == lines
     assert open(mod.FILTER).read() == text
     assert open(mod.EXPECTED).read().splitlines() == out
+
+
+def test_murmur3_x86_32_against_an_independent_library():
+    # scikit-learn ships its own MurmurHash3_x86_32 (Appleby's reference C, wrapped in Cython): a third implementation,
+    # not written by us, agreeing with the oracle on random inputs and seeds -- and on every ordered k-mer of a read
+    # fed the way Hasher.putUnencodedChars feeds it (UTF-16LE).
+    murmurhash3_32 = pytest.importorskip("sklearn.utils").murmurhash3_32
+    rng = random.Random(1)
+    for _ in range(3000):
+        b = bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 70)))
+        seed = rng.getrandbits(32)
+        assert orc.murmur3_x86_32(b, seed) == murmurhash3_32(b, seed=seed, positive=True)
+    seq = "".join(rng.choice("ACGTN") for _ in range(300))
+    got = orc.kmer_hashes_int(seq, 12)
+    exp = [murmurhash3_32(seq[i:i + 12].encode("utf-16-le"), seed=0, positive=False) for i in range(len(seq) - 11)]
+    assert got.tolist() == exp
