@@ -133,3 +133,23 @@ def test_filter_argument_errors():
     e.filter_load_text("1 1\nACGTACGTACGTACGT 0.5\n", repeat_weight=-1.0)
     with pytest.raises(native.MhapError):                                            # unweighted flag must agree
         e.sketch(*native.pack_reads(["ACGT" * 50]), native.SketchParams(16, 8, 12, 8, 0, 0))
+
+
+def test_long_read_h1024_with_filter():
+    # strands above 16384 k-mers take K1a's global-table path, H = 1024 the B=32 lock-step instantiation; both with tf-idf
+    # weights (light weight 3) and a few repeat k-mers carrying their own weights
+    rng = random.Random(12)
+    g = "".join(rng.choice("ACGT") for _ in range(21000))
+    reads = [g[:20000], g[500:18000] + g[500:3000]]           # the second read repeats 2.5 kbp of itself (tf > 1)
+    kmers = sorted({r[i:i + 16] for r in reads for i in range(0, 15000, 5)})
+    text = "\n".join([f"{len(kmers)} {len(kmers)}"] + [f"{km} {rng.choice([2e-6, 2e-5, 1e-3])}" for km in kmers]) + "\n"
+    e = engine()
+    e.filter_load_text(text)
+    f = orc.KmerFilter(text)
+    H = 1024
+    p = native.SketchParams(16, H, 12, 1536, 0, 116)
+    mh, _, _, st = e.sketch(*native.pack_reads(reads), p, both_strands=True, want_ord=False)
+    assert st.tolist() == [0, 0]
+    for i, r in enumerate(reads):
+        assert (mh[2 * i] == orc.minhash_sketch_filtered(r, 16, H, 0.9, f)).all(), i
+        assert (mh[2 * i + 1] == orc.minhash_sketch_filtered(orc.rc(r), 16, H, 0.9, f)).all(), i
