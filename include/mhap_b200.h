@@ -218,11 +218,15 @@ int mhapb_store_reset(mhapb_ctx *ctx, const mhapb_sketch_params *p);
 int mhapb_store_add_reads(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
                           const int64_t *ids, uint32_t n_reads, int both_strands,
                           int64_t *n_added);
-/* Append pre-computed sketches from host arrays (the .dat path, addSequence per record). */
+/* Append pre-computed sketches from host arrays (the .dat path, addSequence per record).  num_hashes and
+ * ordered_kmer_size describe the arrays (a .dat file does not record the run's parameters, only each sketch's
+ * own): a mismatch with the store's parameters fails like the reference does -- "Number of MinHashes of the
+ * sequence does not match current settings." (impl/MinHashSearch.java:105-106), "Sketch k-mer size does not
+ * match between the two sequences." (sketch/BottomOverlapSketch.java:594-595). */
 int mhapb_store_add_sketches(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd,
                              const int32_t *seq_len, const int32_t *seq_len_kmers,
-                             const int32_t *minhash, const int32_t *ord_hash_pos,
-                             const int32_t *ord_n, int32_t ord_stride, uint32_t n);
+                             const int32_t *minhash, int32_t num_hashes, const int32_t *ord_hash_pos,
+                             const int32_t *ord_n, int32_t ord_stride, int32_t ordered_kmer_size, uint32_t n);
 /* Same with the two big blocks (minhash [n][H], ord [n][S][2]) already on this GPU -- the
  * landing buffers of the NCCL all-gather of sketch blocks; the small per-sketch columns stay on
  * the host. */
@@ -241,6 +245,10 @@ int64_t mhapb_store_size(mhapb_ctx *ctx);                          /* AbstractMa
 /* Copy stored sketch idx back to the host (getStoredSequenceHash, AbstractMatchSearch.java:314). */
 int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, int32_t *seq_len,
                     int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n);
+/* Bulk form: stored sketches [first, first+count) into flat host arrays (minhash [count][H], ord [count][ord_stride][2]
+ * with ord_stride from mhapb_store_device_ptrs, rows zero-padded past ord_n).  Any pointer may be NULL. */
+int mhapb_store_get_range(mhapb_ctx *ctx, int64_t first, int64_t count, int64_t *ids, uint8_t *is_fwd, int32_t *seq_len,
+                          int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n);
 /* Device views of the store's blocks (for the all-gather): minhash [n][H] and ord [n][S][2]. */
 int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, void **d_ord_n, int64_t *n,
                             int32_t *num_hashes, int32_t *ord_stride);
@@ -259,13 +267,15 @@ int mhapb_search_self(mhapb_ctx *ctx, const mhapb_search_params *sp, mhapb_hit *
 int mhapb_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, const char *bases,
                              const uint64_t *offsets, const int64_t *ids, uint32_t n_reads,
                              mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
-/* Same with query sketches from host arrays (a .dat query file). */
+/* Same with query sketches from host arrays (a .dat query file).  num_hashes / ordered_kmer_size as in
+ * mhapb_store_add_sketches: "Number of hashes does not match. Stored size S, input size I."
+ * (impl/MinHashSearch.java:157-159) and the ordered k-mer size check of getOverlapInfo. */
 int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, const int64_t *ids,
                                 const uint8_t *is_fwd, const int32_t *seq_len,
-                                const int32_t *seq_len_kmers, const int32_t *minhash,
+                                const int32_t *seq_len_kmers, const int32_t *minhash, int32_t num_hashes,
                                 const int32_t *ord_hash_pos, const int32_t *ord_n,
-                                int32_t ord_stride, uint32_t n, mhapb_hit **out, uint64_t *n_out,
-                                mhapb_stats *stats);
+                                int32_t ord_stride, int32_t ordered_kmer_size, uint32_t n, mhapb_hit **out,
+                                uint64_t *n_out, mhapb_stats *stats);
 /* Query sketches whose blocks are already on this GPU (minhash [n][H], ord [n][ord_stride][2], ord_n [n]
  * device pointers; the small columns on the host) against the store.  to_self=1 applies
  * findMatches(sketch, toSelf=true)'s id rules (MinHashSearch.java:200,215-225) -- the multi-GPU self

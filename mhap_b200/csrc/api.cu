@@ -347,6 +347,13 @@ int store_push_meta(mhapb_ctx *ctx, int64_t id, int fwd, int32_t len, int32_t le
     return MHAPB_OK;
 }
 
+// drop the host columns pushed since meta0 (an add that failed after store_push_meta must leave the store as it was)
+void store_rollback_meta(Store &s, size_t meta0)
+{
+    for (size_t i = meta0; i < s.h_id.size(); i++) s.seen.erase(((uint64_t)s.h_id[i] << 1) | s.h_fwd[i]);
+    s.h_id.resize(meta0); s.h_fwd.resize(meta0); s.h_len.resize(meta0); s.h_lenk.resize(meta0); s.h_ordn.resize(meta0);
+}
+
 int index_build(mhapb_ctx *ctx)
 {
     Store &s = ctx->store;
@@ -600,26 +607,29 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
             if (!strand_kept(r, st)) continue;
             int32_t no = (int32_t)len - s.p.ordered_kmer_size + 1;
             int rc = store_push_meta(ctx, ids ? ids[r] : (int64_t)r + 1, st == 0, (int32_t)len, no, std::min(no, s.p.ordered_sketch_size));
-            if (rc) {
-                for (size_t i = meta0; i < s.h_id.size(); i++) s.seen.erase(((uint64_t)s.h_id[i] << 1) | s.h_fwd[i]);
-                s.h_id.resize(meta0); s.h_fwd.resize(meta0); s.h_len.resize(meta0); s.h_lenk.resize(meta0); s.h_ordn.resize(meta0);
-                return rc;
-            }
+            if (rc) { store_rollback_meta(s, meta0); return rc; }
         }
     }
-    int rc = store_reserve(ctx, added);
-    if (rc) return rc;
-    if (!bases_on_device) rc = h2d_bases(ctx, bases, offsets, n_reads);
-    if (rc) return rc;
-    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
-    CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)added * S * 8, ctx->stream));
-    rc = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>());
-    (void)H;
-    if (rc) return rc;
-    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.h2d_ms += ms;
-    s.n = next;
-    s.indexed = false;
-    return store_sync_columns(ctx, n0);
+    // any failure below leaves the store exactly as it was (s.n is only advanced at the end)
+    auto device_part = [&]() -> int {
+        int rc = store_reserve(ctx, added);
+        if (rc) return rc;
+        if (!bases_on_device) rc = h2d_bases(ctx, bases, offsets, n_reads);
+        if (rc) return rc;
+        const size_t S = (size_t)s.ord_stride;
+        CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)added * S * 8, ctx->stream));
+        rc = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>());
+        if (rc) return rc;
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.h2d_ms += ms;
+        s.n = next;
+        s.indexed = false;
+        rc = store_sync_columns(ctx, n0);
+        if (rc) s.n = n0;
+        return rc;
+    };
+    const int rc = device_part();
+    if (rc) store_rollback_meta(s, meta0);
+    return rc;
 }
 
 } // namespace
@@ -944,6 +954,19 @@ int mhapb_store_add_reads(mhapb_ctx *ctx, const char *bases, const uint64_t *off
     return add_reads_locked(ctx, bases, offsets, ids, n_reads, both_strands, n_added);
 }
 
+// the reference's own checks on sketches that did not come from this context's parameters (.dat records):
+// MinHashSearch.java:105-106 / :157-159 (number of hashes) and BottomOverlapSketch.java:594-595 (ordered k-mer size)
+static int check_sketch_shape(mhapb_ctx *ctx, int32_t num_hashes, int32_t ordered_kmer_size, bool query)
+{
+    const Store &s = ctx->store;
+    if (num_hashes != s.p.num_hashes)
+        return query ? fail(ctx, MHAPB_EINVAL, "Number of hashes does not match. Stored size %d, input size %d.", s.p.num_hashes, num_hashes)
+                     : fail(ctx, MHAPB_EINVAL, "Number of MinHashes of the sequence does not match current settings.");
+    if (ordered_kmer_size != s.p.ordered_kmer_size)
+        return fail(ctx, MHAPB_EINVAL, "Sketch k-mer size does not match between the two sequences.");
+    return MHAPB_OK;
+}
+
 static int add_sketches_common(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd, const int32_t *seq_len,
                                const int32_t *seq_len_kmers, const void *minhash, const void *ord, const int32_t *ord_n,
                                int32_t ord_stride, uint32_t n, cudaMemcpyKind kind)
@@ -962,36 +985,41 @@ static int add_sketches_common(mhapb_ctx *ctx, const int64_t *ids, const uint8_t
     const size_t meta0 = s.h_id.size();
     for (uint32_t i = 0; i < n; i++) {
         int rc = store_push_meta(ctx, ids[i], is_fwd[i] != 0, seq_len[i], seq_len_kmers[i], ord_n[i]);
-        if (rc) {
-            for (size_t j = meta0; j < s.h_id.size(); j++) s.seen.erase(((uint64_t)s.h_id[j] << 1) | s.h_fwd[j]);
-            s.h_id.resize(meta0); s.h_fwd.resize(meta0); s.h_len.resize(meta0); s.h_lenk.resize(meta0); s.h_ordn.resize(meta0);
-            return rc;
-        }
+        if (rc) { store_rollback_meta(s, meta0); return rc; }
     }
-    int rc = store_reserve(ctx, n);
-    if (rc) return rc;
-    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
     const int64_t n0 = s.n;
-    CU(ctx, cudaMemcpyAsync(s.minhash.as<int32_t>() + (size_t)n0 * H, minhash, (size_t)n * H * 4, kind, ctx->stream));
-    if ((size_t)ord_stride == S) CU(ctx, cudaMemcpyAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, ord, (size_t)n * S * 8, kind, ctx->stream));
-    else {
-        CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)n * S * 8, ctx->stream));
-        CU(ctx, cudaMemcpy2DAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, S * 8, ord, (size_t)ord_stride * 8, std::min(S, (size_t)ord_stride) * 8, n, kind, ctx->stream));
-    }
-    CU(ctx, cudaMemcpyAsync(s.ord_n.as<int32_t>() + n0, ord_n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    s.n += n;
-    s.indexed = false;
-    return store_sync_columns(ctx, n0);
+    auto device_part = [&]() -> int {
+        int rc = store_reserve(ctx, n);
+        if (rc) return rc;
+        const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride;
+        CU(ctx, cudaMemcpyAsync(s.minhash.as<int32_t>() + (size_t)n0 * H, minhash, (size_t)n * H * 4, kind, ctx->stream));
+        if ((size_t)ord_stride == S) CU(ctx, cudaMemcpyAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, ord, (size_t)n * S * 8, kind, ctx->stream));
+        else {
+            CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)n * S * 8, ctx->stream));
+            CU(ctx, cudaMemcpy2DAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, S * 8, ord, (size_t)ord_stride * 8, std::min(S, (size_t)ord_stride) * 8, n, kind, ctx->stream));
+        }
+        CU(ctx, cudaMemcpyAsync(s.ord_n.as<int32_t>() + n0, ord_n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        s.n += n;
+        s.indexed = false;
+        rc = store_sync_columns(ctx, n0);
+        if (rc) s.n = n0;
+        return rc;
+    };
+    const int rc = device_part();
+    if (rc) store_rollback_meta(s, meta0);
+    return rc;
 }
 
 int mhapb_store_add_sketches(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd, const int32_t *seq_len,
-                             const int32_t *seq_len_kmers, const int32_t *minhash, const int32_t *ord_hash_pos,
-                             const int32_t *ord_n, int32_t ord_stride, uint32_t n)
+                             const int32_t *seq_len_kmers, const int32_t *minhash, int32_t num_hashes, const int32_t *ord_hash_pos,
+                             const int32_t *ord_n, int32_t ord_stride, int32_t ordered_kmer_size, uint32_t n)
 {
     if (!ctx) return MHAPB_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->store.configured) return fail(ctx, MHAPB_ESTATE, "mhapb_store_reset must be called first");
+    if (n) { int rc = check_sketch_shape(ctx, num_hashes, ordered_kmer_size, false); if (rc) return rc; }
     return add_sketches_common(ctx, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hash_pos, ord_n, ord_stride, n, cudaMemcpyHostToDevice);
 }
 
@@ -1060,6 +1088,27 @@ int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, i
     return MHAPB_OK;
 }
 
+int mhapb_store_get_range(mhapb_ctx *ctx, int64_t first, int64_t count, int64_t *ids, uint8_t *is_fwd, int32_t *seq_len,
+                          int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Store &s = ctx->store;
+    if (first < 0 || count < 0 || first + count > s.n) return fail(ctx, MHAPB_EINVAL, "store range [%lld, %lld) out of range", (long long)first, (long long)(first + count));
+    if (!count) return MHAPB_OK;
+    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.ord_stride, c = (size_t)count;
+    if (ids) memcpy(ids, s.h_id.data() + first, c * 8);
+    if (is_fwd) memcpy(is_fwd, s.h_fwd.data() + first, c);
+    if (seq_len) memcpy(seq_len, s.h_len.data() + first, c * 4);
+    if (seq_len_kmers) memcpy(seq_len_kmers, s.h_lenk.data() + first, c * 4);
+    if (ord_n) memcpy(ord_n, s.h_ordn.data() + first, c * 4);
+    if (minhash) CU(ctx, cudaMemcpyAsync(minhash, s.minhash.as<int32_t>() + (size_t)first * H, c * H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ord_hash_pos) CU(ctx, cudaMemcpyAsync(ord_hash_pos, s.ord.as<int32_t>() + (size_t)first * S * 2, c * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return MHAPB_OK;
+}
+
 int mhapb_store_device_ptrs(mhapb_ctx *ctx, void **d_minhash, void **d_ord, void **d_ord_n, int64_t *n, int32_t *num_hashes, int32_t *ord_stride)
 {
     if (!ctx) return MHAPB_EINVAL;
@@ -1124,9 +1173,9 @@ static int search_query_sketches_locked(mhapb_ctx *ctx, const mhapb_search_param
 }
 
 int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, const int64_t *ids, const uint8_t *is_fwd,
-                                const int32_t *seq_len, const int32_t *seq_len_kmers, const int32_t *minhash,
-                                const int32_t *ord_hash_pos, const int32_t *ord_n, int32_t ord_stride, uint32_t n,
-                                mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
+                                const int32_t *seq_len, const int32_t *seq_len_kmers, const int32_t *minhash, int32_t num_hashes,
+                                const int32_t *ord_hash_pos, const int32_t *ord_n, int32_t ord_stride, int32_t ordered_kmer_size,
+                                uint32_t n, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
 {
     if (!ctx || !sp) return MHAPB_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1134,6 +1183,8 @@ int mhapb_search_query_sketches(mhapb_ctx *ctx, const mhapb_search_params *sp, c
     Store &s = ctx->store;
     if (!s.configured || s.n == 0) return fail(ctx, MHAPB_ESTATE, "search on an empty store");
     if (n && (!ids || !is_fwd || !seq_len || !seq_len_kmers || !minhash || !ord_hash_pos || !ord_n)) return fail(ctx, MHAPB_EINVAL, "null query column");
+    if (ord_stride < 1) return fail(ctx, MHAPB_EINVAL, "ord_stride %d", ord_stride);
+    if (n) { int rc = check_sketch_shape(ctx, num_hashes, ordered_kmer_size, true); if (rc) return rc; }
     const size_t H = (size_t)s.p.num_hashes;
     CU(ctx, ctx->q_minhash.ensure((size_t)n * H * 4 + 4));
     CU(ctx, ctx->q_ord.ensure((size_t)n * ord_stride * 8 + 8));

@@ -305,9 +305,7 @@ int main(int argc, char **argv)
         for (const std::string &pf : list_files(o.p)) {
             const double t0 = now_s();
             std::string name = pf.substr(pf.find_last_of('/') == std::string::npos ? 0 : pf.find_last_of('/') + 1);
-            if (ends_with(name, ".gz")) name = name.substr(0, name.size() - 3);
-            else if (ends_with(name, ".bz2")) name = name.substr(0, name.size() - 4);
-            size_t dot = name.find_last_of('.');
+            size_t dot = name.find_last_of('.');   // main/MhapMain.java:431-434: only the last extension goes (reads.fasta.gz -> reads.fasta.dat)
             if (dot != std::string::npos && dot > 0) name = name.substr(0, dot);
             std::string outp = o.q + "/" + name + ".dat";
             std::ofstream out(outp, std::ios::binary);
@@ -332,13 +330,17 @@ int main(int argc, char **argv)
     fprintf(stderr, "Processing files for storage in reverse index...\n");
     const double t_proc = now_s();
     int64_t n_sketches = 0;
+    int32_t store_ok = o.ordered_kmer;   // the ordered k-mer size the stored sketches carry
     Names store_names;   // empty for .dat stores: ids print as numbers
     if (ends_with(o.s, ".dat")) {
         DatSketches d = read_dat(o.s, 0);
         if (d.n && d.H != o.num_hashes) die("Number of MinHashes of the sequence does not match current settings.");   // MinHashSearch.java:105
         p.ordered_sketch_size = std::max(p.ordered_sketch_size, d.max_ord);
+        // a stored sketch scores with the k-mer size recorded in it (BottomOverlapSketch.kmerSize, :391-395,:613), whatever
+        // --ordered-kmer-size says; sketches made with another size then fail the check of :594-595 when compared
+        if (d.n) { store_ok = d.ok; p.ordered_kmer_size = d.ok; }
         ck(ctx, mhapb_store_reset(ctx, &p));
-        ck(ctx, mhapb_store_add_sketches(ctx, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.ord.data(), d.ordn.data(), d.max_ord, d.n));
+        ck(ctx, mhapb_store_add_sketches(ctx, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.H, d.ord.data(), d.ordn.data(), d.max_ord, d.ok, d.n));
         n_sketches = d.n;
     } else {
         ck(ctx, mhapb_store_reset(ctx, &p));
@@ -388,11 +390,14 @@ int main(int argc, char **argv)
             if (n_sketches == 0) { /* nothing stored: nothing can match */ }
             else if (ends_with(cf, ".dat")) {
                 DatSketches d = read_dat(cf, seq_number_processed);
-                ck(ctx, mhapb_search_query_sketches(ctx, &sp, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.ord.data(),
-                                                    d.ordn.data(), d.max_ord, d.n, &hits, &n, &st));
+                // the library repeats the reference's checks: "Number of hashes does not match..." (MinHashSearch.java:157-159),
+                // "Sketch k-mer size does not match between the two sequences." (BottomOverlapSketch.java:594-595)
+                ck(ctx, mhapb_search_query_sketches(ctx, &sp, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.H, d.ord.data(),
+                                                    d.ordn.data(), d.max_ord, d.ok, d.n, &hits, &n, &st));
                 processed = st.sequences_searched;
                 from_sub = seq_number_processed;
             } else {
+                if (store_ok != o.ordered_kmer) die("Sketch k-mer size does not match between the two sequences.");   // .dat store made with another --ordered-kmer-size
                 Names query_names;
                 for_each_fasta_batch(cf, seq_number_processed, o.num_threads, &query_names, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
                     mhapb_hit *bh = nullptr; uint64_t bn = 0; mhapb_stats bst{};

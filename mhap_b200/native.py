@@ -20,7 +20,7 @@ EXPORTS = [
     "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_xorshift_peaks", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
     "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads",
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
-    "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
+    "mhapb_store_get_range", "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
     "mhapb_search_query_sketches", "mhapb_search_sketches_device", "mhapb_format_match", "mhapb_minhash_equal_count",
     "mhapb_store_reserve", "mhapb_sketch_reserve", "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
 ]
@@ -108,17 +108,18 @@ def load():
     L.mhapb_dat_decode.argtypes = [vp, u64, i64, P(u32), P(i32), P(i32), P(i32), vp, vp, vp, vp, vp, vp, vp]
     L.mhapb_store_reset.argtypes = [vp, P(SketchParams)]
     L.mhapb_store_add_reads.argtypes = [vp, vp, vp, vp, u32, C.c_int, P(i64)]
-    L.mhapb_store_add_sketches.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, u32]
+    L.mhapb_store_add_sketches.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, u32]
     L.mhapb_store_add_sketches_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32]
     L.mhapb_store_size.argtypes = [vp]; L.mhapb_store_size.restype = i64
     L.mhapb_store_reserve.argtypes = [vp, i64]
     L.mhapb_sketch_reserve.argtypes = [vp, P(SketchParams), u64, u32, C.c_int]
     L.mhapb_store_get.argtypes = [vp, i64, P(i64), P(i32), P(i32), P(i32), vp, vp, P(i32)]
+    L.mhapb_store_get_range.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     L.mhapb_store_device_ptrs.argtypes = [vp, P(vp), P(vp), P(vp), P(i64), P(i32), P(i32)]
     L.mhapb_index_build.argtypes = [vp]
     L.mhapb_search_self.argtypes = [vp, P(SearchParams), P(vp), P(u64), P(Stats)]
     L.mhapb_search_query_reads.argtypes = [vp, P(SearchParams), vp, vp, vp, u32, P(vp), P(u64), P(Stats)]
-    L.mhapb_search_query_sketches.argtypes = [vp, P(SearchParams), vp, vp, vp, vp, vp, vp, vp, i32, u32, P(vp), P(u64), P(Stats)]
+    L.mhapb_search_query_sketches.argtypes = [vp, P(SearchParams), vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, u32, P(vp), P(u64), P(Stats)]
     L.mhapb_search_sketches_device.argtypes = [vp, P(SearchParams), C.c_int, vp, vp, vp, vp, vp, vp, vp, i32, u32, P(vp), P(u64), P(Stats)]
     L.mhapb_format_match.argtypes = [P(Hit), C.c_char_p, C.c_size_t]
     L.mhapb_minhash_equal_count.argtypes = [vp, i64, i64, P(i32)]
@@ -268,13 +269,14 @@ class Engine:
                                               int(both_strands), C.byref(added)))
         return added.value
 
-    def store_add_sketches(self, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hp, ord_n):
+    def store_add_sketches(self, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hp, ord_n, ordered_kmer_size=12):
         ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
         seq_len = np.ascontiguousarray(seq_len, dtype=np.int32); slk = np.ascontiguousarray(seq_len_kmers, dtype=np.int32)
         minhash = np.ascontiguousarray(minhash, dtype=np.int32); ord_hp = np.ascontiguousarray(ord_hp, dtype=np.int32)
         ord_n = np.ascontiguousarray(ord_n, dtype=np.int32)
         self._ck(self.L.mhapb_store_add_sketches(self.h, _ptr(ids), _ptr(is_fwd), _ptr(seq_len), _ptr(slk), _ptr(minhash),
-                                                 _ptr(ord_hp), _ptr(ord_n), ord_hp.shape[1], ids.size))
+                                                 minhash.shape[1] if minhash.ndim == 2 else 0, _ptr(ord_hp), _ptr(ord_n), ord_hp.shape[1],
+                                                 ordered_kmer_size, ids.size))
 
     def store_add_sketches_device(self, ids, is_fwd, seq_len, seq_len_kmers, d_minhash: int, d_ord: int, ord_n):
         ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
@@ -294,6 +296,16 @@ class Engine:
         mh = np.zeros(H, dtype=np.int32); od = np.zeros((S, 2), dtype=np.int32)
         self._ck(self.L.mhapb_store_get(self.h, idx, C.byref(id_), C.byref(fwd), C.byref(sl), C.byref(slk), _ptr(mh), _ptr(od), C.byref(on)))
         return dict(id=id_.value, is_fwd=bool(fwd.value), seq_len=sl.value, seq_len_kmers=slk.value, minhash=mh, ord=od[:on.value].copy())
+
+    def store_get_range(self, first: int, count: int, want_ord=True) -> dict:
+        """Stored sketches [first, first+count) as flat arrays (mhapb_store_get_range)."""
+        _, _, _, _, H, S = self.store_device_ptrs()
+        out = dict(ids=np.zeros(count, np.int64), is_fwd=np.zeros(count, np.uint8), seq_len=np.zeros(count, np.int32),
+                   seq_len_kmers=np.zeros(count, np.int32), minhash=np.zeros((count, H), np.int32),
+                   ord=np.zeros((count, S, 2), np.int32) if want_ord else None, ord_n=np.zeros(count, np.int32))
+        self._ck(self.L.mhapb_store_get_range(self.h, first, count, _ptr(out["ids"]), _ptr(out["is_fwd"]), _ptr(out["seq_len"]),
+                                              _ptr(out["seq_len_kmers"]), _ptr(out["minhash"]), _ptr(out["ord"]), _ptr(out["ord_n"])))
+        return out
 
     def store_device_ptrs(self):
         a = C.c_void_p(); b = C.c_void_p(); c = C.c_void_p(); n = C.c_int64(); H = C.c_int32(); S = C.c_int32()
@@ -328,15 +340,15 @@ class Engine:
                                                  C.byref(out), C.byref(n), C.byref(st)))
         return self._collect(out, n, st)
 
-    def search_query_sketches(self, sp: SearchParams, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hp, ord_n):
+    def search_query_sketches(self, sp: SearchParams, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hp, ord_n, ordered_kmer_size=12):
         ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
         seq_len = np.ascontiguousarray(seq_len, dtype=np.int32); slk = np.ascontiguousarray(seq_len_kmers, dtype=np.int32)
         minhash = np.ascontiguousarray(minhash, dtype=np.int32); ord_hp = np.ascontiguousarray(ord_hp, dtype=np.int32)
         ord_n = np.ascontiguousarray(ord_n, dtype=np.int32)
         out = C.c_void_p(); n = C.c_uint64(); st = Stats()
         self._ck(self.L.mhapb_search_query_sketches(self.h, C.byref(sp), _ptr(ids), _ptr(is_fwd), _ptr(seq_len), _ptr(slk),
-                                                    _ptr(minhash), _ptr(ord_hp), _ptr(ord_n), ord_hp.shape[1], ids.size,
-                                                    C.byref(out), C.byref(n), C.byref(st)))
+                                                    _ptr(minhash), minhash.shape[1] if minhash.ndim == 2 else 0, _ptr(ord_hp), _ptr(ord_n),
+                                                    ord_hp.shape[1], ordered_kmer_size, ids.size, C.byref(out), C.byref(n), C.byref(st)))
         return self._collect(out, n, st)
 
     def search_sketches_device(self, sp: SearchParams, to_self: bool, ids, is_fwd, seq_len, seq_len_kmers, d_minhash: int, d_ord: int,

@@ -92,3 +92,39 @@ def assert_same_hits(got, exp, stats_got, stats_exp):
     lg = sorted(native.format_match(h) for h in got if h["accepted"])
     le = sorted(orc.format_match(h) for h in exp if h["accepted"])
     assert lg == le
+
+
+_KEY_FIELDS = ("from_id", "to_id", "from_fwd", "to_fwd", "hit_count", "a1", "a2", "b1", "b2", "valid_count", "intersect", "kmin",
+               "from_len", "to_len", "accepted")
+
+
+def sorted_hits(h):
+    """Hits in the canonical order of their integer key (vectorised: full-size hit sets)."""
+    order = np.lexsort(tuple(h[f] for f in reversed(_KEY_FIELDS)))
+    return h[order]
+
+
+def assert_same_hits_bulk(got, exp, stats_got, stats_exp, lines=2000):
+    """assert_same_hits for hit sets of 10^4..10^6 rows: every integer field bit-exact on the sorted sets, scores within
+    1e-15, the five counters equal, and the printed MatchResult lines of an evenly spaced sample."""
+    assert stats_got == stats_exp, (stats_got, stats_exp)
+    assert len(got) == len(exp), (len(got), len(exp))
+    g, e = sorted_hits(got), sorted_hits(exp)
+    for f in _KEY_FIELDS:
+        bad = np.nonzero(g[f] != e[f])[0]
+        assert bad.size == 0, (f, bad[:5], g[bad[:3]], e[bad[:3]])
+    assert np.all(np.abs(g["score"] - e["score"]) <= 1e-15)
+    step = max(1, len(g) // max(1, lines))
+    for a, b in zip(g[::step], e[::step]):
+        if a["accepted"]:
+            assert native.format_match(a) == orc.format_match(b)
+
+
+def hits_digest(h) -> str:
+    """Order-independent digest of a hit set: sha256 over the sorted integer keys (bench.py prints the same)."""
+    import hashlib
+    s = sorted_hits(h)
+    m = hashlib.sha256()
+    for f in _KEY_FIELDS:
+        m.update(np.ascontiguousarray(s[f]).astype("<i8").tobytes())
+    return m.hexdigest()[:16]

@@ -168,7 +168,7 @@ def test_streamed_batches_and_gzip_input_equal_the_single_batch_run(tmp_path):
     d1.mkdir(); d2.mkdir()
     _run(["-p", str(fa), "-q", str(d1)] + args)
     _run(["-p", str(gz), "-q", str(d2)] + args, env={"MHAPB_FASTA_CHUNK_KB": "64"})
-    assert (d1 / "store.dat").read_bytes() == (d2 / "store_gz.dat").read_bytes()
+    assert (d1 / "store.dat").read_bytes() == (d2 / "store_gz.fasta.dat").read_bytes()   # only the last extension is stripped (MhapMain.java:431-434)
 
 
 def test_store_full_id_prints_fasta_names(tmp_path):

@@ -10,7 +10,9 @@ import numpy as np
 import pytest
 
 from mhap_b200 import native, synth
-from tests.gpu_common import assert_same_hits, engine
+import os
+
+from tests.gpu_common import assert_same_hits, assert_same_hits_bulk, engine
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -65,6 +67,47 @@ def test_config2_full_size_properties_and_sampled_parity():
         o = orc.overlap_info(a["ord"], a["seq_len_kmers"], b["ord"], b["seq_len_kmers"], 12, 0.2)
         assert (o.a1, o.a2, o.b1, o.b2, o.valid_count, o.intersect, o.kmin) == tuple(int(h[k]) for k in ("a1", "a2", "b1", "b2", "valid_count", "intersect", "kmin"))
         assert abs(o.score - h["score"]) < 1e-15
+
+
+def _full_parity(n, L, H, S, seed, keep_all):
+    """Whole BASELINE config against the oracle: every stored sketch (min-hashes + ordered sketch), the complete hit set
+    and the five counters of MhapMain.outputFinalStat (main/MhapMain.java:572-590).  The oracle runs one thread per host
+    core (its pool mirrors Executors.newFixedThreadPool, AbstractMatchSearch.java:70,124)."""
+    threads = os.cpu_count() or 1
+    bases, offs = synth.dataset(n, L, seed=seed)
+    p = native.SketchParams(16, H, 12, S, 0, 116)
+    e = engine()
+    e.store_reset(p)
+    assert e.store_add_reads(bases, offs) == 2 * n
+    hits, stats = e.search_self(native.SearchParams(3, 0, 0.2, 0.78, int(keep_all), 0, 0, -1))
+    st = orc.Store(num_hashes=H, ordered_size=S)
+    assert st.add_reads(bases, offs, threads=threads) == 2 * n
+    # every sketch, in blocks of 4096 rows
+    for first in range(0, 2 * n, 4096):
+        cnt = min(4096, 2 * n - first)
+        g = e.store_get_range(first, cnt)
+        for j in range(cnt):
+            o = st.get(first + j)
+            assert o["id"] == g["ids"][j] and o["is_fwd"] == bool(g["is_fwd"][j]) and o["seq_len"] == g["seq_len"][j]
+            assert (o["minhash"] == g["minhash"][j]).all(), first + j
+            assert o["ord"].shape[0] == g["ord_n"][j] and (o["ord"] == g["ord"][j, :g["ord_n"][j]]).all(), first + j
+    res = st.search_self(threads=threads, keep_all=keep_all)
+    st.close()
+    assert_same_hits_bulk(hits, res.hits, stats, res.stats)
+    return stats
+
+
+def test_config2_full_parity():
+    # BASELINE configs[1] at its own size: 100k reads x 10 kbp, H=512, S=1536 -- the numbers bench.py reports
+    stats = _full_parity(100_000, 10_000, 512, 1536, seed=2, keep_all=False)
+    assert stats["sequences_searched"] == 100_000 and stats["matches_processed"] > 10_000
+
+
+def test_config3_full_parity():
+    # BASELINE configs[2] at its own size: 50k reads x 8 kbp, --ordered-sketch-size 1000; keep_all: also the candidates that
+    # were fully compared and rejected by the threshold
+    stats = _full_parity(50_000, 8_000, 512, 1000, seed=3, keep_all=True)
+    assert stats["sequences_searched"] == 50_000 and stats["fully_compared"] > stats["matches_processed"] > 0
 
 
 def test_config3_shape_ordered_sketch_1000():
