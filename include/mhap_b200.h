@@ -10,8 +10,9 @@
  * Conventions: extern "C"; plain pointers and sizes; every call returns 0 on success and a
  * negative MHAPB_E* code on failure (text via mhapb_last_error); no exception crosses the ABI;
  * the caller owns every buffer it passes in; buffers the library returns are released with
- * mhapb_free.  One context drives one GPU (one process per GPU; multi-GPU jobs create one
- * context per rank and exchange sketch blocks with NCCL above this ABI, see mhapb_store_*_device).
+ * mhapb_free.  One context drives one GPU.  Multi-GPU jobs use one context per GPU joined by an NCCL
+ * communicator that the library owns (mhapb_comm_*): either one process per GPU (mhapb_comm_init_rank, the
+ * collective calls mhapb_dist_*) or one process driving all GPUs (mhapb_multi_*, what a single JVM binds).
  * Calls on one context are serialised by an internal mutex, so the reference's pool threads
  * (AbstractMatchSearch.java:70,124,206) may call concurrently.
  *
@@ -34,6 +35,7 @@ extern "C" {
 #define MHAPB_ENOMEM   -4
 #define MHAPB_EDUPID   -5   /* "Sequence ID already exists in the hash table." impl/MinHashSearch.java:112-117 */
 #define MHAPB_ESTATE   -6   /* call out of order (e.g. search before any sequence was added) */
+#define MHAPB_ECOMM    -7   /* NCCL not loadable / a collective failed */
 
 typedef struct mhapb_ctx mhapb_ctx;
 
@@ -97,6 +99,8 @@ typedef struct {
     float sketch_total_ms;                            /* first K1 launch -> last K1 kernel end, all chunks */
     float search_total_ms;                            /* K2b start -> K2c end (device work only) */
     int64_t kmers_hashed;                             /* k-mers (MinHash k) of the last sketch call */
+    float gather_ms;                                  /* multi-GPU: first to last collective of the last mhapb_dist_* call (its own stream) */
+    float pad_;
 } mhapb_timing;
 
 /* ---- housekeeping ------------------------------------------------------------------------ */
@@ -218,6 +222,10 @@ int mhapb_store_reset(mhapb_ctx *ctx, const mhapb_sketch_params *p);
 int mhapb_store_add_reads(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
                           const int64_t *ids, uint32_t n_reads, int both_strands,
                           int64_t *n_added);
+/* Same with the reads' characters already resident in HBM (d_bases: device pointer; h_offsets stays on the host): the
+ * device-resident figure of bench.py, and callers that stage reads on the GPU themselves. */
+int mhapb_store_add_reads_device(mhapb_ctx *ctx, const void *d_bases, const uint64_t *h_offsets, const int64_t *ids,
+                                 uint32_t n_reads, int both_strands, int64_t *n_added);
 /* Append pre-computed sketches from host arrays (the .dat path, addSequence per record).  num_hashes and
  * ordered_kmer_size describe the arrays (a .dat file does not record the run's parameters, only each sketch's
  * own): a mismatch with the store's parameters fails like the reference does -- "Number of MinHashes of the
@@ -291,6 +299,64 @@ int mhapb_format_match(const mhapb_hit *h, char *buf, size_t buflen);
 /* a10: MinHashSketch.jaccard (sketch/MinHashSketch.java:237-263) between stored sketches i and j:
  * positional equality count; *out_equal / H is the reference's double. */
 int mhapb_minhash_equal_count(mhapb_ctx *ctx, int64_t i, int64_t j, int32_t *out_equal);
+
+/* ---- multi-GPU ---------------------------------------------------------------------------
+ * The reference is one JVM with a thread pool (impl/AbstractMatchSearch.java:67-117,121-199); its users scale out by
+ * partitioning the reads by hand (docs/source/quickstart.rst:23).  Here reads are sharded over the GPUs of one box:
+ * every context sketches, stores and indexes ITS shard (mhapb_store_add_reads), the forward sketches of all shards --
+ * the queries of findMatches -- are exchanged with ONE NCCL all-gather over NVLink (columns + min-hashes first, ordered
+ * sketches behind them, hidden behind K2a and K2b), and every rank answers for the targets it stores.  A pair
+ * (query, target) is therefore found exactly once, on the target's rank; the counters of MhapMain.outputFinalStat are
+ * additive over ranks and are all-reduced, so every rank returns the job-wide mhapb_stats.
+ * NCCL is loaded at run time (libnccl.so.2; override with MHAPB_NCCL_LIB): MHAPB_ECOMM if it is missing. */
+#define MHAPB_COMM_ID_BYTES 128
+/* one process per GPU: rank 0 makes the id (ncclGetUniqueId), the launcher hands it to every rank, each rank joins
+ * with its own context.  Collective over the ranks. */
+int mhapb_comm_unique_id(uint8_t *id /* [MHAPB_COMM_ID_BYTES] */);
+int mhapb_comm_init_rank(mhapb_ctx *ctx, const uint8_t *id, int rank, int nranks);
+/* one process, n contexts on n different GPUs: rank i = ctxs[i] */
+int mhapb_comm_init_all(mhapb_ctx **ctxs, int n);
+int mhapb_comm_destroy(mhapb_ctx *ctx);      /* mhapb_destroy does it too */
+int mhapb_comm_info(mhapb_ctx *ctx, int *rank, int *nranks, int *nccl_version);
+/* COLLECTIVE (every rank of the communicator calls it, from its own thread / process).  Replaces findMatches() to self
+ * (impl/AbstractMatchSearch.java:121-199 -> MinHashSearch.findMatches(sketch,true), impl/MinHashSearch.java:150-251)
+ * for a store sharded over the ranks: *out = the overlaps whose TARGET this rank stores, *stats = job-wide counters. */
+int mhapb_dist_search_self(mhapb_ctx *ctx, const mhapb_search_params *sp, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
+/* COLLECTIVE.  findMatches(SequenceSketchStreamer) (AbstractMatchSearch.java:203-285) with the query file sharded too:
+ * this rank passes ITS shard of the query reads (sketched forward only, :225); all queries meet every store shard. */
+int mhapb_dist_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, const char *bases, const uint64_t *offsets,
+                                  const int64_t *ids, uint32_t n_reads, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
+
+/* Same with this rank's query reads already resident in HBM (bench.py's device-resident figure). */
+int mhapb_dist_search_query_reads_device(mhapb_ctx *ctx, const mhapb_search_params *sp, const void *d_bases, const uint64_t *h_offsets,
+                                         const int64_t *ids, uint32_t n_reads, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
+
+/* One process driving several GPUs -- what MhapMain's single construction site (main/MhapMain.java:554-558) binds:
+ * the same calls as the single-GPU store / search entry points, batches split over the devices by the library (contiguous
+ * parts balanced by bases), one host thread per device inside each call, results merged.  n_devices == 1 forwards to the
+ * single-GPU calls (no NCCL needed). */
+typedef struct mhapb_multi mhapb_multi;
+int  mhapb_multi_create(const int *device_ids, int n_devices, mhapb_multi **out);
+void mhapb_multi_destroy(mhapb_multi *m);
+const char *mhapb_multi_last_error(const mhapb_multi *m);
+int  mhapb_multi_n_devices(const mhapb_multi *m);
+mhapb_ctx *mhapb_multi_ctx(mhapb_multi *m, int i);      /* e.g. to install the -f filter on every device, or to read timings */
+int  mhapb_multi_store_reset(mhapb_multi *m, const mhapb_sketch_params *p);
+int  mhapb_multi_store_reserve(mhapb_multi *m, int64_t n_sketches);
+int  mhapb_multi_store_add_reads(mhapb_multi *m, const char *bases, const uint64_t *offsets, const int64_t *ids, uint32_t n_reads,
+                                 int both_strands, int64_t *n_added);
+int  mhapb_multi_store_add_sketches(mhapb_multi *m, const int64_t *ids, const uint8_t *is_fwd, const int32_t *seq_len,
+                                    const int32_t *seq_len_kmers, const int32_t *minhash, int32_t num_hashes,
+                                    const int32_t *ord_hash_pos, const int32_t *ord_n, int32_t ord_stride,
+                                    int32_t ordered_kmer_size, uint32_t n);
+int64_t mhapb_multi_store_size(mhapb_multi *m);
+int  mhapb_multi_search_self(mhapb_multi *m, const mhapb_search_params *sp, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
+int  mhapb_multi_search_query_reads(mhapb_multi *m, const mhapb_search_params *sp, const char *bases, const uint64_t *offsets,
+                                    const int64_t *ids, uint32_t n_reads, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
+int  mhapb_multi_search_query_sketches(mhapb_multi *m, const mhapb_search_params *sp, const int64_t *ids, const uint8_t *is_fwd,
+                                       const int32_t *seq_len, const int32_t *seq_len_kmers, const int32_t *minhash,
+                                       int32_t num_hashes, const int32_t *ord_hash_pos, const int32_t *ord_n, int32_t ord_stride,
+                                       int32_t ordered_kmer_size, uint32_t n, mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,7 @@
 // api.cu -- the C ABI of include/mhap_b200.h: context, device memory, batching, and the host-side
 // halves of the reference interfaces (status per read, id filters' inputs, score, MatchResult).
 // No CPU fallback: every compute entry point launches the kernels in sketch.cu / search.cu.
-#include "../../include/mhap_b200.h"
-#include "engine.h"
+#include "ctx.h"
 #include "hash.cuh"
 
 #include <algorithm>
@@ -20,78 +19,10 @@
 
 using namespace mhapb;
 
-namespace {
+namespace mhapb { thread_local std::string g_create_error; }
 
-thread_local std::string g_create_error;
 
-struct DevBuf {
-    void *p = nullptr; size_t cap = 0;
-    cudaError_t ensure(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    // grow keeping the first keep_bytes
-    cudaError_t grow(size_t bytes, size_t keep_bytes, cudaStream_t st)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        size_t want = std::max(bytes, cap * 2);
-        void *np = nullptr;
-        cudaError_t e = cudaMalloc(&np, want);
-        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&np, want); }
-        if (e != cudaSuccess) return e;
-        if (p && keep_bytes) { e = cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; e = cudaStreamSynchronize(st); }
-        if (p) cudaFree(p);
-        p = np; cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return static_cast<T *>(p); }
-};
-
-struct Store {
-    mhapb_sketch_params p{};
-    bool configured = false;
-    int64_t n = 0;
-    int ord_stride = 0;
-    DevBuf minhash, ord, ord_n, lenk, len, id;
-    std::vector<int64_t> h_id; std::vector<uint8_t> h_fwd; std::vector<int32_t> h_len, h_lenk, h_ordn;
-    std::unordered_set<uint64_t> seen;
-    // index
-    bool indexed = false;
-    DevBuf slots, postings;
-    int log2capw = 0;
-};
-
-} // namespace
-
-struct mhapb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;   // K1c runs here, concurrently with K1b of the same chunk
-    std::mutex mu;
-    std::string err;
-    mhapb_timing timing{};
-    // sketch scratch
-    DevBuf bases, desc, keys, wts, nlight, nheavy, dupcnt, gtable, ohash, counters;
-    DevBuf out_minhash, out_ord, out_ordn;
-    // search scratch
-    DevBuf qlist, cand, ovl, cand2, ovl2, ovf_list, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
-    Store store;
-    cudaEvent_t ev[8]{};
-    // the -f k-mer filter (FrequencyCounts); view.mode == 0 when none is set
-    DevBuf f_keys, f_idf, f_used, f_bloom;
-    KmerFilterView filter{};
-    mhapb_filter_params filter_params{};
-    bool filter_set = false;
-};
-
-namespace {
+namespace mhapb {
 
 int fail(mhapb_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -101,7 +32,6 @@ int fail(mhapb_ctx *ctx, int code, const char *fmt, ...)
     return code;
 }
 
-#define CU(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(ctx, e__ == cudaErrorMemoryAllocation ? MHAPB_ENOMEM : MHAPB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 
 int check_sketch_params(mhapb_ctx *ctx, const mhapb_sketch_params *p)
 {
@@ -115,7 +45,7 @@ int check_sketch_params(mhapb_ctx *ctx, const mhapb_sketch_params *p)
 
 // Per-read status from lengths alone (SequenceSketchStreamer.java:129-133, MinHashSketch.java:55-56,
 // BottomOverlapSketch.java:530-531).
-inline int read_status(const mhapb_sketch_params &p, uint64_t len)
+int read_status(const mhapb_sketch_params &p, uint64_t len)
 {
     if ((int64_t)len < (int64_t)p.min_olap_length) return 2;
     if ((int64_t)len - p.kmer_size + 1 < 1) return 1;
@@ -152,7 +82,7 @@ int filter_unweighted(const KmerFilterView &v, int unweighted) { return v.mode =
 // slot_valid (optional, size n_reads*per): set to 0 for strands whose every k-mer was filtered out.
 int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_bases, const uint64_t *h_offsets,
                 uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
-                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid = nullptr)
+                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid)
 {
     const KmerFilterView flt = filter_view(ctx);
     if (ctx->filter_set && (ctx->filter_params.repeat_weight < 0.0) != (p.unweighted != 0))
@@ -307,7 +237,7 @@ int store_configure(mhapb_ctx *ctx, const mhapb_sketch_params *p)
     if (rc) return rc;
     Store &s = ctx->store;
     s.p = *p; s.configured = true; s.n = 0; s.ord_stride = p->ordered_sketch_size; s.indexed = false;
-    s.h_id.clear(); s.h_fwd.clear(); s.h_len.clear(); s.h_lenk.clear(); s.h_ordn.clear(); s.seen.clear();
+    s.h_id.clear(); s.h_fwd.clear(); s.h_len.clear(); s.h_lenk.clear(); s.h_ordn.clear(); s.seen.clear(); s.fwd_list_valid = false;
     return MHAPB_OK;
 }
 
@@ -370,22 +300,20 @@ int index_build(mhapb_ctx *ctx)
     CU(ctx, ctx->block_sums.ensure(((nslots + 4095) / 4096 + 1) * 4));
     IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), lg, H, s.n};
     int launches = 0;
-    cudaEventRecord(ctx->ev[0], ctx->stream);
+    cudaEventRecord(ctx->ev[8], ctx->stream);
     CU(ctx, launch_index_build(ctx->stream, s.minhash.as<int32_t>(), s.n, H, iv, ctx->tmp_start.as<uint32_t>(), ctx->block_sums.as<uint32_t>(), &launches));
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&ctx->timing.index_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventRecord(ctx->ev[9], ctx->stream);
+    ctx->index_timing_pending = true;     // no synchronisation here: the probe is enqueued right behind the build
     ctx->timing.kernel_launches += launches;
     s.indexed = true;
     return MHAPB_OK;
 }
 
-struct QuerySet {
-    const int32_t *d_minhash, *d_ord, *d_ordn, *d_lenk, *d_len; const int64_t *d_id; int ord_stride;
-    const int64_t *h_id; const uint8_t *h_fwd; const int32_t *h_len;
-    std::vector<uint32_t> list;   // indices into the query arrays
-};
-
+// K2b + K2c + result compaction as ONE enqueue: the candidate count, the warp kernel's overflow count and the number
+// of surviving pairs stay on the device (every consumer reads its count from the producer's cursor), so the host
+// synchronises twice per search -- once for the counters, once for the surviving pairs -- instead of after every kernel.
+// Capacities are guesses that the counters validate afterwards; an overrun (rare: repeat-rich data) repeats the
+// search with exact sizes.
 int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q, int to_self,
                 mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats)
 {
@@ -394,113 +322,111 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
     if (rc) return rc;
     const int H = s.p.num_hashes;
     IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.log2capw, H, s.n};
-    const int64_t nq = (int64_t)q.list.size();
+    const int64_t nq = q.list_all ? q.n_all : (q.d_list ? q.n_list : (int64_t)q.list.size());
     mhapb_stats st{};
     st.sequences_searched = nq;
     mhapb_hit *hit_arr = nullptr; size_t n_hits = 0;   // malloc'd result, filled by the scoring threads
     int launches = 0;
     ctx->timing.probe_ms = ctx->timing.filter_ms = 0;
     if (nq > 0) {
-        CU(ctx, ctx->qlist.ensure((size_t)nq * 4));
-        CU(ctx, cudaMemcpyAsync(ctx->qlist.p, q.list.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, ctx->scounters.ensure(64));
-        uint64_t cand_cap = std::max<uint64_t>(1 << 16, (uint64_t)nq * 16);
-        unsigned long long cnt[3] = {0, 0, 0};
-        for (int attempt = 0; attempt < 2; attempt++) {
+        const uint32_t *d_qlist = q.d_list;
+        if (!q.list_all && !d_qlist) {
+            CU(ctx, ctx->qlist.ensure((size_t)nq * 4));
+            CU(ctx, cudaMemcpyAsync(ctx->qlist.p, q.list.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+            d_qlist = ctx->qlist.as<uint32_t>();
+        }
+        CU(ctx, ctx->scounters.ensure(128));
+        CU(ctx, ctx->ovf_q.ensure((size_t)nq * 4));
+        // counters (u64): [0] candidates [1] elements processed [2] sequences hit [3] probe overflow queries
+        //                 [4] K2c overflow pairs [5] surviving pairs
+        unsigned long long cnt[8] = {0};
+        uint64_t cand_cap = std::max<uint64_t>(std::max<uint64_t>(1 << 16, (uint64_t)nq * 16), ctx->cand_cap_hint);
+        uint32_t ovf_threads = std::max<uint32_t>(4096u, ctx->ovf_threads_hint);
+        const int ok = s.p.ordered_kmer_size;
+        // Only pairs that can still reach the threshold travel to the host.  score >= accept  <=>  jaccard >= T/(2-T) with
+        // T = accept^ok (jaccardToIdentity is increasing); the device test uses that bound lowered by 1e-9 relative, the
+        // exact double-precision decision (MinHashSearch.java:229) is taken below on the survivors.
+        double jmin = 0.0;
+        if (sp->accept_score > 0.0) {
+            const double T = std::pow(sp->accept_score, (double)ok);
+            jmin = T < 2.0 ? (T / (2.0 - T)) * (1.0 - 1e-9) - 1e-12 : 2.0;
+            if (jmin < 0.0) jmin = 0.0;
+        }
+        const int keep_all = sp->keep_all || sp->accept_score <= 0.0;
+        for (int attempt = 0; attempt < 3; attempt++) {
             CU(ctx, ctx->cand.ensure(cand_cap * sizeof(Candidate)));
-            CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 64, ctx->stream));
+            CU(ctx, ctx->ovl.ensure(cand_cap * sizeof(OverlapOut)));
+            CU(ctx, ctx->ovf_list.ensure(cand_cap * 4 + 16));
+            CU(ctx, ctx->cand2.ensure(cand_cap * sizeof(Candidate)));
+            CU(ctx, ctx->ovl2.ensure(cand_cap * sizeof(OverlapOut)));
+            const uint32_t entries = 2u * (uint32_t)std::max(q.ord_stride, s.ord_stride) + 2u;
+            CU(ctx, ctx->fscratch.ensure((size_t)3 * entries * ovf_threads * 4));
+            CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 128, ctx->stream));
+            unsigned long long *dc = ctx->scounters.as<unsigned long long>();
             ProbeArgs a{};
-            a.q_minhash = q.d_minhash; a.q_id = q.d_id; a.q_len = q.d_len; a.q_list = ctx->qlist.as<uint32_t>(); a.nq_list = nq;
+            a.q_minhash = q.d_minhash; a.q_id = q.d_id; a.q_len = q.d_len; a.q_list = d_qlist; a.nq_list = nq;
             a.t_id = s.id.as<int64_t>(); a.t_len = s.len.as<int32_t>();
             a.to_self = to_self; a.num_min_matches = sp->num_min_matches; a.min_store_length = sp->min_store_length;
-            a.cand = ctx->cand.as<Candidate>(); a.cand_cap = cand_cap; a.counters = ctx->scounters.as<unsigned long long>();
+            a.cand = ctx->cand.as<Candidate>(); a.cand_cap = cand_cap; a.counters = dc; a.ovf_q = ctx->ovf_q.as<uint32_t>();
+            if (q.minhash_ready) CU(ctx, cudaStreamWaitEvent(ctx->stream, q.minhash_ready, 0));
             cudaEventRecord(ctx->ev[0], ctx->stream);
             CU(ctx, launch_probe(ctx->stream, iv, a, &launches));
             cudaEventRecord(ctx->ev[1], ctx->stream);
-            CU(ctx, cudaMemcpyAsync(cnt, ctx->scounters.p, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
-            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.probe_ms += ms;
-            if (cnt[0] <= cand_cap) break;
-            cand_cap = cnt[0];   // rare: more candidates than guessed; rerun with the exact size
-        }
-        st.elements_processed = (int64_t)cnt[1];
-        st.sequences_hit = (int64_t)cnt[2];
-        const uint64_t nc = cnt[0];
-        st.fully_compared = (int64_t)nc;
-        if (nc > 0) {
-            CU(ctx, ctx->ovl.ensure((size_t)nc * sizeof(OverlapOut)));
-            CU(ctx, ctx->ovf_list.ensure((size_t)nc * 4 + 16));
-            CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 64, ctx->stream));
+            if (q.ord_ready) CU(ctx, cudaStreamWaitEvent(ctx->stream, q.ord_ready, 0));
             FilterArgs f{};
-            f.cand = ctx->cand.as<Candidate>(); f.n_cand = nc;
+            f.cand = ctx->cand.as<Candidate>(); f.n_cand = 0; f.n_cand_dev = dc + 0; f.cand_cap = cand_cap;
             f.q_ord = q.d_ord; f.q_ord_n = q.d_ordn; f.q_lenk = q.d_lenk; f.q_stride = q.ord_stride;
             f.t_ord = s.ord.as<int32_t>(); f.t_ord_n = s.ord_n.as<int32_t>(); f.t_lenk = s.lenk.as<int32_t>(); f.t_stride = s.ord_stride;
             f.max_shift = sp->max_shift;
             f.out = ctx->ovl.as<OverlapOut>();
-            f.ovf_list = ctx->ovf_list.as<uint32_t>(); f.ovf_count = ctx->scounters.as<unsigned long long>();
+            f.ovf_list = ctx->ovf_list.as<uint32_t>(); f.ovf_count = dc + 4;
             cudaEventRecord(ctx->ev[2], ctx->stream);
-            // warp-per-candidate kernel first; what it cannot hold in shared memory (more than 1024 match records,
-            // or sketches too large to stage) goes to the thread-per-candidate kernel
-            unsigned long long n_ovf = 0;
-            cudaError_t fe = launch_filter_warp(ctx->stream, f, &launches);
-            if (fe == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); n_ovf = nc; f.sel = nullptr; }
-            else {
-                CU(ctx, fe);
-                CU(ctx, cudaMemcpyAsync(&n_ovf, ctx->scounters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                CU(ctx, cudaStreamSynchronize(ctx->stream));
-                f.sel = ctx->ovf_list.as<uint32_t>();
-            }
-            if (n_ovf > 0) {
-                const uint32_t entries = 2u * (uint32_t)std::max(q.ord_stride, s.ord_stride) + 2u;
-                size_t free_b = 0, total_b = 0;
-                cudaMemGetInfo(&free_b, &total_b);
-                uint64_t budget = std::min<uint64_t>(8ull << 30, (uint64_t)(free_b + ctx->fscratch.cap) / 2);
-                budget = std::max<uint64_t>(budget, 256ull << 20);
-                uint64_t max_threads = std::max<uint64_t>(128, budget / (12ull * entries));
-                max_threads = std::min<uint64_t>(max_threads, 148ull * 1024);
-                uint32_t nth = (uint32_t)std::min<uint64_t>(n_ovf, max_threads);
-                nth = (nth + 127u) & ~127u;
-                CU(ctx, ctx->fscratch.ensure((size_t)3 * entries * nth * 4));
-                f.n_sel = n_ovf;
-                f.scratch = ctx->fscratch.as<int32_t>(); f.scratch_entries = entries; f.n_threads = nth;
-                CU(ctx, launch_filter(ctx->stream, f, &launches));
-            }
+            // warp-per-candidate kernel; pairs with more match records than its shared buffer holds (near-identical reads)
+            // are listed for the thread-per-candidate kernel, which reads the list length on the device
+            CU(ctx, launch_filter_warp(ctx->stream, f, &launches));
+            f.sel = ctx->ovf_list.as<uint32_t>(); f.n_sel_dev = dc + 4; f.n_sel = 0;
+            f.scratch = ctx->fscratch.as<int32_t>(); f.scratch_entries = entries; f.n_threads = ovf_threads;
+            CU(ctx, launch_filter(ctx->stream, f, &launches));
             cudaEventRecord(ctx->ev[3], ctx->stream);
-            // Only pairs that can still reach the threshold travel to the host.  score >= accept  <=>  jaccard >= T/(2-T) with
-            // T = accept^ok (jaccardToIdentity is increasing); the device test uses that bound lowered by 1e-9 relative, the
-            // exact double-precision decision (MinHashSearch.java:229) is taken below on the survivors.
-            const int ok = s.p.ordered_kmer_size;
-            double jmin = 0.0;
-            if (sp->accept_score > 0.0) {
-                const double T = std::pow(sp->accept_score, (double)ok);
-                jmin = T < 2.0 ? (T / (2.0 - T)) * (1.0 - 1e-9) - 1e-12 : 2.0;
-                if (jmin < 0.0) jmin = 0.0;
-            }
-            const int keep_all = sp->keep_all || sp->accept_score <= 0.0;
-            CU(ctx, ctx->cand2.ensure(nc * sizeof(Candidate)));
-            CU(ctx, ctx->ovl2.ensure(nc * sizeof(OverlapOut)));
-            CU(ctx, cudaMemsetAsync(ctx->scounters.p, 0, 64, ctx->stream));
-            CU(ctx, launch_compact_hits(ctx->stream, ctx->cand.as<Candidate>(), ctx->ovl.as<OverlapOut>(), nc, jmin, keep_all,
-                                        ctx->cand2.as<Candidate>(), ctx->ovl2.as<OverlapOut>(), ctx->scounters.as<unsigned long long>(), &launches));
-            unsigned long long nkeep = 0;
-            CU(ctx, cudaMemcpyAsync(&nkeep, ctx->scounters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaEventElapsedTime(&ctx->timing.filter_ms, ctx->ev[2], ctx->ev[3]);
-            std::vector<Candidate> hc(nkeep);
-            std::vector<OverlapOut> ho(nkeep);
-            if (nkeep) {
-                CU(ctx, cudaMemcpyAsync(hc.data(), ctx->cand2.p, nkeep * sizeof(Candidate), cudaMemcpyDeviceToHost, ctx->stream));
-                CU(ctx, cudaMemcpyAsync(ho.data(), ctx->ovl2.p, nkeep * sizeof(OverlapOut), cudaMemcpyDeviceToHost, ctx->stream));
-                CU(ctx, cudaStreamSynchronize(ctx->stream));
-            }
+            CU(ctx, launch_compact_hits(ctx->stream, ctx->cand.as<Candidate>(), ctx->ovl.as<OverlapOut>(), cand_cap, dc + 0, jmin, keep_all,
+                                        ctx->cand2.as<Candidate>(), ctx->ovl2.as<OverlapOut>(), dc + 5, &launches));
+            CU(ctx, cudaMemcpyAsync(cnt, dc, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));                      // sync 1 of 2: the counters
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.probe_ms += ms;
+            cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.filter_ms += ms;
+            if (cnt[0] <= cand_cap) break;
+            cand_cap = cnt[0];   // rare: more candidates than guessed; rerun with the exact size
+        }
+        if (cnt[0] > cand_cap) return fail(ctx, MHAPB_ECUDA, "candidate buffer overrun after resize");
+        ctx->cand_cap_hint = std::min<uint64_t>(cnt[0] + cnt[0] / 8, 1ull << 31);
+        if (cnt[4] > ovf_threads) ctx->ovf_threads_hint = (uint32_t)std::min<uint64_t>((cnt[4] + 127) & ~127ull, 148ull * 1024);
+        st.elements_processed = (int64_t)cnt[1];
+        st.sequences_hit = (int64_t)cnt[2];
+        st.fully_compared = (int64_t)cnt[0];
+        const unsigned long long nkeep = cnt[5];
+        if (nkeep > 0) {
+            CU(ctx, ctx->h_cand.ensure(nkeep * sizeof(Candidate)));
+            CU(ctx, ctx->h_ovl.ensure(nkeep * sizeof(OverlapOut)));
+            const Candidate *hc = ctx->h_cand.as<Candidate>();
+            const OverlapOut *ho = ctx->h_ovl.as<OverlapOut>();
+            cudaEventRecord(ctx->ev[6], ctx->stream);
+            CU(ctx, cudaMemcpyAsync(ctx->h_cand.p, ctx->cand2.p, nkeep * sizeof(Candidate), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(ctx->h_ovl.p, ctx->ovl2.p, nkeep * sizeof(OverlapOut), cudaMemcpyDeviceToHost, ctx->stream));
+            cudaEventRecord(ctx->ev[7], ctx->stream);
+            CU(ctx, cudaStreamSynchronize(ctx->stream));                      // sync 2 of 2: the surviving pairs
+            cudaEventElapsedTime(&ctx->timing.d2h_ms, ctx->ev[6], ctx->ev[7]);
             // score + MatchResult fields, split over host threads (order of hits is unspecified, as in the reference)
-            const unsigned nthr = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), nkeep / 4096 + 1));
-            std::vector<std::vector<mhapb_hit>> part(nthr);
+            hit_arr = (mhapb_hit *)malloc(sizeof(mhapb_hit) * (size_t)nkeep);
+            if (!hit_arr) return fail(ctx, MHAPB_ENOMEM, "malloc hits");
+            const unsigned nthr = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), nkeep / 16384 + 1));
             std::vector<int64_t> acc(nthr, 0);
+            std::vector<uint64_t> kept(nthr, 0);
+            // every thread scores a contiguous slice in place (slot i of the result for pair i); rejected pairs leave
+            // holes that are closed afterwards
             auto work = [&](unsigned t) {
                 const uint64_t lo = nkeep * t / nthr, hi = nkeep * (t + 1) / nthr;
-                std::vector<mhapb_hit> &outv = part[t];
-                outv.reserve((size_t)(hi - lo));
+                uint64_t w = lo;
                 for (uint64_t i = lo; i < hi; i++) {
                     const OverlapOut &o = ho[i];
                     double score = 0.0;   // OverlapInfo.EMPTY
@@ -514,14 +440,15 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
                     mhapb_hit h{};
                     const uint32_t qi = hc[i].q, ti = hc[i].t;
                     h.from_id = q.h_id[qi]; h.to_id = s.h_id[ti];
-                    h.from_fwd = q.h_fwd[qi]; h.to_fwd = s.h_fwd[ti];
+                    h.from_fwd = q.h_fwd ? q.h_fwd[qi] : 1; h.to_fwd = s.h_fwd[ti];
                     h.hit_count = (int32_t)hc[i].count;
                     h.a1 = o.a1; h.a2 = o.a2; h.b1 = o.b1; h.b2 = o.b2;
                     h.valid_count = o.valid; h.intersect = o.inter; h.kmin = o.kmin;
                     h.from_len = q.h_len[qi]; h.to_len = s.h_len[ti];
                     h.score = score; h.accepted = accept ? 1 : 0;
-                    outv.push_back(h);
+                    hit_arr[w++] = h;
                 }
+                kept[t] = w - lo;
             };
             if (nthr == 1) work(0);
             else {
@@ -530,18 +457,12 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
                 for (auto &x : th) x.join();
             }
             size_t total = 0;
-            std::vector<size_t> offs(nthr, 0);
-            for (unsigned t = 0; t < nthr; t++) { offs[t] = total; total += part[t].size(); st.matches_processed += acc[t]; }
-            hit_arr = (mhapb_hit *)malloc(sizeof(mhapb_hit) * std::max<size_t>(1, total));
-            if (!hit_arr) return fail(ctx, MHAPB_ENOMEM, "malloc hits");
-            n_hits = total;
-            auto copy_part = [&](unsigned t) { if (!part[t].empty()) memcpy(hit_arr + offs[t], part[t].data(), sizeof(mhapb_hit) * part[t].size()); };
-            if (nthr == 1) copy_part(0);
-            else {
-                std::vector<std::thread> th;
-                for (unsigned t = 0; t < nthr; t++) th.emplace_back(copy_part, t);
-                for (auto &x : th) x.join();
+            for (unsigned t = 0; t < nthr; t++) {
+                const uint64_t lo = nkeep * t / nthr;
+                if (total != lo && kept[t]) memmove(hit_arr + total, hit_arr + lo, sizeof(mhapb_hit) * kept[t]);
+                total += kept[t]; st.matches_processed += acc[t];
             }
+            n_hits = total;
         }
     }
     ctx->timing.kernel_launches += launches;
@@ -567,7 +488,8 @@ int h2d_bases(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, uint32
 }
 
 // sketch reads and append them to the store (shared by store_add_reads and the tests' store_get path)
-int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, const int64_t *ids, uint32_t n_reads, int both, int64_t *n_added)
+int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, const int64_t *ids, uint32_t n_reads, int both, int64_t *n_added,
+                     const uint8_t *d_resident = nullptr /* the reads are already in HBM at this address: no H2D */)
 {
     Store &s = ctx->store;
     if (!s.configured) return fail(ctx, MHAPB_ESTATE, "mhapb_store_reset must be called first");
@@ -579,14 +501,16 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
     // finds those before rows are assigned.  Forward strand empty => the read is skipped; only the reverse strand
     // empty => the forward sketch alone is stored (SequenceSketchStreamer.java:123-156,225-240).
     std::vector<uint8_t> valid((size_t)n_reads * per, 1);
-    bool bases_on_device = false;
+    bool bases_on_device = d_resident != nullptr;
+    if (d_resident) { cudaEventRecord(ctx->ev[4], ctx->stream); cudaEventRecord(ctx->ev[5], ctx->stream); }
+    auto dev_bases = [&]() { return d_resident ? d_resident : ctx->bases.as<uint8_t>(); };
     if (filter_can_empty(filter_view(ctx)) && n_reads) {
         std::vector<int64_t> ident((size_t)n_reads * per);
         for (size_t i = 0; i < ident.size(); i++) ident[i] = (int64_t)i;
-        int rc0 = h2d_bases(ctx, bases, offsets, n_reads);
+        int rc0 = bases_on_device ? MHAPB_OK : h2d_bases(ctx, bases, offsets, n_reads);
         if (rc0) return rc0;
         bases_on_device = true;
-        rc0 = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, both, ident, nullptr, nullptr, 0, nullptr, &valid);
+        rc0 = sketch_core(ctx, s.p, dev_bases(), offsets, n_reads, both, ident, nullptr, nullptr, 0, nullptr, &valid);
         if (rc0) return rc0;
     }
     auto strand_kept = [&](uint32_t r, int st) { return valid[(size_t)r * per] && valid[(size_t)r * per + st]; };
@@ -618,11 +542,11 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
         if (rc) return rc;
         const size_t S = (size_t)s.ord_stride;
         CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)added * S * 8, ctx->stream));
-        rc = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>());
+        rc = sketch_core(ctx, s.p, dev_bases(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>());
         if (rc) return rc;
         float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.h2d_ms += ms;
         s.n = next;
-        s.indexed = false;
+        s.indexed = false; s.fwd_list_valid = false;
         rc = store_sync_columns(ctx, n0);
         if (rc) s.n = n0;
         return rc;
@@ -630,6 +554,45 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
     const int rc = device_part();
     if (rc) store_rollback_meta(s, meta0);
     return rc;
+}
+
+int sketch_query_reads(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, const int64_t *ids, uint32_t n_reads,
+                       std::vector<int64_t> *qid, std::vector<int32_t> *qlen, std::vector<int32_t> *qlenk, const uint8_t *d_resident)
+{
+    Store &s = ctx->store;
+    std::vector<int64_t> rows(n_reads, -1);
+    int64_t nq = 0;
+    std::vector<uint8_t> valid(n_reads, 1);
+    bool bases_on_device = d_resident != nullptr;
+    auto dev_bases = [&]() { return d_resident ? d_resident : ctx->bases.as<uint8_t>(); };
+    if (filter_can_empty(filter_view(ctx)) && n_reads) {   // see add_reads_locked
+        std::vector<int64_t> ident(n_reads);
+        for (size_t i = 0; i < ident.size(); i++) ident[i] = (int64_t)i;
+        int rc0 = bases_on_device ? MHAPB_OK : h2d_bases(ctx, bases, offsets, n_reads);
+        if (rc0) return rc0;
+        bases_on_device = true;
+        rc0 = sketch_core(ctx, s.p, dev_bases(), offsets, n_reads, 0, ident, nullptr, nullptr, 0, nullptr, &valid);
+        if (rc0) return rc0;
+    }
+    for (uint32_t r = 0; r < n_reads; r++) {
+        uint64_t len = offsets[r + 1] - offsets[r];
+        if (read_status(s.p, len) || !valid[r]) continue;
+        rows[r] = nq++;
+        qid->push_back(ids ? ids[r] : (int64_t)r + 1); qlen->push_back((int32_t)len);
+        qlenk->push_back((int32_t)len - s.p.ordered_kmer_size + 1);
+    }
+    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.p.ordered_sketch_size;
+    CU(ctx, ctx->q_minhash.ensure((size_t)nq * H * 4 + 16));
+    CU(ctx, ctx->q_ord.ensure((size_t)nq * S * 8 + 16));
+    CU(ctx, ctx->q_ordn.ensure((size_t)nq * 4 + 16));
+    if (nq) {
+        int rc = bases_on_device ? MHAPB_OK : h2d_bases(ctx, bases, offsets, n_reads);
+        if (rc) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->q_ord.p, 0, (size_t)nq * S * 8, ctx->stream));
+        rc = sketch_core(ctx, s.p, dev_bases(), offsets, n_reads, 0, rows, ctx->q_minhash.as<int32_t>(), ctx->q_ord.as<int32_t>(), (int)S, ctx->q_ordn.as<int32_t>());
+        if (rc) return rc;
+    }
+    return MHAPB_OK;
 }
 
 } // namespace
@@ -671,6 +634,10 @@ void mhapb_destroy(mhapb_ctx *ctx)
                       &ctx->q_id, &ctx->eq, &ctx->store.minhash, &ctx->store.ord, &ctx->store.ord_n, &ctx->store.lenk, &ctx->store.len,
                       &ctx->store.id, &ctx->store.slots, &ctx->store.postings, &ctx->f_keys, &ctx->f_idf, &ctx->f_used, &ctx->f_bloom};
     for (auto b : bufs) b->release();
+    DevBuf *more[] = {&ctx->ovf_q, &ctx->store.fwd_list, &ctx->g_minhash, &ctx->g_ord, &ctx->g_ordn, &ctx->g_lenk, &ctx->g_len, &ctx->g_id, &ctx->g_pack, &ctx->g_small};
+    for (auto b : more) b->release();
+    ctx->h_cand.release(); ctx->h_ovl.release();
+    comm_release(ctx);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
@@ -684,6 +651,11 @@ int mhapb_get_timing(mhapb_ctx *ctx, mhapb_timing *out)
 {
     if (!ctx || !out) return MHAPB_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->index_timing_pending) {
+        cudaSetDevice(ctx->device);
+        if (cudaEventSynchronize(ctx->ev[9]) == cudaSuccess) cudaEventElapsedTime(&ctx->timing.index_ms, ctx->ev[8], ctx->ev[9]);
+        ctx->index_timing_pending = false;
+    }
     *out = ctx->timing;
     return MHAPB_OK;
 }
@@ -967,6 +939,17 @@ static int check_sketch_shape(mhapb_ctx *ctx, int32_t num_hashes, int32_t ordere
     return MHAPB_OK;
 }
 
+int mhapb_store_add_reads_device(mhapb_ctx *ctx, const void *d_bases, const uint64_t *h_offsets, const int64_t *ids, uint32_t n_reads,
+                                 int both_strands, int64_t *n_added)
+{
+    if (!ctx) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!h_offsets || (!d_bases && n_reads && h_offsets[n_reads] > h_offsets[0])) return fail(ctx, MHAPB_EINVAL, "null bases/offsets");
+    reset_sketch_timing(ctx);
+    return add_reads_locked(ctx, nullptr, h_offsets, ids, n_reads, both_strands, n_added, (const uint8_t *)d_bases);
+}
+
 static int add_sketches_common(mhapb_ctx *ctx, const int64_t *ids, const uint8_t *is_fwd, const int32_t *seq_len,
                                const int32_t *seq_len_kmers, const void *minhash, const void *ord, const int32_t *ord_n,
                                int32_t ord_stride, uint32_t n, cudaMemcpyKind kind)
@@ -1001,7 +984,7 @@ static int add_sketches_common(mhapb_ctx *ctx, const int64_t *ids, const uint8_t
         CU(ctx, cudaMemcpyAsync(s.ord_n.as<int32_t>() + n0, ord_n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         s.n += n;
-        s.indexed = false;
+        s.indexed = false; s.fwd_list_valid = false;
         rc = store_sync_columns(ctx, n0);
         if (rc) s.n = n0;
         return rc;
@@ -1147,7 +1130,19 @@ int mhapb_search_self(mhapb_ctx *ctx, const mhapb_search_params *sp, mhapb_hit *
     q.h_id = s.h_id.data(); q.h_fwd = s.h_fwd.data(); q.h_len = s.h_len.data();
     int64_t first = std::max<int64_t>(0, sp->query_first);
     int64_t last = sp->query_count < 0 ? s.n : std::min<int64_t>(s.n, first + sp->query_count);
-    for (int64_t i = first; i < last; i++) if (s.h_fwd[i]) q.list.push_back((uint32_t)i);   // AbstractMatchSearch.java:128-129
+    if (first == 0 && last == s.n) {   // every forward sketch queries: the list lives on the device, rebuilt only when the store changed
+        if (!s.fwd_list_valid) {
+            std::vector<uint32_t> l;
+            for (int64_t i = 0; i < s.n; i++) if (s.h_fwd[i]) l.push_back((uint32_t)i);   // AbstractMatchSearch.java:128-129
+            CU(ctx, s.fwd_list.ensure(l.size() * 4 + 4));
+            CU(ctx, cudaMemcpyAsync(s.fwd_list.p, l.data(), l.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            s.fwd_list_n = (int64_t)l.size(); s.fwd_list_valid = true;
+        }
+        q.d_list = s.fwd_list.as<uint32_t>(); q.n_list = s.fwd_list_n;
+    } else {
+        for (int64_t i = first; i < last; i++) if (s.h_fwd[i]) q.list.push_back((uint32_t)i);
+    }
     return search_core(ctx, sp, q, 1, out, n_out, stats);
 }
 
@@ -1168,7 +1163,10 @@ static int search_query_sketches_locked(mhapb_ctx *ctx, const mhapb_search_param
     q.d_minhash = d_minhash; q.d_ord = d_ord; q.d_ordn = d_ordn;
     q.d_lenk = ctx->q_lenk.as<int32_t>(); q.d_len = ctx->q_len.as<int32_t>(); q.d_id = ctx->q_id.as<int64_t>(); q.ord_stride = ord_stride;
     q.h_id = ids; q.h_fwd = is_fwd; q.h_len = seq_len;
-    for (uint32_t i = 0; i < n; i++) if (is_fwd[i]) q.list.push_back(i);   // AbstractMatchSearch.java:225 dequeue(true)
+    bool all_fwd = true;
+    for (uint32_t i = 0; i < n && all_fwd; i++) all_fwd = is_fwd[i] != 0;
+    if (all_fwd) { q.list_all = true; q.n_all = n; }
+    else for (uint32_t i = 0; i < n; i++) if (is_fwd[i]) q.list.push_back(i);   // AbstractMatchSearch.java:225 dequeue(true)
     return search_core(ctx, sp, q, to_self, out, n_out, stats);
 }
 
@@ -1222,40 +1220,12 @@ int mhapb_search_query_reads(mhapb_ctx *ctx, const mhapb_search_params *sp, cons
     if (!s.configured || s.n == 0) return fail(ctx, MHAPB_ESTATE, "search on an empty store");
     if (!offsets || (!bases && n_reads && offsets[n_reads] > offsets[0])) return fail(ctx, MHAPB_EINVAL, "null bases/offsets");
     reset_sketch_timing(ctx);
-    // forward-only sketches of the valid query reads, compacted
-    std::vector<int64_t> rows(n_reads, -1), qid; std::vector<uint8_t> qfwd; std::vector<int32_t> qlen, qlenk;
-    int64_t nq = 0;
-    std::vector<uint8_t> valid(n_reads, 1);
-    bool bases_on_device = false;
-    if (filter_can_empty(filter_view(ctx)) && n_reads) {   // see add_reads_locked
-        std::vector<int64_t> ident(n_reads);
-        for (size_t i = 0; i < ident.size(); i++) ident[i] = (int64_t)i;
-        int rc0 = h2d_bases(ctx, bases, offsets, n_reads);
-        if (rc0) return rc0;
-        bases_on_device = true;
-        rc0 = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, 0, ident, nullptr, nullptr, 0, nullptr, &valid);
-        if (rc0) return rc0;
-    }
-    for (uint32_t r = 0; r < n_reads; r++) {
-        uint64_t len = offsets[r + 1] - offsets[r];
-        if (read_status(s.p, len) || !valid[r]) continue;
-        rows[r] = nq++;
-        qid.push_back(ids ? ids[r] : (int64_t)r + 1); qfwd.push_back(1); qlen.push_back((int32_t)len);
-        qlenk.push_back((int32_t)len - s.p.ordered_kmer_size + 1);
-    }
-    const size_t H = (size_t)s.p.num_hashes, S = (size_t)s.p.ordered_sketch_size;
-    CU(ctx, ctx->q_minhash.ensure((size_t)nq * H * 4 + 4));
-    CU(ctx, ctx->q_ord.ensure((size_t)nq * S * 8 + 8));
-    CU(ctx, ctx->q_ordn.ensure((size_t)nq * 4 + 4));
-    if (nq) {
-        int rc = bases_on_device ? MHAPB_OK : h2d_bases(ctx, bases, offsets, n_reads);
-        if (rc) return rc;
-        CU(ctx, cudaMemsetAsync(ctx->q_ord.p, 0, (size_t)nq * S * 8, ctx->stream));
-        rc = sketch_core(ctx, s.p, ctx->bases.as<uint8_t>(), offsets, n_reads, 0, rows, ctx->q_minhash.as<int32_t>(), ctx->q_ord.as<int32_t>(), (int)S, ctx->q_ordn.as<int32_t>());
-        if (rc) return rc;
-    }
+    std::vector<int64_t> qid; std::vector<int32_t> qlen, qlenk;
+    int rc = sketch_query_reads(ctx, bases, offsets, ids, n_reads, &qid, &qlen, &qlenk, nullptr);
+    if (rc) return rc;
+    const std::vector<uint8_t> qfwd(qid.size(), 1);
     return search_query_sketches_locked(ctx, sp, qid.data(), qfwd.data(), qlen.data(), qlenk.data(), ctx->q_minhash.as<int32_t>(),
-                                        ctx->q_ord.as<int32_t>(), ctx->q_ordn.as<int32_t>(), (int32_t)S, (uint32_t)nq, out, n_out, stats);
+                                        ctx->q_ord.as<int32_t>(), ctx->q_ordn.as<int32_t>(), s.p.ordered_sketch_size, (uint32_t)qid.size(), out, n_out, stats);
 }
 
 int mhapb_format_match(const mhapb_hit *h, char *buf, size_t buflen)

@@ -101,7 +101,8 @@ struct ProbeArgs {
     const int32_t *t_len;      // [n_store]
     int to_self, num_min_matches, min_store_length;
     Candidate *cand; uint64_t cand_cap;
-    unsigned long long *counters;  // [0]=n_cand [1]=elements_processed [2]=sequences_hit
+    unsigned long long *counters;  // [0]=n_cand [1]=elements_processed [2]=sequences_hit [3]=n queries in ovf_q
+    uint32_t *ovf_q;               // [nq_list] queries whose hit table overflowed in the first pass
 };
 cudaError_t launch_probe(cudaStream_t st, IndexView iv, ProbeArgs a, int *launches);
 
@@ -109,6 +110,8 @@ struct OverlapOut { int32_t a1, a2, b1, b2, valid, inter, kmin, empty; };
 
 struct FilterArgs {
     const Candidate *cand; uint64_t n_cand;
+    const unsigned long long *n_cand_dev; uint64_t cand_cap;   // when set: the count is read on the device (min(*n_cand_dev, cand_cap))
+    const unsigned long long *n_sel_dev;                       // thread-per-candidate kernel: count of sel[] read on the device
     const int32_t *q_ord; const int32_t *q_ord_n; const int32_t *q_lenk; int q_stride;   // [nq][stride][2]
     const int32_t *t_ord; const int32_t *t_ord_n; const int32_t *t_lenk; int t_stride;
     double max_shift;
@@ -119,15 +122,15 @@ struct FilterArgs {
 };
 // thread-per-candidate kernel (any sketch size, any match count; serial merge per thread)
 cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches);
-// warp-per-candidate kernel (sketches staged in shared memory, hash-range-partitioned merge); returns
-// cudaErrorInvalidConfiguration if the sketches do not fit shared memory (caller uses launch_filter)
+// warp-per-candidate kernel (hash-range-partitioned merge, any sketch size; pairs with more than 512 match records are
+// handed to launch_filter through ovf_list / ovf_count)
 cudaError_t launch_filter_warp(cudaStream_t st, FilterArgs a, int *launches);
 
 // Compact the (candidate, overlap) pairs that can still pass the score threshold: non-empty overlaps whose bottom-k
 // jaccard inter/kmin is >= jmin (a bound the caller lowers by a safety margin; the exact double-precision score
 // test stays on the host).  keep_all copies everything.  d_count: 64-bit cursor, zero on entry.
-cudaError_t launch_compact_hits(cudaStream_t st, const Candidate *cand, const OverlapOut *ovl, uint64_t n, double jmin, int keep_all,
-                                Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *d_count, int *launches);
+cudaError_t launch_compact_hits(cudaStream_t st, const Candidate *cand, const OverlapOut *ovl, uint64_t n, const unsigned long long *n_dev,
+                                double jmin, int keep_all, Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *d_count, int *launches);
 
 cudaError_t launch_equal_count(cudaStream_t st, const int32_t *a, const int32_t *b, int H, int32_t *d_out, int *launches);
 

@@ -29,26 +29,53 @@ __device__ __forceinline__ uint32_t slot_hash(uint32_t value, int log2capw)
 // ---------------------------------------------------------------------------------------------
 // Sub-table w (capw slots, capw = pow2 >= 2*n_store) holds the distinct values of min-hash word w,
 // i.e. it is the reference's hashes.get(w) map.  During the count pass a slot is (value | cnt<<32).
-__global__ void k_index_count(const int32_t *__restrict__ minhash, int64_t n_store, int H, uint64_t *slots, int log2capw)
+// Work order: a CTA owns one (word group, sketch range) tile, word groups outermost.  A group is 8 consecutive words = the 32-byte
+// sector of a min-hash row, so every sector read from HBM is fully used, and the sub-tables the CTAs resident at any moment
+// insert into are those of one or two word groups (8 x capw x 8 B = 32 MB for 2*10^5 sketches): they stay in the 126 MB L2 and
+// the CAS / add traffic never goes to DRAM.  (The first version walked the rows linearly, word innermost: consecutive threads
+// hit 512 different sub-tables -- 2 GB of working set, one DRAM sector per atomic; ncu: 31-38 % of DRAM throughput for 8-byte slots.)
+constexpr int kIdxGroup = 8;          // words per group
+constexpr int kIdxTileRows = 2048;    // sketches per tile
+
+__device__ __forceinline__ bool index_tile(int64_t tile, int64_t tiles_per_group, int64_t n_store, int H, int *w0, int *nw, int64_t *r0, int64_t *r1)
 {
-    const int64_t total = n_store * H;
+    const int64_t g = tile / tiles_per_group, t = tile % tiles_per_group;
+    *w0 = (int)g * kIdxGroup;
+    *nw = min(kIdxGroup, H - *w0);
+    *r0 = t * kIdxTileRows;
+    *r1 = min(n_store, *r0 + kIdxTileRows);
+    return *w0 < H;
+}
+
+__global__ void __launch_bounds__(256) k_index_count(const int32_t *__restrict__ minhash, int64_t n_store, int H, uint64_t *slots, int log2capw)
+{
     const uint32_t capmask = (1u << log2capw) - 1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int w = (int)(i % H);
-        const uint32_t v = (uint32_t)minhash[i];
-        uint64_t *sub = slots + ((size_t)w << log2capw);
-        uint32_t p = slot_hash(v, log2capw);
-        for (;;) {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&sub[p]);
-            if (cur == kEmptySlot) {
-                cur = atomicCAS(reinterpret_cast<unsigned long long *>(&sub[p]), (unsigned long long)kEmptySlot, (unsigned long long)v);
-                if (cur == kEmptySlot) cur = v;
+    const int64_t tiles_per_group = (n_store + kIdxTileRows - 1) / kIdxTileRows;
+    const int64_t n_tiles = tiles_per_group * ((H + kIdxGroup - 1) / kIdxGroup);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int w0, nw; int64_t r0, r1;
+        index_tile(tile, tiles_per_group, n_store, H, &w0, &nw, &r0, &r1);
+        // thread -> (row, word in group): 8 consecutive threads read one 32-byte sector
+        for (int64_t e = threadIdx.x; e < (r1 - r0) * kIdxGroup; e += blockDim.x) {
+            const int64_t row = r0 + (e >> 3);
+            const int wi = (int)(e & 7);
+            if (wi >= nw) continue;
+            const int w = w0 + wi;
+            const uint32_t v = (uint32_t)minhash[row * H + w];
+            uint64_t *sub = slots + ((size_t)w << log2capw);
+            uint32_t p = slot_hash(v, log2capw);
+            for (;;) {
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&sub[p]);
+                if (cur == kEmptySlot) {
+                    cur = atomicCAS(reinterpret_cast<unsigned long long *>(&sub[p]), (unsigned long long)kEmptySlot, (unsigned long long)v);
+                    if (cur == kEmptySlot) cur = v;
+                }
+                if ((uint32_t)cur == v) {
+                    atomicAdd(reinterpret_cast<unsigned int *>(&sub[p]) + 1, 1u);   // cnt lives in the high word
+                    break;
+                }
+                p = (p + 1) & capmask;
             }
-            if ((uint32_t)cur == v) {
-                atomicAdd(reinterpret_cast<unsigned int *>(&sub[p]) + 1, 1u);   // cnt lives in the high word
-                break;
-            }
-            p = (p + 1) & capmask;
         }
     }
 }
@@ -118,19 +145,27 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint64_t *__r
     for (int q = 0; q < kScanItems; q++) { if (base + q < n) start[base + q] = run; run += c[q]; }
 }
 
-__global__ void k_index_fill(const int32_t *__restrict__ minhash, int64_t n_store, int H, const uint64_t *__restrict__ slots,
-                             int log2capw, uint32_t *start, uint32_t *postings)
+__global__ void __launch_bounds__(256) k_index_fill(const int32_t *__restrict__ minhash, int64_t n_store, int H, const uint64_t *__restrict__ slots,
+                                                    int log2capw, uint32_t *start, uint32_t *postings)
 {
-    const int64_t total = n_store * H;
     const uint32_t capmask = (1u << log2capw) - 1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int w = (int)(i % H);
-        const uint32_t v = (uint32_t)minhash[i];
-        const size_t sub = (size_t)w << log2capw;
-        uint32_t p = slot_hash(v, log2capw);
-        while ((uint32_t)slots[sub + p] != v || slots[sub + p] == kEmptySlot) p = (p + 1) & capmask;
-        uint32_t pos = atomicAdd(&start[sub + p], 1u);
-        postings[pos] = (uint32_t)(i / H);
+    const int64_t tiles_per_group = (n_store + kIdxTileRows - 1) / kIdxTileRows;
+    const int64_t n_tiles = tiles_per_group * ((H + kIdxGroup - 1) / kIdxGroup);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int w0, nw; int64_t r0, r1;
+        index_tile(tile, tiles_per_group, n_store, H, &w0, &nw, &r0, &r1);
+        for (int64_t e = threadIdx.x; e < (r1 - r0) * kIdxGroup; e += blockDim.x) {
+            const int64_t row = r0 + (e >> 3);
+            const int wi = (int)(e & 7);
+            if (wi >= nw) continue;
+            const int w = w0 + wi;
+            const uint32_t v = (uint32_t)minhash[row * H + w];
+            const size_t sub = (size_t)w << log2capw;
+            uint32_t p = slot_hash(v, log2capw);
+            for (;;) { const uint64_t sl = slots[sub + p]; if (sl != kEmptySlot && (uint32_t)sl == v) break; p = (p + 1) & capmask; }
+            const uint32_t pos = atomicAdd(&start[sub + p], 1u);
+            postings[pos] = (uint32_t)row;
+        }
     }
 }
 
@@ -154,12 +189,14 @@ cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = sms * 8;
-    k_index_count<<<grid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw);
+    const int64_t n_tiles = ((n_store + kIdxTileRows - 1) / kIdxTileRows) * ((H + kIdxGroup - 1) / kIdxGroup);
+    const int tgrid = (int)std::min<int64_t>(n_tiles, (int64_t)sms * 8);
+    k_index_count<<<tgrid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw);
     const size_t nb = (nslots + kScanTile - 1) / kScanTile;
     k_scan_tiles<<<(unsigned)nb, kScanThreads, 0, st>>>(iv.slots, nslots, d_block_sums);
     k_scan_sums<<<1, kScanThreads, 0, st>>>(d_block_sums, nb);
     k_scan_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(iv.slots, nslots, d_block_sums, d_tmp_start);
-    k_index_fill<<<grid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw, d_tmp_start, iv.postings);
+    k_index_fill<<<tgrid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw, d_tmp_start, iv.postings);
     k_index_pack<<<grid, 256, 0, st>>>(iv.slots, nslots, d_tmp_start, iv.postings);
     *launches += 6;
     return cudaGetLastError();
@@ -169,11 +206,15 @@ cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_
 // K2b: probe + hit counting
 // ---------------------------------------------------------------------------------------------
 // One CTA per query.  The H buckets are walked by the CTA's threads and the per-target hit counts
-// (the reference's bestSequenceHit map) live in a shared-memory open-addressed table.  A query
-// that touches more distinct targets than the table holds is recounted with dense per-range
-// counters (exact, a few extra bucket walks; only repeat-rich queries get there).
+// (the reference's bestSequenceHit map) live in a shared-memory open-addressed table.
+// Two launches share the kernel template: the first pass gives every query a SMALL table (1024 slots, 8 KB: 16 CTAs
+// per SM instead of 6, and an 8 KB clear per query instead of 32 KB -- with the index sharded over N GPUs a query meets
+// ~1/N of its hits per rank, the clear was most of the per-query cost); a query that touches more distinct targets than
+// the small table holds is appended to an overflow list and redone by the second pass with the 4096-slot table, which
+// in turn falls back to dense per-range counters (exact, a few extra bucket walks; only repeat-rich queries get there).
 constexpr int kProbeThreads = 128;
-constexpr int kHitCap = 4096;          // slots in the shared table (32 KB)
+constexpr int kHitCapSmall = 1024, kHitMaxSmall = 704;
+constexpr int kHitCap = 4096;          // slots in the big table (32 KB)
 constexpr int kHitMaxDistinct = 3072;  // switch to the dense path above this many distinct targets
 constexpr int kDenseRange = 2 * kHitCap * 2;   // u16 counters in the same 32 KB
 
@@ -211,20 +252,24 @@ __device__ __forceinline__ void emit_candidate(const ProbeArgs &a, uint32_t q, u
     if (p < a.cand_cap) { Candidate c; c.q = q; c.t = t; c.count = count; a.cand[p] = c; }
 }
 
+// SECOND = false: queries a.q_list[0..nq_list) (or 0..nq_list), table of CAP slots, overflowing queries -> a.ovf_q / counters[3]
+// SECOND = true : queries a.ovf_q[0..counters[3]), big table + dense fallback
+template <int CAP, int MAXD, bool SECOND>
 __global__ void __launch_bounds__(kProbeThreads)
 k_probe(IndexView iv, ProbeArgs a)
 {
-    __shared__ HitSlot s_tab[kHitCap];
+    __shared__ HitSlot s_tab[CAP];
     __shared__ int s_distinct, s_overflow;
     __shared__ unsigned long long s_elements;
 
-    for (int64_t qi = blockIdx.x; qi < a.nq_list; qi += gridDim.x) {
-        const uint32_t q = a.q_list ? a.q_list[qi] : (uint32_t)qi;
+    const int64_t n_work = SECOND ? (int64_t)a.counters[3] : a.nq_list;
+    for (int64_t qi = blockIdx.x; qi < n_work; qi += gridDim.x) {
+        const uint32_t q = SECOND ? a.ovf_q[qi] : (a.q_list ? a.q_list[qi] : (uint32_t)qi);
         const int32_t *qmh = a.q_minhash + (size_t)q * iv.H;
         const int64_t qid = a.q_id[q];
         const int32_t qlen = a.q_len[q];
 
-        for (int i = threadIdx.x; i < kHitCap; i += blockDim.x) { s_tab[i].t = 0xffffffffu; s_tab[i].c = 0; }
+        for (int i = threadIdx.x; i < CAP; i += blockDim.x) { s_tab[i].t = 0xffffffffu; s_tab[i].c = 0; }
         if (threadIdx.x == 0) { s_distinct = 0; s_overflow = 0; s_elements = 0; }
         __syncthreads();
 
@@ -232,20 +277,22 @@ k_probe(IndexView iv, ProbeArgs a)
         for (int w = threadIdx.x; w < iv.H; w += blockDim.x) {
             uint32_t begin;
             if (!find_bucket(iv, w, (uint32_t)qmh[w], &begin)) continue;
+            if (!SECOND && *reinterpret_cast<volatile int *>(&s_overflow)) break;   // the second pass redoes this query from scratch
             for (uint32_t p = begin;; p++) {
                 const uint32_t raw = __ldg(&iv.postings[p]);
                 const uint32_t t = raw & ~kLastFlag;
                 elements++;
-                if (!s_overflow) {
-                    uint32_t hs = (t * 0x9E3779B1u) >> 20;   // 12 bits
+                if (!*reinterpret_cast<volatile int *>(&s_overflow)) {
+                    uint32_t hs = (t * 0x9E3779B1u) >> (32 - (CAP == 4096 ? 12 : 10));
+                    static_assert(CAP == 4096 || CAP == 1024, "table sizes");
                     for (;;) {
                         uint32_t old = atomicCAS(&s_tab[hs].t, 0xffffffffu, t);
                         if (old == 0xffffffffu) {
-                            if (atomicAdd(&s_distinct, 1) + 1 > kHitMaxDistinct) s_overflow = 1;
+                            if (atomicAdd(&s_distinct, 1) + 1 > MAXD) s_overflow = 1;
                             old = t;
                         }
                         if (old == t) { atomicAdd(&s_tab[hs].c, 1u); break; }
-                        hs = (hs + 1) & (kHitCap - 1);
+                        hs = (hs + 1) & (CAP - 1);
                     }
                 }
                 if (raw & kLastFlag) break;
@@ -255,12 +302,14 @@ k_probe(IndexView iv, ProbeArgs a)
         __syncthreads();
 
         if (!s_overflow) {
-            for (int i = threadIdx.x; i < kHitCap; i += blockDim.x) {
+            for (int i = threadIdx.x; i < CAP; i += blockDim.x) {
                 const uint32_t t = s_tab[i].t;
                 if (t == 0xffffffffu) continue;
                 if (pass_filters(a, qid, qlen, t, s_tab[i].c)) emit_candidate(a, q, t, s_tab[i].c);
             }
             if (threadIdx.x == 0) { atomicAdd(&a.counters[1], s_elements); atomicAdd(&a.counters[2], (unsigned long long)s_distinct); }
+        } else if (!SECOND) {
+            if (threadIdx.x == 0) { const unsigned long long p = atomicAdd(&a.counters[3], 1ull); a.ovf_q[p] = q; }
         } else {
             // dense recount: targets [r0, r0+kDenseRange) per pass, u16 counters (count <= H <= 2048)
             uint16_t *cnt = reinterpret_cast<uint16_t *>(s_tab);
@@ -303,10 +352,13 @@ cudaError_t launch_probe(cudaStream_t st, IndexView iv, ProbeArgs a, int *launch
 {
     if (a.nq_list <= 0) return cudaSuccess;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t grid = (int64_t)sms * 6;
+    int64_t grid = (int64_t)sms * 16;
     if (grid > a.nq_list) grid = a.nq_list;
-    k_probe<<<(unsigned)grid, kProbeThreads, 0, st>>>(iv, a);
-    (*launches)++;
+    k_probe<kHitCapSmall, kHitMaxSmall, false><<<(unsigned)grid, kProbeThreads, 0, st>>>(iv, a);
+    // second pass over the overflow list (count read on the device: no host round trip; empty list = an idle launch)
+    int64_t grid2 = std::min<int64_t>((int64_t)sms * 6, a.nq_list);
+    k_probe<kHitCap, kHitMaxDistinct, true><<<(unsigned)grid2, kProbeThreads, 0, st>>>(iv, a);
+    *launches += 2;
     return cudaGetLastError();
 }
 
@@ -424,7 +476,9 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs a)
     sc.p2 = a.scratch + (size_t)a.scratch_entries * a.n_threads + tid;
     sc.tmp = a.scratch + 2 * (size_t)a.scratch_entries * a.n_threads + tid;
 
-    const uint64_t n_work = a.sel ? a.n_sel : a.n_cand;
+    uint64_t n_work = a.sel ? a.n_sel : a.n_cand;
+    if (a.sel && a.n_sel_dev) n_work = *a.n_sel_dev;                      // the warp kernel's overflow cursor
+    else if (!a.sel && a.n_cand_dev) n_work = min((uint64_t)*a.n_cand_dev, a.cand_cap);
     for (uint64_t wi = tid; wi < n_work; wi += a.n_threads) {
         const uint64_t ci = a.sel ? a.sel[wi] : wi;
         const Candidate c = a.cand[ci];
@@ -501,74 +555,82 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs a)
 // ---------------------------------------------------------------------------------------------
 // K2c, warp-per-candidate (the default)
 // ---------------------------------------------------------------------------------------------
-// Both ordered sketches are staged in shared memory with coalesced loads.  recordMatchingKmers is a
-// merge-join on hash whose state never carries across hash values (elements of either sketch with a
-// hash the other side lacks are skipped without a record; the first/last handling of duplicate hashes
-// stays inside one hash value), so the hash axis is cut into 32 ranges at values taken from sketch A and
-// every lane runs the reference's sequential loop on its range; concatenating the lanes' records in lane
-// order reproduces the reference's record order.  Median = exact k-th smallest by an 8-bit radix select;
-// optimizeShifts = ordered compaction of pos1 runs; the bottom-k merge is partitioned the same way, the
-// lane in which the union count crosses k finishing it sequentially.
+// recordMatchingKmers is a merge-join on hash whose state never carries across hash values (elements of either
+// sketch with a hash the other side lacks are skipped without a record; the first/last handling of duplicate hashes
+// stays inside one hash value), so the hash axis is cut into 32 ranges at values taken from sketch A and every lane
+// runs the reference's sequential loop on its range, straight from L2/L1; concatenating the lanes' records in lane
+// order reproduces the reference's record order.  Median = exact k-th smallest (rank by counting for <= 32 records,
+// 8-bit radix select above); optimizeShifts = ordered compaction of pos1 runs; the bottom-k merge is partitioned the
+// same way, the lane in which the union count crosses k finishing it sequentially.
+//
+// The first version of this kernel executed 28 700 warp instructions per candidate with 12.6 of 32 threads active
+// (profiles/r2a_k2_probe_filter_ncu_summary.txt): every `||` of the reference's if / else-if chain became a branch and the
+// three outcomes of a merge step ran one after the other.  Here a merge step is straight-line code -- the two window tests
+// are one unsigned compare each, "advance A" / "advance B" are predicates, the element that moved is reloaded under its
+// predicate -- and only an actual hash match (a few per lane) takes a branch; the two counting loops and the walk of the
+// bottom-k intersect are one fused pass.
 constexpr int kFwRecCap = 512;      // match records kept in shared memory per warp
 constexpr int kFwLaneCap = kFwRecCap / 2 / 32;   // private first-try slot per lane (8 records)
 // (a pair with more match records than kFwRecCap goes to the thread-per-candidate kernel)
 
-struct FwWindow { int32_t v1lo, v1hi, v2lo, v2hi, median, absmax; };
+// MatchData.valid1Lower/valid1Upper/valid2Lower/valid2Upper as (lower, width): pos is inside iff (unsigned)(pos - lo) < width
+struct FwWindow { int32_t lo1, w1, lo2, w2, median, absmax; };
 
 __device__ __forceinline__ FwWindow fw_window(int32_t median, int32_t absmax, int32_t len1, int32_t len2)
 {
     FwWindow w;
     w.median = median; w.absmax = absmax;
-    w.v1lo = max(0, -median - absmax); w.v2lo = max(0, median - absmax);            // MatchData.valid1Lower/valid2Lower
-    w.v1hi = min(len1, len2 - median + absmax); w.v2hi = min(len2, len1 + median + absmax);
+    w.lo1 = max(0, -median - absmax); w.lo2 = max(0, median - absmax);
+    w.w1 = max(0, min(len1, len2 - median + absmax) - w.lo1);
+    w.w2 = max(0, min(len2, len1 + median + absmax) - w.lo2);
     return w;
 }
 
-// Shared-memory layout of a staged sketch: element i lives at i + (i >> 5).  Lanes walk ranges that start
-// about n/32 elements apart (48 for S=1536, i.e. 96 words = a multiple of the 32 banks), so without the
-// skew every lane's loads would hit the same bank.
-struct FwSketch {
-    const int2 *p; bool skew;
-    __device__ __forceinline__ int2 operator[](int i) const { return skew ? p[i + (i >> 5)] : __ldg(p + i); }
-};
-
-__device__ __forceinline__ int fw_lower_bound(const FwSketch s, int n, int32_t h)
+__device__ __forceinline__ int fw_lower_bound(const int2 *__restrict__ s, int n, int32_t h)
 {
     int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (s[mid].x < h) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&s[mid]).x < h) lo = mid + 1; else hi = mid; }
     return lo;
 }
 
 // the reference loop (sketch/BottomOverlapSketch.java:428-515) on A[i1..e1) x B[i2..e2): returns the number of match
 // records and stores the first `cap` of them in out
-__device__ int fw_merge_range(const FwSketch A, int i1, int e1, const FwSketch Bs, int i2, int e2, const FwWindow &w, int2 *out, int cap)
+__device__ __forceinline__ int fw_merge_range(const int2 *__restrict__ A, int i1, const int e1, const int2 *__restrict__ Bs, int i2, const int e2,
+                                              const FwWindow &w, int2 *out, const int cap)
 {
     int count = 0;
     if (i1 >= e1 || i2 >= e2) return 0;
-    int2 a = A[i1], b = Bs[i2];
+    int2 a = __ldg(A + i1), b = __ldg(Bs + i2);
     for (;;) {
-        if (a.x < b.x || a.y < w.v1lo || a.y >= w.v1hi) { if (++i1 >= e1) break; a = A[i1]; }
-        else if (b.x < a.x || b.y < w.v2lo || b.y >= w.v2hi) { if (++i2 >= e2) break; b = Bs[i2]; }
-        else {
+        const bool aout = (uint32_t)(a.y - w.lo1) >= (uint32_t)w.w1;
+        const bool bout = (uint32_t)(b.y - w.lo2) >= (uint32_t)w.w2;
+        bool adv1 = (a.x < b.x) | aout;                        // :438
+        bool adv2 = !adv1 & ((b.x < a.x) | bout);              // :440
+        if (!(adv1 | adv2)) {                                  // equal hashes, both positions inside their windows
             const int32_t diff = (b.y - a.y) - w.median;
-            if (diff > w.absmax) { if (++i1 >= e1) break; a = A[i1]; }
-            else if (diff < -w.absmax) { if (++i2 >= e2) break; b = Bs[i2]; }
+            if (diff > w.absmax) adv1 = true;
+            else if (diff < -w.absmax) adv2 = true;
             else {
                 if (count < cap) out[count] = make_int2(a.y, b.y);
                 count++;
                 int i1last = i1, i2last = i2;
                 int32_t p1 = a.y, p2 = b.y;
-                for (int t = i1 + 1; t < e1; t++) { const int2 x = A[t]; if (!(x.x == a.x && x.y >= w.v1lo && x.y < w.v1hi)) break; i1last = t; p1 = x.y; }
-                for (int t = i2 + 1; t < e2; t++) { const int2 x = Bs[t]; if (!(x.x == b.x && x.y >= w.v2lo && x.y < w.v2hi)) break; i2last = t; p2 = x.y; }
+                for (int t = i1 + 1; t < e1; t++) { const int2 x = __ldg(A + t); if (!(x.x == a.x && (uint32_t)(x.y - w.lo1) < (uint32_t)w.w1)) break; i1last = t; p1 = x.y; }
+                for (int t = i2 + 1; t < e2; t++) { const int2 x = __ldg(Bs + t); if (!(x.x == b.x && (uint32_t)(x.y - w.lo2) < (uint32_t)w.w2)) break; i2last = t; p2 = x.y; }
                 if (i1 != i1last || i2 != i2last) {
                     if (count < cap) out[count] = make_int2(p1, p2);
                     count++;
                     i1 = i1last + 1; i2 = i2last + 1;
                 } else { i1++; i2++; }
                 if (i1 >= e1 || i2 >= e2) break;
-                a = A[i1]; b = Bs[i2];
+                a = __ldg(A + i1); b = __ldg(Bs + i2);
+                continue;
             }
         }
+        i1 += adv1; i2 += adv2;
+        if (i1 >= e1 || i2 >= e2) break;
+        if (adv1) a = __ldg(A + i1);
+        if (adv2) b = __ldg(Bs + i2);
     }
     return count;
 }
@@ -582,9 +644,21 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total)
     return incl - v;
 }
 
-// exact k-th smallest (0-based) of the shifts rec[i].y - rec[i].x, i < n: MSB-first 8-bit radix select
+// exact k-th smallest (0-based) of the shifts rec[i].y - rec[i].x, i < n
 __device__ int32_t fw_select_shift(const int2 *rec, int n, int k, uint32_t *hist, int lane)
 {
+    if (n <= 32) {   // rank by counting: one record per lane, n shuffles
+        int32_t v = 0;
+        if (lane < n) { const int2 r = rec[lane]; v = r.y - r.x; }
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const int32_t vj = __shfl_sync(kFull, v, j);
+            rank += (vj < v) | ((vj == v) & (j < lane));
+        }
+        const unsigned who = __ballot_sync(kFull, lane < n && rank == k);
+        return __shfl_sync(kFull, v, __ffs(who) - 1);
+    }
+    // MSB-first 8-bit radix select
     uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k + 1;
     for (int pass = 3; pass >= 0; pass--) {
         const int shift = pass * 8;
@@ -628,42 +702,36 @@ __device__ __forceinline__ void fw_update(const int2 *rec, int count, int32_t le
     *absmax = min(max(len1, len2), (int32_t)((double)overlap * max_shift));
 }
 
-template <bool STAGE>
-__global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a, int capA, int capB)
+__global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
 {
     extern __shared__ __align__(16) uint8_t fw_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = (size_t)(capA + capB + kFwRecCap) * 8 + 256 * 4;
+    const size_t per_warp = (size_t)kFwRecCap * 8 + 256 * 4;
     uint8_t *base = fw_smem + (size_t)wib * per_warp;
-    int2 *sA = reinterpret_cast<int2 *>(base);
-    int2 *sB = sA + capA;
-    int2 *rec = sB + capB;
-    // STAGE: both sketches copied to shared memory (skewed layout).  !STAGE: every lane walks its own contiguous
-    // range straight from L2/L1 (capA = capB = 0), which leaves room for 4x more resident warps.
+    int2 *rec = reinterpret_cast<int2 *>(base);
     uint32_t *hist = reinterpret_cast<uint32_t *>(rec + kFwRecCap);
     const uint64_t warp_id = (uint64_t)blockIdx.x * wpb + wib, n_warps = (uint64_t)gridDim.x * wpb;
+    // the candidate count is read on the device (it is K2b's cursor): no host round trip between probe and filter
+    uint64_t n_cand = a.n_cand;
+    if (a.n_cand_dev) { n_cand = *a.n_cand_dev; if (n_cand > a.cand_cap) n_cand = a.cand_cap; }
 
-    for (uint64_t ci = warp_id; ci < a.n_cand; ci += n_warps) {
+    for (uint64_t ci = warp_id; ci < n_cand; ci += n_warps) {
         const Candidate c = a.cand[ci];
         const int nA = a.q_ord_n[c.q], nB = a.t_ord_n[c.t];
         const int32_t len1 = a.q_lenk[c.q], len2 = a.t_lenk[c.t];
-        const int2 *gA = reinterpret_cast<const int2 *>(a.q_ord) + (size_t)c.q * a.q_stride;
-        const int2 *gB = reinterpret_cast<const int2 *>(a.t_ord) + (size_t)c.t * a.t_stride;
+        const int2 *A = reinterpret_cast<const int2 *>(a.q_ord) + (size_t)c.q * a.q_stride;
+        const int2 *Bs = reinterpret_cast<const int2 *>(a.t_ord) + (size_t)c.t * a.t_stride;
         __syncwarp();
-        if (STAGE) {
-            for (int i = lane; i < nA; i += 32) sA[i + (i >> 5)] = __ldg(&gA[i]);
-            for (int i = lane; i < nB; i += 32) sB[i + (i >> 5)] = __ldg(&gB[i]);
-        }
-        __syncwarp();
-        const FwSketch A{STAGE ? sA : gA, STAGE}, Bs{STAGE ? sB : gB, STAGE};
         OverlapOut o; o.a1 = o.a2 = o.b1 = o.b2 = o.valid = o.inter = o.kmin = 0; o.empty = 1;
         bool overflow = false;
 
         // hash ranges: lane l takes hashes in [h_l, h_{l+1}), h_l = A[l*nA/32].x (h_0 = -inf)
         int a0 = 0, b0 = 0;
         if (lane > 0 && nA > 0) {
-            const int32_t h = A[(int)(((long long)lane * nA) >> 5)].x;
-            a0 = fw_lower_bound(A, nA, h); b0 = fw_lower_bound(Bs, nB, h);
+            a0 = (int)(((long long)lane * nA) >> 5);
+            const int32_t h = __ldg(A + a0).x;
+            while (a0 > 0 && __ldg(A + a0 - 1).x == h) a0--;        // = lower_bound(A, h): equal hashes are adjacent
+            b0 = fw_lower_bound(Bs, nB, h);
         }
         int a1 = __shfl_down_sync(kFull, a0, 1), b1 = __shfl_down_sync(kFull, b0, 1);
         if (lane == 31) { a1 = nA; b1 = nB; }
@@ -744,20 +812,28 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a, int capA, int
                 o.b1 = max(0, java_round_div(n * le2 - re2, n - 1));
                 o.b2 = min(len2, java_round_div(n * re2 - le2, n - 1));
                 o.valid = valid;
-                // computeKBottomSketchJaccard (:304-364) over the entries whose position is inside [a1,a2] / [b1,b2]
-                int sa = 0, sbn = 0;
-                for (int i = a0; i < a1; i++) { const int32_t p = A[i].y; sa += (p >= o.a1 && p <= o.a2); }
-                for (int j = b0; j < b1; j++) { const int32_t p = Bs[j].y; sbn += (p >= o.b1 && p <= o.b2); }
-                // this lane's share of the two-pointer walk run to exhaustion: equal pairings and union steps
-                int inter_l = 0;
+                // computeKBottomSketchJaccard (:304-364) over the entries whose position is inside [a1,a2] / [b1,b2].
+                // One fused pass over this lane's two ranges: entries outside their window are skipped, the others are
+                // counted (sa, sbn) as the two-pointer walk consumes them; equal hashes are consumed together (inter_l).
+                const int32_t wa_lo = o.a1, wb_lo = o.b1;
+                const uint32_t wa_w = (uint32_t)max(0, o.a2 - o.a1 + 1), wb_w = (uint32_t)max(0, o.b2 - o.b1 + 1);
+                int sa = 0, sbn = 0, inter_l = 0;
                 {
                     int i = a0, j = b0;
-                    for (;;) {
-                        while (i < a1 && !(A[i].y >= o.a1 && A[i].y <= o.a2)) i++;
-                        while (j < b1 && !(Bs[j].y >= o.b1 && Bs[j].y <= o.b2)) j++;
-                        if (i >= a1 || j >= b1) break;
-                        const int32_t ha = A[i].x, hb = Bs[j].x;
-                        if (ha < hb) i++; else if (ha > hb) j++; else { inter_l++; i++; j++; }
+                    int2 ea = make_int2(0, 0), eb = make_int2(0, 0);
+                    if (i < a1) ea = __ldg(A + i);
+                    if (j < b1) eb = __ldg(Bs + j);
+                    while (i < a1 || j < b1) {
+                        const bool ha = i < a1, hb = j < b1;
+                        const bool ain = ha & ((uint32_t)(ea.y - wa_lo) < wa_w), bin = hb & ((uint32_t)(eb.y - wb_lo) < wb_w);
+                        const bool skipa = ha & !ain, skipb = hb & !bin, noskip = !(skipa | skipb);
+                        const bool takea = noskip & ain & (!bin | (ea.x <= eb.x));
+                        const bool takeb = noskip & bin & (!ain | (eb.x <= ea.x));
+                        sa += takea; sbn += takeb; inter_l += takea & takeb;
+                        const bool adva = skipa | takea, advb = skipb | takeb;
+                        i += adva; j += advb;
+                        if (adva && i < a1) ea = __ldg(A + i);
+                        if (advb && j < b1) eb = __ldg(Bs + j);
                     }
                 }
                 const int union_l = sa + sbn - inter_l;
@@ -772,12 +848,12 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a, int capA, int
                     else if (ubefore < k) {                                       // the range in which the walk stops
                         int i = a0, j = b0, uni = ubefore;
                         while (uni < k) {
-                            while (i < a1 && !(A[i].y >= o.a1 && A[i].y <= o.a2)) i++;
-                            while (j < b1 && !(Bs[j].y >= o.b1 && Bs[j].y <= o.b2)) j++;
+                            while (i < a1 && !((uint32_t)(__ldg(A + i).y - wa_lo) < wa_w)) i++;
+                            while (j < b1 && !((uint32_t)(__ldg(Bs + j).y - wb_lo) < wb_w)) j++;
                             if (i >= a1) { j++; }                                 // only B entries left in range: each is one union step
                             else if (j >= b1) { i++; }
                             else {
-                                const int32_t ha = A[i].x, hb = Bs[j].x;
+                                const int32_t ha = __ldg(A + i).x, hb = __ldg(Bs + j).x;
                                 if (ha < hb) i++; else if (ha > hb) j++; else { inter++; i++; j++; }
                             }
                             uni++;
@@ -795,35 +871,27 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a, int capA, int
 
 cudaError_t launch_filter_warp(cudaStream_t st, FilterArgs a, int *launches)
 {
-    if (a.n_cand == 0) return cudaSuccess;
-    static int stage = -1;
-    if (stage < 0) { const char *e = getenv("MHAPB_K2C_STAGE"); stage = (e && e[0] == '1') ? 1 : 0; }
-    int capA = 0, capB = 0;
-    if (stage) { capA = (a.q_stride + a.q_stride / 32 + 4) & ~3; capB = (a.t_stride + a.t_stride / 32 + 4) & ~3; }
-    const size_t per_warp = (size_t)(capA + capB + kFwRecCap) * 8 + 256 * 4;
-    if (per_warp > 100 * 1024) return cudaErrorInvalidConfiguration;
+    if (a.n_cand == 0 && !a.n_cand_dev) return cudaSuccess;
+    const size_t per_warp = (size_t)kFwRecCap * 8 + 256 * 4;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > 110 * 1024) wpb >>= 1;
+    const int wpb = 4;
     const size_t smem = per_warp * wpb;
-    auto kern = stage ? k_filter_warp<true> : k_filter_warp<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_warp, wpb * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+    }
     uint64_t grid = (uint64_t)sms * per_sm;
-    const uint64_t need = (a.n_cand + wpb - 1) / wpb;
-    if (grid > need) grid = need;
-    kern<<<(unsigned)grid, wpb * 32, smem, st>>>(a, capA, capB);
+    if (!a.n_cand_dev) { const uint64_t need = (a.n_cand + wpb - 1) / wpb; if (grid > need) grid = need; }
+    k_filter_warp<<<(unsigned)grid, wpb * 32, smem, st>>>(a);
     (*launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches)
 {
-    if (a.n_cand == 0) return cudaSuccess;
+    if (a.n_threads == 0) return cudaSuccess;
     unsigned grid = (a.n_threads + 127) / 128;
     k_filter<<<grid, 128, 0, st>>>(a);
     (*launches)++;
@@ -833,10 +901,11 @@ cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches)
 // ---------------------------------------------------------------------------------------------
 // result compaction: only pairs that can still pass the threshold travel to the host
 // ---------------------------------------------------------------------------------------------
-__global__ void k_compact_hits(const Candidate *__restrict__ cand, const OverlapOut *__restrict__ ovl, uint64_t n, double jmin, int keep_all,
-                               Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *count)
+__global__ void k_compact_hits(const Candidate *__restrict__ cand, const OverlapOut *__restrict__ ovl, uint64_t n, const unsigned long long *n_dev,
+                               double jmin, int keep_all, Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *count)
 {
     const int lane = threadIdx.x & 31;
+    if (n_dev) n = min((uint64_t)*n_dev, n);   // n = the capacity, *n_dev = K2b's candidate cursor
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
         bool keep = false;
@@ -856,13 +925,13 @@ __global__ void k_compact_hits(const Candidate *__restrict__ cand, const Overlap
     }
 }
 
-cudaError_t launch_compact_hits(cudaStream_t st, const Candidate *cand, const OverlapOut *ovl, uint64_t n, double jmin, int keep_all,
-                                Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *d_count, int *launches)
+cudaError_t launch_compact_hits(cudaStream_t st, const Candidate *cand, const OverlapOut *ovl, uint64_t n, const unsigned long long *n_dev,
+                                double jmin, int keep_all, Candidate *cand_out, OverlapOut *ovl_out, unsigned long long *d_count, int *launches)
 {
     if (n == 0) return cudaSuccess;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     uint64_t grid = std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 8);
-    k_compact_hits<<<(unsigned)grid, 256, 0, st>>>(cand, ovl, n, jmin, keep_all, cand_out, ovl_out, d_count);
+    k_compact_hits<<<(unsigned)grid, 256, 0, st>>>(cand, ovl, n, n_dev, jmin, keep_all, cand_out, ovl_out, d_count);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -45,6 +45,7 @@ struct Options {
     std::string s, q, p, f;
     int k = 16, num_hashes = 512, num_min_matches = 3, num_threads = 1, ordered_kmer = 12, ordered_sketch = 1536;
     int min_store_length = 0, min_olap_length = 116, settings = 0, device = 0;
+    std::vector<int> devices;   // --devices 0,1,2 / 0-7: the reads are sharded over these GPUs (mhapb_multi_*, NCCL inside the library)
     double threshold = 0.78, max_shift = 0.2, repeat_weight = 0.9, filter_threshold = 1.0e-5, repeat_idf_scale = 3.0;
     int supress_noise = 0;
     bool no_self = false, store_full_id = false, no_rc = false, no_tf = false;
@@ -76,6 +77,20 @@ Options parse(int argc, char **argv)
         else if (a == "--min-olap-length") o.min_olap_length = atoi(need(i));
         else if (a == "--settings") o.settings = atoi(need(i));
         else if (a == "--device") o.device = atoi(need(i));
+        else if (a == "--devices") {
+            std::string v = need(i);
+            size_t pos = 0;
+            while (pos <= v.size()) {
+                size_t c = v.find(',', pos);
+                std::string tok = v.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
+                size_t dash = tok.find('-');
+                if (tok.empty()) die("--devices: empty entry");
+                if (dash != std::string::npos && dash > 0) { for (int d = atoi(tok.substr(0, dash).c_str()); d <= atoi(tok.substr(dash + 1).c_str()); d++) o.devices.push_back(d); }
+                else o.devices.push_back(atoi(tok.c_str()));
+                if (c == std::string::npos) break;
+                pos = c + 1;
+            }
+        }
         else if (a == "--no-self") o.no_self = true;
         else if (a == "--no-rc") o.no_rc = true;   // main/MhapMain.java: does not stop rc sketches being stored (MinHashSearch.java:80)
         else if (a == "--store-full-id") o.store_full_id = true;
@@ -244,6 +259,7 @@ DatSketches read_dat(const std::string &path, int64_t offset)
 }
 
 void ck(mhapb_ctx *ctx, int rc) { if (rc) die(mhapb_last_error(ctx)); }
+void ckm(mhapb_multi *m, int rc) { if (rc) die(mhapb_multi_last_error(m)); }
 
 struct Totals { mhapb_stats st{}; };
 
@@ -283,8 +299,13 @@ int main(int argc, char **argv)
     Options o = parse(argc, argv);
     g_full_ids = o.store_full_id;
     const double t_total = now_s();
-    mhapb_ctx *ctx = nullptr;
-    if (mhapb_create(o.device, &ctx)) die(mhapb_last_error(nullptr));
+    // one context per GPU behind mhapb_multi (a single device forwards to the single-GPU calls); ctx = the first device,
+    // which also serves the -p mode
+    if (o.devices.empty()) o.devices.push_back(o.device);
+    mhapb_multi *multi = nullptr;
+    if (mhapb_multi_create(o.devices.data(), (int)o.devices.size(), &multi)) die(mhapb_last_error(nullptr));
+    const int n_dev = mhapb_multi_n_devices(multi);
+    mhapb_ctx *ctx = mhapb_multi_ctx(multi, 0);
     mhapb_sketch_params p{o.k, o.num_hashes, o.ordered_kmer, o.ordered_sketch, o.repeat_weight < 0.0 ? 1 : 0, o.min_olap_length};
 
     if (!o.f.empty()) {   // main/MhapMain.java:340-372: read the k-mer filter set
@@ -293,8 +314,9 @@ int main(int argc, char **argv)
         std::vector<uint8_t> text = read_text_any(o.f);
         mhapb_filter_params fp{o.filter_threshold, o.repeat_weight, o.repeat_idf_scale, o.supress_noise, o.no_tf ? 1 : 0};
         int64_t n_repeat = 0;
-        if (mhapb_filter_load_text(ctx, &fp, (const char *)text.data(), text.size(), o.no_rc ? 0 : 1, &n_repeat))
-            die(std::string("Could not parse k-mer filter file. ") + mhapb_last_error(ctx));
+        for (int d = 0; d < n_dev; d++)   // every device sketches with the same filter
+            if (mhapb_filter_load_text(mhapb_multi_ctx(multi, d), &fp, (const char *)text.data(), text.size(), o.no_rc ? 0 : 1, &n_repeat))
+                die(std::string("Could not parse k-mer filter file. ") + mhapb_last_error(mhapb_multi_ctx(multi, d)));
         fprintf(stderr, "Time (s) to read filter file: %g\n", now_s() - t0);
         fprintf(stderr, "Read in k-mer filter with %lld repeat k-mers.\n", (long long)n_repeat);
     }
@@ -323,7 +345,7 @@ int main(int argc, char **argv)
             fprintf(stderr, "Time (s): %g\n", now_s() - t0);
         }
         fprintf(stderr, "Total time (s): %g\n", now_s() - t_total);
-        mhapb_destroy(ctx);
+        mhapb_multi_destroy(multi);
         return 0;
     }
 
@@ -339,14 +361,15 @@ int main(int argc, char **argv)
         // a stored sketch scores with the k-mer size recorded in it (BottomOverlapSketch.kmerSize, :391-395,:613), whatever
         // --ordered-kmer-size says; sketches made with another size then fail the check of :594-595 when compared
         if (d.n) { store_ok = d.ok; p.ordered_kmer_size = d.ok; }
-        ck(ctx, mhapb_store_reset(ctx, &p));
-        ck(ctx, mhapb_store_add_sketches(ctx, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.H, d.ord.data(), d.ordn.data(), d.max_ord, d.ok, d.n));
+        ckm(multi, mhapb_multi_store_reset(multi, &p));
+        ckm(multi, mhapb_multi_store_add_sketches(multi, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.H, d.ord.data(), d.ordn.data(), d.max_ord, d.ok, d.n));
         n_sketches = d.n;
     } else {
-        ck(ctx, mhapb_store_reset(ctx, &p));
+        ckm(multi, mhapb_multi_store_reset(multi, &p));
         {   // one allocation of the per-call scratch for the largest batch instead of one per ramp step
-            const size_t chunk = fasta_chunk_bytes(o.s);
-            ck(ctx, mhapb_sketch_reserve(ctx, &p, chunk, (uint32_t)std::min<size_t>(chunk / 500 + 64, 1u << 24), 1));
+            const size_t chunk = fasta_chunk_bytes(o.s) / (size_t)n_dev + 65536;
+            for (int d = 0; d < n_dev; d++)
+                ck(mhapb_multi_ctx(multi, d), mhapb_sketch_reserve(mhapb_multi_ctx(multi, d), &p, chunk, (uint32_t)std::min<size_t>(chunk / 500 + 64, 1u << 24), 1));
         }
         struct stat fst;
         const double file_bytes = (!ends_with(o.s, ".gz") && !ends_with(o.s, ".bz2") && stat(o.s.c_str(), &fst) == 0) ? (double)fst.st_size : 0.0;
@@ -354,14 +377,14 @@ int main(int argc, char **argv)
             if (b.seq == 0 && file_bytes > 0 && b.text_len > 0 && (double)b.text_len < file_bytes) {
                 // size the store once from the first batch's record density instead of growing it batch by batch
                 const double est_reads = file_bytes / (double)b.text_len * b.n_reads() * 1.03 + 64;
-                ck(ctx, mhapb_store_reserve(ctx, (int64_t)(2 * est_reads)));
+                ckm(multi, mhapb_multi_store_reserve(multi, (int64_t)(2 * est_reads)));
             }
             int64_t added = 0;
-            ck(ctx, mhapb_store_add_reads(ctx, b.bases, b.offsets.data(), ids.data(), b.n_reads(), 1, &added));
+            ckm(multi, mhapb_multi_store_add_reads(multi, b.bases, b.offsets.data(), ids.data(), b.n_reads(), 1, &added));
             n_sketches += added;
         });
     }
-    if (n_sketches > 0) ck(ctx, mhapb_index_build(ctx));
+    if (n_sketches > 0 && n_dev == 1) ck(ctx, mhapb_index_build(ctx));   // several devices: every rank builds its index behind the exchange
     fprintf(stderr, "Stored %lld sequences in the index.\n", (long long)n_sketches);
     int64_t seq_number_processed = n_sketches / 2;   // main/MhapMain.java:462
     fprintf(stderr, "Processed %lld unique sequences (fwd and rev).\n", (long long)n_sketches);
@@ -374,7 +397,7 @@ int main(int argc, char **argv)
         const double t0 = now_s();
         if (n_sketches > 0) {
             mhapb_hit *hits = nullptr; uint64_t n = 0; mhapb_stats st{};
-            ck(ctx, mhapb_search_self(ctx, &sp, &hits, &n, &st));
+            ckm(multi, mhapb_multi_search_self(multi, &sp, &hits, &n, &st));
             emit(hits, n, st, tot, 0, store_names.empty() ? nullptr : &store_names, 0, store_names.empty() ? nullptr : &store_names);
         }
         fprintf(stderr, "Time (s) to score and output to self: %g\n", now_s() - t0);
@@ -392,7 +415,7 @@ int main(int argc, char **argv)
                 DatSketches d = read_dat(cf, seq_number_processed);
                 // the library repeats the reference's checks: "Number of hashes does not match..." (MinHashSearch.java:157-159),
                 // "Sketch k-mer size does not match between the two sequences." (BottomOverlapSketch.java:594-595)
-                ck(ctx, mhapb_search_query_sketches(ctx, &sp, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.H, d.ord.data(),
+                ckm(multi, mhapb_multi_search_query_sketches(multi, &sp, d.ids.data(), d.fwd.data(), d.len.data(), d.lenk.data(), d.mh.data(), d.H, d.ord.data(),
                                                     d.ordn.data(), d.max_ord, d.ok, d.n, &hits, &n, &st));
                 processed = st.sequences_searched;
                 from_sub = seq_number_processed;
@@ -401,7 +424,7 @@ int main(int argc, char **argv)
                 Names query_names;
                 for_each_fasta_batch(cf, seq_number_processed, o.num_threads, &query_names, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
                     mhapb_hit *bh = nullptr; uint64_t bn = 0; mhapb_stats bst{};
-                    ck(ctx, mhapb_search_query_reads(ctx, &sp, b.bases, b.offsets.data(), ids.data(), b.n_reads(), &bh, &bn, &bst));
+                    ckm(multi, mhapb_multi_search_query_reads(multi, &sp, b.bases, b.offsets.data(), ids.data(), b.n_reads(), &bh, &bn, &bst));
                     emit(bh, bn, bst, tot, 0, &query_names, seq_number_processed, store_names.empty() ? nullptr : &store_names);
                     processed += bst.sequences_searched;
                 });
@@ -416,7 +439,7 @@ int main(int argc, char **argv)
     fprintf(stderr, "Total time (s): %g\n", now_s() - t_total);
     // main/MhapMain.java:572-590
     const mhapb_stats &s = tot.st;
-    const double size = (double)mhapb_store_size(ctx);
+    const double size = (double)mhapb_multi_store_size(multi);
     fprintf(stderr, "Total matches found: %lld\n", (long long)s.matches_processed);
     fprintf(stderr, "Average number of matches per lookup: %g\n", (double)s.matches_processed / (double)s.sequences_searched);
     fprintf(stderr, "Average number of table elements processed per lookup: %g\n", (double)s.elements_processed / (double)s.sequences_searched);
@@ -424,6 +447,6 @@ int main(int argc, char **argv)
     fprintf(stderr, "Average %% of hashed sequences hit per lookup: %g\n", (double)s.sequences_hit / (size * (double)s.sequences_searched) * 100.0);
     fprintf(stderr, "Average %% of hashed sequences hit that are matches: %g\n", (double)s.matches_processed / (double)s.sequences_hit * 100.0);
     fprintf(stderr, "Average %% of hashed sequences fully compared that are matches: %g\n", (double)s.matches_processed / (double)s.fully_compared * 100.0);
-    mhapb_destroy(ctx);
+    mhapb_multi_destroy(multi);
     return 0;
 }

@@ -18,12 +18,18 @@ LIB_PATH = os.path.join(_HERE, "libmhap_b200.so")
 EXPORTS = [
     "mhapb_version", "mhapb_create", "mhapb_destroy", "mhapb_last_error", "mhapb_free", "mhapb_get_timing",
     "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_xorshift_peaks", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
-    "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads",
+    "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads", "mhapb_store_add_reads_device",
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_get_range", "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
     "mhapb_search_query_sketches", "mhapb_search_sketches_device", "mhapb_format_match", "mhapb_minhash_equal_count",
     "mhapb_store_reserve", "mhapb_sketch_reserve", "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
+    "mhapb_comm_unique_id", "mhapb_comm_init_rank", "mhapb_comm_init_all", "mhapb_comm_destroy", "mhapb_comm_info",
+    "mhapb_dist_search_self", "mhapb_dist_search_query_reads", "mhapb_dist_search_query_reads_device",
+    "mhapb_multi_create", "mhapb_multi_destroy", "mhapb_multi_last_error", "mhapb_multi_n_devices", "mhapb_multi_ctx",
+    "mhapb_multi_store_reset", "mhapb_multi_store_reserve", "mhapb_multi_store_add_reads", "mhapb_multi_store_add_sketches",
+    "mhapb_multi_store_size", "mhapb_multi_search_self", "mhapb_multi_search_query_reads", "mhapb_multi_search_query_sketches",
 ]
+COMM_ID_BYTES = 128
 
 
 class MhapError(RuntimeError):
@@ -74,7 +80,7 @@ class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("hash_dedup_ms", C.c_float), ("minhash_ms", C.c_float),
                 ("ordered_ms", C.c_float), ("index_ms", C.c_float), ("probe_ms", C.c_float), ("filter_ms", C.c_float),
                 ("kernel_launches", C.c_int64), ("xorshift_steps", C.c_int64), ("sketch_total_ms", C.c_float),
-                ("search_total_ms", C.c_float), ("kmers_hashed", C.c_int64)]
+                ("search_total_ms", C.c_float), ("kmers_hashed", C.c_int64), ("gather_ms", C.c_float), ("pad_", C.c_float)]
 
 
 _lib = None
@@ -108,6 +114,7 @@ def load():
     L.mhapb_dat_decode.argtypes = [vp, u64, i64, P(u32), P(i32), P(i32), P(i32), vp, vp, vp, vp, vp, vp, vp]
     L.mhapb_store_reset.argtypes = [vp, P(SketchParams)]
     L.mhapb_store_add_reads.argtypes = [vp, vp, vp, vp, u32, C.c_int, P(i64)]
+    L.mhapb_store_add_reads_device.argtypes = [vp, vp, vp, vp, u32, C.c_int, P(i64)]
     L.mhapb_store_add_sketches.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, u32]
     L.mhapb_store_add_sketches_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32]
     L.mhapb_store_size.argtypes = [vp]; L.mhapb_store_size.restype = i64
@@ -127,6 +134,27 @@ def load():
     L.mhapb_filter_set.argtypes = [vp, P(FilterParams), vp, vp, u64, vp, u64, i32]
     L.mhapb_filter_load_text.argtypes = [vp, P(FilterParams), C.c_char_p, u64, C.c_int, P(i64)]
     L.mhapb_filter_clear.argtypes = [vp]
+    L.mhapb_comm_unique_id.argtypes = [vp]
+    L.mhapb_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.mhapb_comm_init_all.argtypes = [P(vp), C.c_int]
+    L.mhapb_comm_destroy.argtypes = [vp]
+    L.mhapb_comm_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int)]
+    L.mhapb_dist_search_self.argtypes = [vp, P(SearchParams), P(vp), P(u64), P(Stats)]
+    L.mhapb_dist_search_query_reads.argtypes = [vp, P(SearchParams), vp, vp, vp, u32, P(vp), P(u64), P(Stats)]
+    L.mhapb_dist_search_query_reads_device.argtypes = [vp, P(SearchParams), vp, vp, vp, u32, P(vp), P(u64), P(Stats)]
+    L.mhapb_multi_create.argtypes = [P(C.c_int), C.c_int, P(vp)]
+    L.mhapb_multi_destroy.argtypes = [vp]; L.mhapb_multi_destroy.restype = None
+    L.mhapb_multi_last_error.argtypes = [vp]; L.mhapb_multi_last_error.restype = C.c_char_p
+    L.mhapb_multi_n_devices.argtypes = [vp]
+    L.mhapb_multi_ctx.argtypes = [vp, C.c_int]; L.mhapb_multi_ctx.restype = vp
+    L.mhapb_multi_store_reset.argtypes = [vp, P(SketchParams)]
+    L.mhapb_multi_store_reserve.argtypes = [vp, i64]
+    L.mhapb_multi_store_add_reads.argtypes = [vp, vp, vp, vp, u32, C.c_int, P(i64)]
+    L.mhapb_multi_store_add_sketches.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, u32]
+    L.mhapb_multi_store_size.argtypes = [vp]; L.mhapb_multi_store_size.restype = i64
+    L.mhapb_multi_search_self.argtypes = [vp, P(SearchParams), P(vp), P(u64), P(Stats)]
+    L.mhapb_multi_search_query_reads.argtypes = [vp, P(SearchParams), vp, vp, vp, u32, P(vp), P(u64), P(Stats)]
+    L.mhapb_multi_search_query_sketches.argtypes = [vp, P(SearchParams), vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, u32, P(vp), P(u64), P(Stats)]
     _lib = L
     return L
 
@@ -269,6 +297,14 @@ class Engine:
                                               int(both_strands), C.byref(added)))
         return added.value
 
+    def store_add_reads_device(self, d_bases: int, offsets, ids=None, both_strands=True) -> int:
+        """Reads already resident in HBM at device address d_bases (mhapb_store_add_reads_device)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        added = C.c_int64()
+        self._ck(self.L.mhapb_store_add_reads_device(self.h, d_bases, _ptr(offsets), _ptr(ids), offsets.size - 1, int(both_strands), C.byref(added)))
+        return added.value
+
     def store_add_sketches(self, ids, is_fwd, seq_len, seq_len_kmers, minhash, ord_hp, ord_n, ordered_kmer_size=12):
         ids = np.ascontiguousarray(ids, dtype=np.int64); is_fwd = np.ascontiguousarray(is_fwd, dtype=np.uint8)
         seq_len = np.ascontiguousarray(seq_len, dtype=np.int32); slk = np.ascontiguousarray(seq_len_kmers, dtype=np.int32)
@@ -360,10 +396,125 @@ class Engine:
                                                      d_minhash, d_ord, d_ord_n, ord_stride, ids.size, C.byref(out), C.byref(n), C.byref(st)))
         return self._collect(out, n, st)
 
+    # ---- multi-GPU: one context per rank, NCCL inside the library ----
+    def comm_init_rank(self, comm_id: bytes, rank: int, nranks: int):
+        """Join the job's communicator (collective).  comm_id = comm_unique_id() of rank 0, handed over by the launcher."""
+        assert len(comm_id) == COMM_ID_BYTES
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._ck(self.L.mhapb_comm_init_rank(self.h, buf, rank, nranks))
+
+    def comm_info(self):
+        r = C.c_int(); n = C.c_int(); v = C.c_int()
+        self._ck(self.L.mhapb_comm_info(self.h, C.byref(r), C.byref(n), C.byref(v)))
+        return r.value, n.value, v.value
+
+    def dist_search_self(self, sp: SearchParams):
+        """COLLECTIVE: hits whose target this rank stores + job-wide counters (mhapb_dist_search_self)."""
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        self._ck(self.L.mhapb_dist_search_self(self.h, C.byref(sp), C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
+    def dist_search_query_reads(self, sp: SearchParams, bases, offsets, ids=None):
+        """COLLECTIVE: this rank's shard of the query reads; all queries meet every store shard."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        b = bases if bases.size else np.zeros(1, dtype=np.uint8)
+        self._ck(self.L.mhapb_dist_search_query_reads(self.h, C.byref(sp), _ptr(b), _ptr(offsets), _ptr(ids), offsets.size - 1,
+                                                      C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
+    def dist_search_query_reads_device(self, sp: SearchParams, d_bases: int, offsets, ids=None):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        self._ck(self.L.mhapb_dist_search_query_reads_device(self.h, C.byref(sp), d_bases, _ptr(offsets), _ptr(ids), offsets.size - 1,
+                                                             C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
     def minhash_equal_count(self, i: int, j: int) -> int:
         out = C.c_int32()
         self._ck(self.L.mhapb_minhash_equal_count(self.h, i, j, C.byref(out)))
         return out.value
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it; the launcher distributes the bytes)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = load().mhapb_comm_unique_id(buf)
+    if rc:
+        raise MhapError(rc, (load().mhapb_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
+class MultiEngine:
+    """mhapb_multi: one process driving several GPUs (what a single JVM would bind)."""
+
+    def __init__(self, devices):
+        self.L = load()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.L.mhapb_multi_create(devs, len(devices), C.byref(h))
+        if rc:
+            raise MhapError(rc, (self.L.mhapb_last_error(None) or b"").decode())
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mhapb_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise MhapError(rc, (self.L.mhapb_multi_last_error(self.h) or b"").decode())
+        return rc
+
+    def store_reset(self, params: SketchParams):
+        self._ck(self.L.mhapb_multi_store_reset(self.h, C.byref(params)))
+
+    def store_add_reads(self, bases, offsets, ids=None, both_strands=True) -> int:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        added = C.c_int64()
+        b = bases if bases.size else np.zeros(1, dtype=np.uint8)
+        self._ck(self.L.mhapb_multi_store_add_reads(self.h, _ptr(b), _ptr(offsets), _ptr(ids), offsets.size - 1, int(both_strands), C.byref(added)))
+        return added.value
+
+    def store_size(self) -> int:
+        return int(self.L.mhapb_multi_store_size(self.h))
+
+    def _collect(self, out, n, st):
+        if n.value:
+            raw = (C.c_char * (n.value * C.sizeof(Hit))).from_address(out.value)
+            hits = np.frombuffer(raw, dtype=HIT_DTYPE).copy()
+        else:
+            hits = np.zeros(0, dtype=HIT_DTYPE)
+        self.L.mhapb_free(out)
+        return hits, {f: int(getattr(st, f)) for f, _ in Stats._fields_}
+
+    def search_self(self, sp: SearchParams):
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        self._ck(self.L.mhapb_multi_search_self(self.h, C.byref(sp), C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
+
+    def search_query_reads(self, sp: SearchParams, bases, offsets, ids=None):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        out = C.c_void_p(); n = C.c_uint64(); st = Stats()
+        b = bases if bases.size else np.zeros(1, dtype=np.uint8)
+        self._ck(self.L.mhapb_multi_search_query_reads(self.h, C.byref(sp), _ptr(b), _ptr(offsets), _ptr(ids), offsets.size - 1,
+                                                       C.byref(out), C.byref(n), C.byref(st)))
+        return self._collect(out, n, st)
 
 
 def format_match(hit_row) -> str:

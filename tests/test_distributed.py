@@ -1,6 +1,8 @@
-"""CPU suite, part 3: the multi-GPU host logic (shard plan, padded all-gather of sketch blocks, per-rank
-query ranges, counter all-reduce) with world_size 2 and 3 over gloo.  The compute behind the backend
-protocol is the oracle here (tests may use it); on GPUs the same code runs GpuBackend over NCCL."""
+"""CPU suite, part 3: the multi-GPU host logic with world_size 2 and 3 over gloo -- shard plan, communicator bootstrap
+(rank 0's 128-byte id reaches every rank), the sharded self / store-vs-query plan reproducing the single-process result,
+disjoint per-rank hit sets, merged hits and digests.  The compute behind the backend protocol is the oracle here
+(tests/dist_standin.py); on GPUs the same callers run GpuBackend, whose exchange + search is one library call over NCCL
+(tests/test_gpu_multirank.py checks that path on hardware)."""
 import os
 import socket
 
@@ -10,58 +12,19 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mhap_b200.distributed import SketchBlock, all_gather_blocks, shard_range, sharded_query_overlap, sharded_self_overlap
+from mhap_b200 import native
+from mhap_b200.distributed import bootstrap_comm, gather_hits, hits_digest, shard_range, sharded_query_overlap, sharded_self_overlap
 from oracle import oracle as orc
+from tests.dist_standin import OracleBackend, SketchBlock, all_gather_blocks
 
 H, S = 64, 200
 
 
-class OracleBackend:
-    """Oracle stand-in for GpuBackend: the local shard is stored and indexed, every rank's sketches query it."""
+class FakeEngine:
+    """Records what bootstrap_comm hands to mhapb_comm_init_rank (no GPU in this container)."""
 
-    def __init__(self):
-        self.store = None
-
-    def store_shard(self, bases, offsets, ids, build_index=True):
-        st = orc.Store(num_hashes=H, ordered_size=S)
-        st.add_reads(bases, offsets, ids=ids)
-        self.store = st
-        self.indexed = build_index
-        return self._block(st)
-
-    def index_build(self):
-        self.indexed = True
-
-    def sketch_queries(self, bases, offsets, ids):
-        qs = orc.Store(num_hashes=H, ordered_size=S)
-        qs.add_reads(bases, offsets, ids=ids, both_strands=False)
-        return self._block(qs)
-
-    @staticmethod
-    def _block(st):
-        rows = [st.get(i) for i in range(len(st))]
-        n = len(rows)
-        od = np.zeros((n, S, 2), np.int32)
-        for i, r in enumerate(rows):
-            od[i, :r["ord"].shape[0]] = r["ord"]
-        t = torch.from_numpy
-        return SketchBlock(ids=t(np.array([r["id"] for r in rows], np.int64)), is_fwd=t(np.array([r["is_fwd"] for r in rows], np.uint8)),
-                           seq_len=t(np.array([r["seq_len"] for r in rows], np.int32)),
-                           seq_len_kmers=t(np.array([r["seq_len_kmers"] for r in rows], np.int32)),
-                           ord_n=t(np.array([r["ord"].shape[0] for r in rows], np.int32)),
-                           minhash=t(np.stack([r["minhash"] for r in rows]) if n else np.zeros((0, H), np.int32)), ord=t(od))
-
-    def search_all(self, g, to_self=True):
-        assert self.indexed, "search before the index build"
-        qs = orc.Store(num_hashes=H, ordered_size=S)
-        for i in range(g.n):
-            qs.add_sketch(int(g.ids[i]), bool(g.is_fwd[i]), int(g.seq_len[i]), g.minhash[i].numpy(), int(g.seq_len_kmers[i]),
-                          g.ord[i, :int(g.ord_n[i])].numpy())
-        if len(self.store) == 0:
-            return np.zeros(0, orc.HIT_DTYPE), dict(elements_processed=0, sequences_hit=0, fully_compared=0, matches_processed=0,
-                                                   sequences_searched=int(g.is_fwd.sum()))
-        r = self.store.search_query(qs, keep_all=True, to_self=to_self)
-        return r.hits, r.stats
+    def comm_init_rank(self, comm_id, rank, nranks):
+        self.joined = (bytes(comm_id), rank, nranks)
 
 
 def _reads(n, L, seed, genome_seed=None):
@@ -91,7 +54,13 @@ def _worker(rank, world, port, n_reads, q):
     first, cnt = shard_range(n_reads, rank, world)
     bases, offs = orc.pack_reads(reads[first:first + cnt])
     ids = np.arange(first + 1, first + cnt + 1, dtype=np.int64)
-    hits, stats, info = sharded_self_overlap(OracleBackend(), bases, offs, ids, dist)
+    eng = FakeEngine()
+    assert bootstrap_comm(eng, dist, make_id=lambda: bytes(range(128))) == (rank, world)
+    assert eng.joined == (bytes(range(128)), rank, world)        # rank 0's id reached every rank
+    be = OracleBackend(H, S, dist)
+    hits, stats = sharded_self_overlap(be, bases, offs, ids, dist)
+    merged = gather_hits(hits, dist)
+    info = dict(be.info, digest=hits_digest(merged) if rank == 0 else None, n_merged=len(merged) if rank == 0 else None)
     q.put((rank, sorted(_key(h) for h in hits), stats, info))
     dist.barrier()
     dist.destroy_process_group()
@@ -107,8 +76,9 @@ def _worker_query(rank, world, port, n_store, n_query, q):
     f2, c2 = shard_range(n_query, rank, world)
     qb, qo = orc.pack_reads(query[f2:f2 + c2])
     qids = np.arange(f2 + 1, f2 + c2 + 1, dtype=np.int64) + n_store      # main/MhapMain.java:537 id offset of the query file
-    hits, stats, info = sharded_query_overlap(OracleBackend(), (sb, so, sids), (qb, qo, qids), dist)
-    q.put((rank, sorted(_key(h) for h in hits), stats, info))
+    be = OracleBackend(H, S, dist)
+    hits, stats = sharded_query_overlap(be, (sb, so, sids), (qb, qo, qids), dist)
+    q.put((rank, sorted(_key(h) for h in hits), stats, be.info))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -126,6 +96,7 @@ def test_sharded_self_overlap_equals_single_process(world):
     st.add_reads(*orc.pack_reads(reads))
     ref = st.search_self(keep_all=True)
     assert len(ref.hits) > 20
+    n_fwd = sum(1 for i in range(len(st)) if st.get(i)["is_fwd"])
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -141,7 +112,9 @@ def test_sharded_self_overlap_equals_single_process(world):
     assert all_hits == sorted(_key(h) for h in ref.hits)
     for rank, hits, stats, info in res:
         assert stats == ref.stats                      # all-reduced, job-wide counters on every rank
-        assert info["n_store"] == len(st) and sum(info["counts"]) == len(st)
+        assert info["n_queries"] == n_fwd and sum(info["counts"]) == n_fwd      # only forward sketches travel
+        if rank == 0:
+            assert info["n_merged"] == len(ref.hits) and info["digest"] == hits_digest(ref.hits)
     # hit lists are disjoint by target (toId)
     owners = {}
     for rank, hits, _, _ in res:
@@ -175,7 +148,7 @@ def test_sharded_store_vs_query_equals_single_process(world):
     assert sorted(k for _, hits, _, _ in res for k in hits) == sorted(_key(h) for h in ref.hits)
     for rank, hits, stats, info in res:
         assert stats == ref.stats
-        assert info["n_queries"] == len(qs) and sum(info["query_counts"]) == len(qs)
+        assert info["n_queries"] == len(qs) and sum(info["counts"]) == len(qs)
 
 
 def test_shard_range_covers_everything():
@@ -192,3 +165,19 @@ def test_all_gather_blocks_single_process_is_identity():
                     minhash=torch.zeros((3, 4), dtype=torch.int32), ord=torch.zeros((3, 5, 2), dtype=torch.int32))
     g, counts = all_gather_blocks(b, None)
     assert g is b and counts == [3]
+
+
+def test_bootstrap_without_process_group_is_single_rank():
+    assert bootstrap_comm(FakeEngine(), None) == (0, 1)
+
+
+def test_hits_digest_is_order_independent():
+    rng = np.random.default_rng(1)
+    h = np.zeros(50, dtype=native.HIT_DTYPE)
+    for f in ("from_id", "to_id", "a1", "a2", "b1", "b2", "hit_count"):
+        h[f] = rng.integers(0, 1000, 50)
+    h["score"] = rng.random(50)
+    d = hits_digest(h)
+    assert hits_digest(h[rng.permutation(50)]) == d
+    h2 = h.copy(); h2["a1"][7] += 1
+    assert hits_digest(h2) != d
