@@ -82,7 +82,7 @@ int filter_unweighted(const KmerFilterView &v, int unweighted) { return v.mode =
 // slot_valid (optional, size n_reads*per): set to 0 for strands whose every k-mer was filtered out.
 int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_bases, const uint64_t *h_offsets,
                 uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
-                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid)
+                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid, const char *h_bases)
 {
     const KmerFilterView flt = filter_view(ctx);
     if (ctx->filter_set && (ctx->filter_params.repeat_weight < 0.0) != (p.unweighted != 0))
@@ -116,6 +116,9 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
 
     size_t pos = 0;
     std::vector<StrandDesc> chunk;
+    std::vector<cudaEvent_t> hevs;
+    uint64_t copied_hi = 0;
+    if (h_bases) CU(ctx, cudaStreamSynchronize(ctx->stream2));   // the previous call's copies are long done; keeps the stream's order simple
     while (pos < all.size()) {
         uint64_t tot = 0;
         chunk.clear();
@@ -160,6 +163,20 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         }
         CU(ctx, cudaMemcpyAsync(ctx->desc.p, chunk.data(), (size_t)n * sizeof(StrandDesc), cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
+        if (h_bases) {   // this chunk's characters: H2D on the copy stream, K1a waits for it; the next chunk's copy overlaps this chunk's K1
+            uint64_t lo = ~0ull, hi = 0;
+            for (int i = 0; i < n; i++) { lo = std::min<uint64_t>(lo, chunk[i].base_off); hi = std::max<uint64_t>(hi, chunk[i].base_off + chunk[i].len); }
+            lo = std::max(lo, copied_hi);           // a read whose two strands straddle two chunks was copied with the first
+            if (hi > lo) {
+                cudaEvent_t h0, h1; cudaEventCreate(&h0); cudaEventCreate(&h1);
+                cudaEventRecord(h0, ctx->stream2);
+                CU(ctx, cudaMemcpyAsync(const_cast<uint8_t *>(d_bases) + lo, h_bases + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream2));
+                cudaEventRecord(h1, ctx->stream2);
+                CU(ctx, cudaStreamWaitEvent(ctx->stream, h1, 0));
+                hevs.push_back(h0); hevs.push_back(h1);
+                copied_hi = hi;
+            }
+        }
         SketchScratch sc;
         sc.keys = ctx->keys.as<uint64_t>(); sc.wts = ctx->wts.as<uint32_t>();
         sc.nlight = ctx->nlight.as<int32_t>(); sc.nheavy = ctx->nheavy.as<int32_t>();
@@ -210,6 +227,8 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         float c = 0; cudaEventElapsedTime(&c, cevs[i], cevs[i + 1]); ctx->timing.ordered_ms += c;
     }
     for (auto e : cevs) cudaEventDestroy(e);
+    for (size_t i = 0; i + 1 < hevs.size(); i += 2) { float c = 0; cudaEventElapsedTime(&c, hevs[i], hevs[i + 1]); ctx->timing.h2d_ms += c; }
+    for (auto e : hevs) cudaEventDestroy(e);
     if (evs.size() >= 2) { float t = 0; cudaEventElapsedTime(&t, evs.front(), evs.back()); ctx->timing.sketch_total_ms += t; }
     for (auto e : evs) cudaEventDestroy(e);
     ctx->timing.kernel_launches += launches;
@@ -237,7 +256,7 @@ int store_configure(mhapb_ctx *ctx, const mhapb_sketch_params *p)
     if (rc) return rc;
     Store &s = ctx->store;
     s.p = *p; s.configured = true; s.n = 0; s.ord_stride = p->ordered_sketch_size; s.indexed = false;
-    s.h_id.clear(); s.h_fwd.clear(); s.h_len.clear(); s.h_lenk.clear(); s.h_ordn.clear(); s.seen.clear(); s.fwd_list_valid = false;
+    s.h_id.clear(); s.h_fwd.clear(); s.h_len.clear(); s.h_lenk.clear(); s.h_ordn.clear(); s.seen.clear(); s.ids_monotonic = true; s.any_key = false; s.last_key = 0; s.fwd_list_valid = false;
     return MHAPB_OK;
 }
 
@@ -271,8 +290,17 @@ int store_sync_columns(mhapb_ctx *ctx, int64_t from)
 int store_push_meta(mhapb_ctx *ctx, int64_t id, int fwd, int32_t len, int32_t lenk, int32_t ordn)
 {
     Store &s = ctx->store;
-    uint64_t key = ((uint64_t)id << 1) | (uint64_t)(fwd ? 1 : 0);
-    if (!s.seen.insert(key).second) return fail(ctx, MHAPB_EDUPID, "Sequence ID already exists in the hash table.");
+    // order: (id, forward) before (id, reverse) before (id+1, forward), as the streamer produces them
+    const uint64_t key = (((uint64_t)id ^ 0x8000000000000000ull) << 1) | (uint64_t)(fwd ? 0 : 1);
+    if (s.ids_monotonic) {
+        if (!s.any_key || key > s.last_key) { s.last_key = key; s.any_key = true; }
+        else {   // out of order: fall back to the set, built once from what is stored
+            s.ids_monotonic = false;
+            s.seen.clear();
+            for (size_t i = 0; i < s.h_id.size(); i++) s.seen.insert((((uint64_t)s.h_id[i] ^ 0x8000000000000000ull) << 1) | (uint64_t)(s.h_fwd[i] ? 0 : 1));
+        }
+    }
+    if (!s.ids_monotonic && !s.seen.insert(key).second) return fail(ctx, MHAPB_EDUPID, "Sequence ID already exists in the hash table.");
     s.h_id.push_back(id); s.h_fwd.push_back((uint8_t)(fwd ? 1 : 0)); s.h_len.push_back(len); s.h_lenk.push_back(lenk); s.h_ordn.push_back(ordn);
     return MHAPB_OK;
 }
@@ -280,8 +308,12 @@ int store_push_meta(mhapb_ctx *ctx, int64_t id, int fwd, int32_t len, int32_t le
 // drop the host columns pushed since meta0 (an add that failed after store_push_meta must leave the store as it was)
 void store_rollback_meta(Store &s, size_t meta0)
 {
-    for (size_t i = meta0; i < s.h_id.size(); i++) s.seen.erase(((uint64_t)s.h_id[i] << 1) | s.h_fwd[i]);
+    if (!s.ids_monotonic) for (size_t i = meta0; i < s.h_id.size(); i++) s.seen.erase((((uint64_t)s.h_id[i] ^ 0x8000000000000000ull) << 1) | (uint64_t)(s.h_fwd[i] ? 0 : 1));
     s.h_id.resize(meta0); s.h_fwd.resize(meta0); s.h_len.resize(meta0); s.h_lenk.resize(meta0); s.h_ordn.resize(meta0);
+    if (s.ids_monotonic) {
+        s.any_key = meta0 > 0;
+        if (meta0 > 0) s.last_key = (((uint64_t)s.h_id[meta0 - 1] ^ 0x8000000000000000ull) << 1) | (uint64_t)(s.h_fwd[meta0 - 1] ? 0 : 1);
+    }
 }
 
 int index_build(mhapb_ctx *ctx)
@@ -538,13 +570,14 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
     auto device_part = [&]() -> int {
         int rc = store_reserve(ctx, added);
         if (rc) return rc;
-        if (!bases_on_device) rc = h2d_bases(ctx, bases, offsets, n_reads);
-        if (rc) return rc;
+        const bool stream_h2d = !bases_on_device;      // copy chunk by chunk under K1 instead of all reads up front
+        if (stream_h2d) CU(ctx, ctx->bases.ensure((size_t)offsets[n_reads] + 64));
         const size_t S = (size_t)s.ord_stride;
         CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)added * S * 8, ctx->stream));
-        rc = sketch_core(ctx, s.p, dev_bases(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>());
+        rc = sketch_core(ctx, s.p, dev_bases(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>(),
+                         nullptr, stream_h2d ? bases : nullptr);
         if (rc) return rc;
-        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.h2d_ms += ms;
+        if (!stream_h2d && !d_resident) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.h2d_ms += ms; }
         s.n = next;
         s.indexed = false; s.fwd_list_valid = false;
         rc = store_sync_columns(ctx, n0);

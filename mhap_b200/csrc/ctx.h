@@ -70,6 +70,10 @@ struct Store {
     int ord_stride = 0;
     DevBuf minhash, ord, ord_n, lenk, len, id;
     std::vector<int64_t> h_id; std::vector<uint8_t> h_fwd; std::vector<int32_t> h_len, h_lenk, h_ordn;
+    // duplicate-id detection ("Sequence ID already exists in the hash table.", MinHashSearch.java:112-117).  FASTA ids arrive
+    // in increasing order, so the common case is one compare per sketch; the hash set is only materialised when an id
+    // arrives out of order (200 k set inserts cost 10+ ms of host time in front of every K1 launch).
+    bool ids_monotonic = true; uint64_t last_key = 0; bool any_key = false;
     std::unordered_set<uint64_t> seen;
     // device list of the forward rows (the queries of a self search), rebuilt when the store changes
     DevBuf fwd_list; int64_t fwd_list_n = 0; bool fwd_list_valid = false;
@@ -139,7 +143,9 @@ void reset_sketch_timing(mhapb_ctx *ctx);
 int h2d_bases(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets, uint32_t n_reads);
 int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_bases, const uint64_t *h_offsets,
                 uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
-                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid = nullptr);
+                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid = nullptr,
+                const char *h_bases = nullptr /* host copy of the reads: each chunk's characters are copied to d_bases (= ctx->bases) on the
+                                                 second stream right before its K1a, so the H2D of chunk i+1 runs under K1 of chunk i */);
 int index_build(mhapb_ctx *ctx);
 int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q, int to_self,
                 mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);

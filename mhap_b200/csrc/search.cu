@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t slot_hash(uint32_t value, int log2capw)
 // the CAS / add traffic never goes to DRAM.  (The first version walked the rows linearly, word innermost: consecutive threads
 // hit 512 different sub-tables -- 2 GB of working set, one DRAM sector per atomic; ncu: 31-38 % of DRAM throughput for 8-byte slots.)
 constexpr int kIdxGroup = 8;          // words per group
-constexpr int kIdxTileRows = 2048;    // sketches per tile
+constexpr int kIdxTileRows = 256;     // sketches per tile (small: the CTAs resident at one moment span one or two word groups)
 
 __device__ __forceinline__ bool index_tile(int64_t tile, int64_t tiles_per_group, int64_t n_store, int H, int *w0, int *nw, int64_t *r0, int64_t *r1)
 {
@@ -190,7 +190,7 @@ cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = sms * 8;
     const int64_t n_tiles = ((n_store + kIdxTileRows - 1) / kIdxTileRows) * ((H + kIdxGroup - 1) / kIdxGroup);
-    const int tgrid = (int)std::min<int64_t>(n_tiles, (int64_t)sms * 8);
+    const int tgrid = (int)std::min<int64_t>(n_tiles, 1 << 30);   // one tile per CTA, in tile order: short-lived CTAs also let the collectives' kernels in
     k_index_count<<<tgrid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw);
     const size_t nb = (nslots + kScanTile - 1) / kScanTile;
     k_scan_tiles<<<(unsigned)nb, kScanThreads, 0, st>>>(iv.slots, nslots, d_block_sums);
@@ -594,7 +594,12 @@ __device__ __forceinline__ int fw_lower_bound(const int2 *__restrict__ s, int n,
 }
 
 // the reference loop (sketch/BottomOverlapSketch.java:428-515) on A[i1..e1) x B[i2..e2): returns the number of match
-// records and stores the first `cap` of them in out
+// records and stores the first `cap` of them in out.
+// A step is straight-line: both window tests are one unsigned compare each, "advance A" / "advance B" are predicates and
+// the element that moved is reloaded under its predicate (A / Bs are plain register pointers, so the reload is one
+// IMAD.WIDE + one LDG; the first version re-derived the row address from the constant bank with five instructions per
+// load and branched around it -- 40 instructions per step).  [Keeping the next element of each side in flight one step
+// ahead was measured slower: 19.2 vs 14.9 ms, 72 registers and twice the loads.]
 __device__ __forceinline__ int fw_merge_range(const int2 *__restrict__ A, int i1, const int e1, const int2 *__restrict__ Bs, int i2, const int e2,
                                               const FwWindow &w, int2 *out, const int cap)
 {
@@ -721,6 +726,7 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
         const int32_t len1 = a.q_lenk[c.q], len2 = a.t_lenk[c.t];
         const int2 *A = reinterpret_cast<const int2 *>(a.q_ord) + (size_t)c.q * a.q_stride;
         const int2 *Bs = reinterpret_cast<const int2 *>(a.t_ord) + (size_t)c.t * a.t_stride;
+        asm volatile("" : "+l"(A), "+l"(Bs));   // keep the two row addresses in registers: element i is then one IMAD.WIDE away
         __syncwarp();
         OverlapOut o; o.a1 = o.a2 = o.b1 = o.b2 = o.valid = o.inter = o.kmin = 0; o.empty = 1;
         bool overflow = false;

@@ -39,11 +39,25 @@ struct CharsGlobal {
 
 __device__ __forceinline__ void stage_chars(uint8_t *dst, const uint8_t *g, uint32_t len, uint32_t rc)
 {
-    // coalesced byte loads; a 10 kbp read is 10 KB, this is noise next to K1b
-    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
-        uint8_t c = upper_char(__ldg(g + i));
-        if (rc) dst[len - 1 - i] = complement_char(c);
-        else dst[i] = c;
+    // 16-byte loads from the aligned window around the read (its first byte sits anywhere in the batch), one byte store per
+    // character with FastaData's upper-casing and, for the reverse strand, Utils.rc applied on the way.  The byte-wise
+    // version showed up with 25 % of K1c's stall samples (profiles/r2c): a CTA stages one strand at a time and waits for it.
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)15;
+    const int head = (int)(reinterpret_cast<uintptr_t>(g) - a0);
+    const uint4 *src = reinterpret_cast<const uint4 *>(a0);
+    const int nvec = (head + (int)len + 15) >> 4;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        const uint4 q = __ldg(src + v);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const int i = v * 16 + b - head;
+            if (i >= 0 && i < (int)len) {
+                const uint8_t c = upper_char((uint8_t)(w[b >> 2] >> ((b & 3) * 8)));
+                if (rc) dst[len - 1 - i] = complement_char(c);
+                else dst[i] = c;
+            }
+        }
     }
 }
 
@@ -794,6 +808,9 @@ k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, S
 // (hash biased to unsigned order << 32 | position) -- which is exactly "ascending signed hash,
 // ties by ascending position" of fastutil's stable radixSortIndirect -- then bitonic-sort the
 // S survivors in shared memory.
+constexpr int kOrdBinBits = 11, kOrdBins = 1 << kOrdBinBits;   // buckets of the select/sort histogram (top bits of the hash)
+constexpr int kOrdMaxBin = 64;                                  // a fuller bucket among the selected ones -> generic path
+
 template <bool LONG, int KC /* compile-time ordered k, 0 = runtime */>
 __global__ void __launch_bounds__(512)
 k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc, int s_begin, int s_end, int ok, int S,
@@ -803,13 +820,19 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int s_strand, s_nsel;
     __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_digit, s_before, s_bin;
+    __shared__ uint32_t s_digit, s_before, s_bin, s_bstar, s_maxbin, s_nbl, s_wsum[16];
+    __shared__ uint64_t s_T, s_bl[kOrdMaxBin];
 
     uint64_t *sel = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *oh;
+    uint32_t *hist2k = nullptr;
     uint8_t *chars = nullptr;
     if (LONG) oh = sc.ohash + (size_t)blockIdx.x * len_cap;
-    else { oh = reinterpret_cast<uint32_t *>(smem_raw + (size_t)sel_cap * 8); chars = smem_raw + (size_t)sel_cap * 8 + (size_t)len_cap * 4; }
+    else {
+        hist2k = reinterpret_cast<uint32_t *>(smem_raw + (size_t)sel_cap * 8);
+        oh = hist2k + kOrdBins;
+        chars = reinterpret_cast<uint8_t *>(oh + len_cap);
+    }
 
     for (;;) {
         if (threadIdx.x == 0) { s_strand = s_begin + (int)atomicAdd(queue, 1u); s_nsel = 0; }
@@ -868,6 +891,93 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
         __syncthreads();
 
         const int nsel = min(S, no);
+        bool generic = LONG;
+        if constexpr (!LONG) {
+            // ---- bucket select + bucket sort (the common case) -------------------------------------------------------
+            // ONE histogram over the top 11 bits of the (order-biased) hash serves both steps: its running sum locates the
+            // bucket b* in which the S-th smallest key falls (everything below is selected, b* itself is split exactly by
+            // ranking its few keys), and the same running sum is where each bucket starts in the sorted output, so the
+            // selected keys are scattered straight to their bucket and every bucket (2-5 keys for a 10 kbp strand) is
+            // finished by one thread with an insertion sort.  This replaced an 8-bit radix select (2-3 passes over all
+            // hashes) + compaction + a 66-stage bitonic sort of 2048 keys, which was 36 % of the kernel's instructions.
+            // Degenerate strands (low complexity: hundreds of equal hashes in one bucket) take the generic path below.
+            uint32_t *cur = hist2k;
+            for (int i = threadIdx.x; i < kOrdBins; i += blockDim.x) cur[i] = 0;
+            if (threadIdx.x == 0) { s_bstar = kOrdBins; s_before = 0; s_bin = 0; s_maxbin = 0; s_nbl = 0; }
+            __syncthreads();
+            for (int i = threadIdx.x; i < no; i += blockDim.x) atomicAdd(&cur[oh[i] >> (32 - kOrdBinBits)], 1u);
+            __syncthreads();
+            {   // exclusive scan over the buckets, kOrdBins / blockDim.x per thread
+                constexpr int PER = kOrdBins / 512;
+                uint32_t c[PER], sum = 0;
+#pragma unroll
+                for (int q = 0; q < PER; q++) { c[q] = cur[threadIdx.x * PER + q]; sum += c[q]; }
+                uint32_t incl = sum;
+                const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+                if (lane == 31) s_wsum[wid] = incl;
+                __syncthreads();
+                if (wid == 0) {
+                    uint32_t x = lane < 16 ? s_wsum[lane] : 0, xi = x;
+#pragma unroll
+                    for (int o = 1; o < 16; o <<= 1) { uint32_t v = __shfl_up_sync(kFull, xi, o); if (lane >= o) xi += v; }
+                    if (lane < 16) s_wsum[lane] = xi - x;
+                }
+                __syncthreads();
+                uint32_t run = incl - sum + s_wsum[wid];
+                uint32_t mx = 0;
+#pragma unroll
+                for (int q = 0; q < PER; q++) {
+                    const uint32_t before = run;
+                    run += c[q];
+                    cur[threadIdx.x * PER + q] = before;                               // bucket start = scatter cursor
+                    if (before < (uint32_t)nsel) mx = max(mx, c[q]);                    // buckets that receive selected keys
+                    if (before < (uint32_t)nsel && (uint32_t)nsel <= run && no > nsel) { s_bstar = threadIdx.x * PER + q; s_before = before; s_bin = c[q]; }
+                }
+                if (mx > kOrdMaxBin) atomicMax(&s_maxbin, mx);
+            }
+            __syncthreads();
+            const uint32_t bstar = s_bstar;
+            generic = s_maxbin > kOrdMaxBin;
+            uint64_t Tb = ~0ull;                    // keys of bucket b* are selected iff <= Tb
+            if (!generic && bstar < (uint32_t)kOrdBins && s_bin > (uint32_t)nsel - s_before) {
+                // split b* exactly: its keys (<= kOrdMaxBin of them), ranked by (hash, position)
+                for (int i = threadIdx.x; i < no; i += blockDim.x)
+                    if ((oh[i] >> (32 - kOrdBinBits)) == bstar) { const uint32_t p = atomicAdd(&s_nbl, 1u); s_bl[p] = ((uint64_t)oh[i] << 32) | (uint32_t)i; }
+                __syncthreads();
+                const uint32_t nb_ = s_nbl, need = (uint32_t)nsel - s_before;
+                if (threadIdx.x < nb_) {
+                    const uint64_t me = s_bl[threadIdx.x];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < nb_; j++) rank += s_bl[j] < me;
+                    if (rank == need - 1) s_T = me;
+                }
+                __syncthreads();
+                Tb = s_T;
+            }
+            if (!generic) {
+                for (int i = threadIdx.x; i < no; i += blockDim.x) {
+                    const uint32_t h = oh[i], bin = h >> (32 - kOrdBinBits);
+                    const uint64_t key = ((uint64_t)h << 32) | (uint32_t)i;
+                    if (bin < bstar || (bin == bstar && key <= Tb)) sel[atomicAdd(&cur[bin], 1u)] = key;
+                }
+                __syncthreads();
+                // cur[b] is now the END of bucket b (b <= b*), its start the end of the bucket before
+                const uint32_t last = min(bstar, (uint32_t)kOrdBins - 1);
+                for (uint32_t bkt = threadIdx.x; bkt <= last; bkt += blockDim.x) {
+                    const uint32_t beg = bkt ? cur[bkt - 1] : 0u, end = min(cur[bkt], (uint32_t)nsel);
+                    for (uint32_t x = beg + 1; x < end; x++) {
+                        const uint64_t v = sel[x];
+                        uint32_t y = x;
+                        while (y > beg && sel[y - 1] > v) { sel[y] = sel[y - 1]; y--; }
+                        sel[y] = v;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (generic) {
         uint64_t T = ~0ull;   // select keys <= T
         if (no > S) {
             uint64_t prefix = 0, mask = 0;
@@ -933,6 +1043,7 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
                 }
                 __syncthreads();
             }
+        }
         }
         int2 *row = reinterpret_cast<int2 *>(ord) + (size_t)d.row * ord_stride;
         for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
@@ -1140,11 +1251,14 @@ cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const Strand
     if (first_long > 0) {
         uint32_t len_cap = (uint32_t)align16((size_t)max_len_short + 16);
         // a short read may have fewer ordered k-mers than S, but never more than len_cap
-        size_t smem = (size_t)sel_cap * 8 + (size_t)len_cap * 4 + len_cap;
+        size_t smem = (size_t)sel_cap * 8 + (size_t)kOrdBins * 4 + (size_t)len_cap * 4 + len_cap;
         auto kern = ok == 12 ? k_ordered<false, 12> : k_ordered<false, 0>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int per_sm = smem <= 100 * 1024 ? 2 : 1;
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
         if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
         int grid = sm_count() * per_sm;
         if (grid > first_long) grid = first_long;

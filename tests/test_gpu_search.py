@@ -203,13 +203,20 @@ def test_gpu_backend_sharded_paths_single_rank():
     ost.add_reads(sb, so, ids=sids, threads=4)
     oq = orc.Store(num_hashes=128, ordered_size=400)
     oq.add_reads(qb, qo, ids=qids, both_strands=False, threads=4)
-    hits, stats, info = sharded_query_overlap(be, (sb, so, sids), (qb, qo, qids))
+    hits, stats = sharded_query_overlap(be, (sb, so, sids), (qb, qo, qids))
     res = ost.search_query(oq, keep_all=True, threads=4)
-    assert info["n_queries"] == len(oq) == 119
+    assert stats["sequences_searched"] == len(oq) == 119
     assert_same_hits(hits, res.hits, stats, res.stats)
     assert len(hits) > 50
-    hits, stats, info = sharded_self_overlap(be, sb, so, sids)
+    hits, stats = sharded_self_overlap(be, sb, so, sids)
     res = ost.search_self(keep_all=True, threads=4)
+    assert_same_hits(hits, res.hits, stats, res.stats)
+    # the collective entry points on a context without a communicator = a job of one rank (same path, no collectives)
+    e = engine()
+    hits, stats = e.dist_search_self(sp)
+    assert_same_hits(hits, res.hits, stats, res.stats)
+    hits, stats = e.dist_search_query_reads(sp, qb, qo, qids)
+    res = ost.search_query(oq, keep_all=True, threads=4)
     assert_same_hits(hits, res.hits, stats, res.stats)
 
 
