@@ -253,6 +253,8 @@ int64_t mhapb_store_size(mhapb_ctx *ctx);                          /* AbstractMa
 /* Copy stored sketch idx back to the host (getStoredSequenceHash, AbstractMatchSearch.java:314). */
 int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, int32_t *seq_len,
                     int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n);
+/* The parameters the store was configured with (mhapb_store_reset; ordered_kmer_size may come from a .dat store). */
+int mhapb_store_params(mhapb_ctx *ctx, mhapb_sketch_params *out);
 /* Bulk form: stored sketches [first, first+count) into flat host arrays (minhash [count][H], ord [count][ord_stride][2]
  * with ord_stride from mhapb_store_device_ptrs, rows zero-padded past ord_n).  Any pointer may be NULL. */
 int mhapb_store_get_range(mhapb_ctx *ctx, int64_t first, int64_t count, int64_t *ids, uint8_t *is_fwd, int32_t *seq_len,

@@ -1104,6 +1104,15 @@ int mhapb_store_get(mhapb_ctx *ctx, int64_t idx, int64_t *id, int32_t *is_fwd, i
     return MHAPB_OK;
 }
 
+int mhapb_store_params(mhapb_ctx *ctx, mhapb_sketch_params *out)
+{
+    if (!ctx || !out) return MHAPB_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->store.configured) return fail(ctx, MHAPB_ESTATE, "mhapb_store_reset must be called first");
+    *out = ctx->store.p;
+    return MHAPB_OK;
+}
+
 int mhapb_store_get_range(mhapb_ctx *ctx, int64_t first, int64_t count, int64_t *ids, uint8_t *is_fwd, int32_t *seq_len,
                           int32_t *seq_len_kmers, int32_t *minhash, int32_t *ord_hash_pos, int32_t *ord_n)
 {

@@ -53,6 +53,9 @@ NcclApi *nccl_api()
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // NCCL writes its banner / debug lines to stdout unless told otherwise; stdout is the overlap stream of the
+        // command-line driver (MatchResult lines), so they go to stderr unless the user chose a file
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
         const char *names[] = {getenv("MHAPB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char *n : names) {
             if (!n || !*n) continue;

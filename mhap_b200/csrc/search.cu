@@ -722,6 +722,15 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
 
     for (uint64_t ci = warp_id; ci < n_cand; ci += n_warps) {
         const Candidate c = a.cand[ci];
+        if (ci + n_warps < n_cand) {
+            // pull the NEXT pair's two sketches towards L2 while this pair is merged: the merges are chains of dependent
+            // loads, and with the queries in a gathered block of several GB (multi-GPU) most of them missed L2
+            const Candidate cn = a.cand[ci + n_warps];
+            const char *pa = reinterpret_cast<const char *>(reinterpret_cast<const int2 *>(a.q_ord) + (size_t)cn.q * a.q_stride);
+            const char *pb = reinterpret_cast<const char *>(reinterpret_cast<const int2 *>(a.t_ord) + (size_t)cn.t * a.t_stride);
+            for (int o = lane * 128; o < a.q_stride * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(pa + o));
+            for (int o = lane * 128; o < a.t_stride * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(pb + o));
+        }
         const int nA = a.q_ord_n[c.q], nB = a.t_ord_n[c.t];
         const int32_t len1 = a.q_lenk[c.q], len2 = a.t_lenk[c.t];
         const int2 *A = reinterpret_cast<const int2 *>(a.q_ord) + (size_t)c.q * a.q_stride;

@@ -20,7 +20,7 @@ EXPORTS = [
     "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_xorshift_peaks", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
     "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads", "mhapb_store_add_reads_device",
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
-    "mhapb_store_get_range", "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
+    "mhapb_store_get_range", "mhapb_store_params", "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
     "mhapb_search_query_sketches", "mhapb_search_sketches_device", "mhapb_format_match", "mhapb_minhash_equal_count",
     "mhapb_store_reserve", "mhapb_sketch_reserve", "mhapb_kmer_hash", "mhapb_filter_set", "mhapb_filter_load_text", "mhapb_filter_clear",
     "mhapb_comm_unique_id", "mhapb_comm_init_rank", "mhapb_comm_init_all", "mhapb_comm_destroy", "mhapb_comm_info",
@@ -121,6 +121,7 @@ def load():
     L.mhapb_store_reserve.argtypes = [vp, i64]
     L.mhapb_sketch_reserve.argtypes = [vp, P(SketchParams), u64, u32, C.c_int]
     L.mhapb_store_get.argtypes = [vp, i64, P(i64), P(i32), P(i32), P(i32), vp, vp, P(i32)]
+    L.mhapb_store_params.argtypes = [vp, P(SketchParams)]
     L.mhapb_store_get_range.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     L.mhapb_store_device_ptrs.argtypes = [vp, P(vp), P(vp), P(vp), P(i64), P(i32), P(i32)]
     L.mhapb_index_build.argtypes = [vp]
