@@ -425,7 +425,8 @@ static int multi_run(mhapb_multi *m, F f)
         for (int i = 0; i < n; i++) th.emplace_back([&, i] { rc[i] = f(i); });
         for (auto &t : th) t.join();
     }
-    for (int i = 0; i < n; i++) if (rc[i]) return multi_fail(m, rc[i], std::string("device ") + std::to_string(m->ctx[i]->device) + ": " + mhapb_last_error(m->ctx[i]));
+    // a single device reports the library's (= the reference's) message verbatim; several prefix the device
+    for (int i = 0; i < n; i++) if (rc[i]) return multi_fail(m, rc[i], n == 1 ? std::string(mhapb_last_error(m->ctx[i])) : std::string("device ") + std::to_string(m->ctx[i]->device) + ": " + mhapb_last_error(m->ctx[i]));
     return MHAPB_OK;
 }
 
