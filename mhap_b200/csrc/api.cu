@@ -323,14 +323,15 @@ int index_build(mhapb_ctx *ctx)
     if (s.indexed) return MHAPB_OK;
     const int H = s.p.num_hashes;
     if ((uint64_t)s.n * (uint64_t)H >= 0xfffffff0ull || s.n >= 0x7fffffff) return fail(ctx, MHAPB_EINVAL, "store too large for 32-bit postings (%lld sketches x %d)", (long long)s.n, H);
-    int lg = 4; while ((1ll << lg) < 2 * s.n) lg++;
+    int lg = 5; while ((1ll << lg) < 2 * s.n) lg++;
     s.log2capw = lg;
     const size_t nslots = (size_t)H << lg;
     CU(ctx, s.slots.ensure(nslots * 8));
     CU(ctx, s.postings.ensure((size_t)s.n * H * 4));
+    CU(ctx, s.present.ensure(nslots / 8 + 64));
     CU(ctx, ctx->tmp_start.ensure(nslots * 4));
     CU(ctx, ctx->block_sums.ensure(((nslots + 4095) / 4096 + 1) * 4));
-    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), lg, H, s.n};
+    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.present.as<uint32_t>(), lg, H, s.n, 0};
     int launches = 0;
     cudaEventRecord(ctx->ev[8], ctx->stream);
     CU(ctx, launch_index_build(ctx->stream, s.minhash.as<int32_t>(), s.n, H, iv, ctx->tmp_start.as<uint32_t>(), ctx->block_sums.as<uint32_t>(), &launches));
@@ -353,7 +354,8 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
     int rc = index_build(ctx);
     if (rc) return rc;
     const int H = s.p.num_hashes;
-    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.log2capw, H, s.n};
+    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.present.as<uint32_t>(), s.log2capw, H, s.n,
+                 q.d_minhash != s.minhash.as<int32_t>() ? 1 : 0};
     const int64_t nq = q.list_all ? q.n_all : (q.d_list ? q.n_list : (int64_t)q.list.size());
     mhapb_stats st{};
     st.sequences_searched = nq;
@@ -667,7 +669,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
                       &ctx->q_id, &ctx->eq, &ctx->store.minhash, &ctx->store.ord, &ctx->store.ord_n, &ctx->store.lenk, &ctx->store.len,
                       &ctx->store.id, &ctx->store.slots, &ctx->store.postings, &ctx->f_keys, &ctx->f_idf, &ctx->f_used, &ctx->f_bloom};
     for (auto b : bufs) b->release();
-    DevBuf *more[] = {&ctx->ovf_q, &ctx->store.fwd_list, &ctx->g_minhash, &ctx->g_ord, &ctx->g_ordn, &ctx->g_lenk, &ctx->g_len, &ctx->g_id, &ctx->g_pack, &ctx->g_small};
+    DevBuf *more[] = {&ctx->ovf_q, &ctx->store.fwd_list, &ctx->store.present, &ctx->g_minhash, &ctx->g_ord, &ctx->g_ordn, &ctx->g_lenk, &ctx->g_len, &ctx->g_id, &ctx->g_pack, &ctx->g_small};
     for (auto b : more) b->release();
     ctx->h_cand.release(); ctx->h_ovl.release();
     comm_release(ctx);

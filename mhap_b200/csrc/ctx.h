@@ -79,7 +79,7 @@ struct Store {
     DevBuf fwd_list; int64_t fwd_list_n = 0; bool fwd_list_valid = false;
     // index
     bool indexed = false;
-    DevBuf slots, postings;
+    DevBuf slots, postings, present;
     int log2capw = 0;
 };
 

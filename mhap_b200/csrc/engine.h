@@ -81,9 +81,12 @@ size_t dedup_table_cap_short();   // slots per block in SketchScratch.dupcnt
 struct IndexView {
     uint64_t *slots;      // [H][capw]  (value | begin<<32), empty = ~0
     uint32_t *postings;   // [n_store*H] sketch index, MSB set on the last entry of a bucket
+    uint32_t *present;    // [H*capw/32] one bit per slot: occupied.  32 MB for 2*10^5 sketches -- it stays in L2, so a probe
+                          // that lands on an empty slot (most probes once the index is sharded over several GPUs) costs no DRAM
     int       log2capw;
     int       H;
     int64_t   n_store;
+    int       use_present;   // probe: consult `present` first (off when the store queries itself: every probe hits, the bitmap is pure overhead)
 };
 
 cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_t n_store, int H, IndexView iv,
@@ -119,6 +122,7 @@ struct FilterArgs {
     OverlapOut *out;
     const uint32_t *sel; uint64_t n_sel;          // thread-per-candidate kernel: only candidates sel[0..n_sel) (NULL: all)
     uint32_t *ovf_list; unsigned long long *ovf_count;   // warp kernel: candidates it hands to the thread-per-candidate kernel
+    int prefetch;                                        // warp kernel: pull the next pair's sketches towards L2 (set by the launcher)
 };
 // thread-per-candidate kernel (any sketch size, any match count; serial merge per thread)
 cudaError_t launch_filter(cudaStream_t st, FilterArgs a, int *launches);

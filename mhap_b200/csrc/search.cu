@@ -170,10 +170,13 @@ __global__ void __launch_bounds__(256) k_index_fill(const int32_t *__restrict__ 
 }
 
 // after the fill start[] holds each bucket's end: flag the last posting, rewrite slot as (value | begin<<32)
-__global__ void k_index_pack(uint64_t *slots, size_t n, const uint32_t *__restrict__ start, uint32_t *postings)
+__global__ void k_index_pack(uint64_t *slots, size_t n, const uint32_t *__restrict__ start, uint32_t *postings, uint32_t *present)
 {
+    // n is a multiple of 32 and the stride a multiple of the warp size: a warp always covers 32 consecutive slots
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         uint64_t s = slots[i];
+        const unsigned occ = __ballot_sync(kFull, s != kEmptySlot);
+        if ((threadIdx.x & 31) == 0) present[i >> 5] = occ;
         if (s == kEmptySlot) continue;
         uint32_t cnt = (uint32_t)(s >> 32), end = start[i];
         postings[end - 1] |= kLastFlag;
@@ -197,7 +200,7 @@ cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_
     k_scan_sums<<<1, kScanThreads, 0, st>>>(d_block_sums, nb);
     k_scan_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(iv.slots, nslots, d_block_sums, d_tmp_start);
     k_index_fill<<<tgrid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw, d_tmp_start, iv.postings);
-    k_index_pack<<<grid, 256, 0, st>>>(iv.slots, nslots, d_tmp_start, iv.postings);
+    k_index_pack<<<grid, 256, 0, st>>>(iv.slots, nslots, d_tmp_start, iv.postings, iv.present);
     *launches += 6;
     return cudaGetLastError();
 }
@@ -223,9 +226,11 @@ struct HitSlot { uint32_t t; uint32_t c; };
 __device__ __forceinline__ bool find_bucket(const IndexView &iv, int w, uint32_t v, uint32_t *begin)
 {
     const uint64_t *sub = iv.slots + ((size_t)w << iv.log2capw);
+    const uint32_t *pres = iv.present + ((size_t)w << (iv.log2capw - 5));
     const uint32_t capmask = (1u << iv.log2capw) - 1;
     uint32_t p = slot_hash(v, iv.log2capw);
     for (;;) {
+        if (iv.use_present && !((__ldg(&pres[p >> 5]) >> (p & 31)) & 1u)) return false;   // empty slot: answered from the L2-resident bitmap
         uint64_t s = __ldg(&sub[p]);
         if (s == kEmptySlot) return false;
         if ((uint32_t)s == v) { *begin = (uint32_t)(s >> 32); return true; }
@@ -586,10 +591,17 @@ __device__ __forceinline__ FwWindow fw_window(int32_t median, int32_t absmax, in
     return w;
 }
 
+// Element i of a sketch.  SM = false: straight from global memory (L1/L2).  SM = true: from the warp's staged copy in shared
+// memory, laid out at i + (i >> 5): the lanes walk ranges that start about n/32 elements apart (48 for S = 1536, i.e. 96 words
+// = a multiple of the 32 banks), so without the skew every lane's loads would hit the same bank.
+template <bool SM>
+__device__ __forceinline__ int2 fw_ld(const int2 *__restrict__ p, int i) { if (SM) return p[i + (i >> 5)]; else return __ldg(p + i); }
+
+template <bool SM>
 __device__ __forceinline__ int fw_lower_bound(const int2 *__restrict__ s, int n, int32_t h)
 {
     int lo = 0, hi = n;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&s[mid]).x < h) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (fw_ld<SM>(s, mid).x < h) lo = mid + 1; else hi = mid; }
     return lo;
 }
 
@@ -600,12 +612,13 @@ __device__ __forceinline__ int fw_lower_bound(const int2 *__restrict__ s, int n,
 // IMAD.WIDE + one LDG; the first version re-derived the row address from the constant bank with five instructions per
 // load and branched around it -- 40 instructions per step).  [Keeping the next element of each side in flight one step
 // ahead was measured slower: 19.2 vs 14.9 ms, 72 registers and twice the loads.]
+template <bool SM>
 __device__ __forceinline__ int fw_merge_range(const int2 *__restrict__ A, int i1, const int e1, const int2 *__restrict__ Bs, int i2, const int e2,
                                               const FwWindow &w, int2 *out, const int cap)
 {
     int count = 0;
     if (i1 >= e1 || i2 >= e2) return 0;
-    int2 a = __ldg(A + i1), b = __ldg(Bs + i2);
+    int2 a = fw_ld<SM>(A, i1), b = fw_ld<SM>(Bs, i2);
     for (;;) {
         const bool aout = (uint32_t)(a.y - w.lo1) >= (uint32_t)w.w1;
         const bool bout = (uint32_t)(b.y - w.lo2) >= (uint32_t)w.w2;
@@ -620,22 +633,22 @@ __device__ __forceinline__ int fw_merge_range(const int2 *__restrict__ A, int i1
                 count++;
                 int i1last = i1, i2last = i2;
                 int32_t p1 = a.y, p2 = b.y;
-                for (int t = i1 + 1; t < e1; t++) { const int2 x = __ldg(A + t); if (!(x.x == a.x && (uint32_t)(x.y - w.lo1) < (uint32_t)w.w1)) break; i1last = t; p1 = x.y; }
-                for (int t = i2 + 1; t < e2; t++) { const int2 x = __ldg(Bs + t); if (!(x.x == b.x && (uint32_t)(x.y - w.lo2) < (uint32_t)w.w2)) break; i2last = t; p2 = x.y; }
+                for (int t = i1 + 1; t < e1; t++) { const int2 x = fw_ld<SM>(A, t); if (!(x.x == a.x && (uint32_t)(x.y - w.lo1) < (uint32_t)w.w1)) break; i1last = t; p1 = x.y; }
+                for (int t = i2 + 1; t < e2; t++) { const int2 x = fw_ld<SM>(Bs, t); if (!(x.x == b.x && (uint32_t)(x.y - w.lo2) < (uint32_t)w.w2)) break; i2last = t; p2 = x.y; }
                 if (i1 != i1last || i2 != i2last) {
                     if (count < cap) out[count] = make_int2(p1, p2);
                     count++;
                     i1 = i1last + 1; i2 = i2last + 1;
                 } else { i1++; i2++; }
                 if (i1 >= e1 || i2 >= e2) break;
-                a = __ldg(A + i1); b = __ldg(Bs + i2);
+                a = fw_ld<SM>(A, i1); b = fw_ld<SM>(Bs, i2);
                 continue;
             }
         }
         i1 += adv1; i2 += adv2;
         if (i1 >= e1 || i2 >= e2) break;
-        if (adv1) a = __ldg(A + i1);
-        if (adv2) b = __ldg(Bs + i2);
+        if (adv1) a = fw_ld<SM>(A, i1);
+        if (adv2) b = fw_ld<SM>(Bs, i2);
     }
     return count;
 }
@@ -707,14 +720,21 @@ __device__ __forceinline__ void fw_update(const int2 *rec, int count, int32_t le
     *absmax = min(max(len1, len2), (int32_t)((double)overlap * max_shift));
 }
 
-__global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
+// SM = true: both sketches of a pair are first copied into the warp's shared memory with coalesced 8-byte cp.async
+// (capA / capB skewed slots each) and the three passes over them (two merges, the bottom-k walk) run from there.
+// Straight from global memory every lane walks its own contiguous range, so one warp-wide load touches 32 different
+// lines, and with the index sharded over several GPUs each pair brings a query sketch nobody else touches:
+// 15 ms at N=1, 34 ms at N=8 for the same 3*10^5 pairs per rank (profiles/r2i_bench_config1_n8.json).
+template <bool SM>
+__global__ void __launch_bounds__(SM ? 224 : 128) k_filter_warp(FilterArgs a, int capA, int capB)
 {
     extern __shared__ __align__(16) uint8_t fw_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const size_t per_warp = (size_t)kFwRecCap * 8 + 256 * 4;
+    const size_t per_warp = (size_t)(kFwRecCap + capA + capB) * 8 + 256 * 4;
     uint8_t *base = fw_smem + (size_t)wib * per_warp;
     int2 *rec = reinterpret_cast<int2 *>(base);
     uint32_t *hist = reinterpret_cast<uint32_t *>(rec + kFwRecCap);
+    int2 *sA = reinterpret_cast<int2 *>(hist + 256), *sB = sA + capA;
     const uint64_t warp_id = (uint64_t)blockIdx.x * wpb + wib, n_warps = (uint64_t)gridDim.x * wpb;
     // the candidate count is read on the device (it is K2b's cursor): no host round trip between probe and filter
     uint64_t n_cand = a.n_cand;
@@ -722,7 +742,7 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
 
     for (uint64_t ci = warp_id; ci < n_cand; ci += n_warps) {
         const Candidate c = a.cand[ci];
-        if (ci + n_warps < n_cand) {
+        if (a.prefetch && ci + n_warps < n_cand) {
             // pull the NEXT pair's two sketches towards L2 while this pair is merged: the merges are chains of dependent
             // loads, and with the queries in a gathered block of several GB (multi-GPU) most of them missed L2
             const Candidate cn = a.cand[ci + n_warps];
@@ -737,6 +757,14 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
         const int2 *Bs = reinterpret_cast<const int2 *>(a.t_ord) + (size_t)c.t * a.t_stride;
         asm volatile("" : "+l"(A), "+l"(Bs));   // keep the two row addresses in registers: element i is then one IMAD.WIDE away
         __syncwarp();
+        if (SM) {
+            const uint32_t da = (uint32_t)__cvta_generic_to_shared(sA), db = (uint32_t)__cvta_generic_to_shared(sB);
+            for (int i = lane; i < nA; i += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(da + 8u * (uint32_t)(i + (i >> 5))), "l"(A + i) : "memory");
+            for (int i = lane; i < nB; i += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(db + 8u * (uint32_t)(i + (i >> 5))), "l"(Bs + i) : "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            A = sA; Bs = sB;
+        }
         OverlapOut o; o.a1 = o.a2 = o.b1 = o.b2 = o.valid = o.inter = o.kmin = 0; o.empty = 1;
         bool overflow = false;
 
@@ -744,9 +772,9 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
         int a0 = 0, b0 = 0;
         if (lane > 0 && nA > 0) {
             a0 = (int)(((long long)lane * nA) >> 5);
-            const int32_t h = __ldg(A + a0).x;
-            while (a0 > 0 && __ldg(A + a0 - 1).x == h) a0--;        // = lower_bound(A, h): equal hashes are adjacent
-            b0 = fw_lower_bound(Bs, nB, h);
+            const int32_t h = fw_ld<SM>(A, a0).x;
+            while (a0 > 0 && fw_ld<SM>(A, a0 - 1).x == h) a0--;        // = lower_bound(A, h): equal hashes are adjacent
+            b0 = fw_lower_bound<SM>(Bs, nB, h);
         }
         int a1 = __shfl_down_sync(kFull, a0, 1), b1 = __shfl_down_sync(kFull, b0, 1);
         if (lane == 31) { a1 = nA; b1 = nB; }
@@ -761,7 +789,7 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
             // of the buffer, then the slots are packed in lane order into the lower half; a lane with more matches (or a
             // pair with more than half the buffer) repeats the merge writing at its final offset
             int2 *slot = rec + kFwRecCap / 2 + lane * kFwLaneCap;
-            const int mine = fw_merge_range(A, a0, a1, Bs, b0, b1, w, slot, kFwLaneCap);
+            const int mine = fw_merge_range<SM>(A, a0, a1, Bs, b0, b1, w, slot, kFwLaneCap);
             int total;
             const int off = warp_excl_scan(mine, lane, &total);
             count = total;
@@ -770,7 +798,7 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
             const bool fits = __all_sync(kFull, mine <= kFwLaneCap) && total <= kFwRecCap / 2;
             __syncwarp();
             if (fits) { for (int j = 0; j < mine; j++) rec[off + j] = slot[j]; }
-            else fw_merge_range(A, a0, a1, Bs, b0, b1, w, rec + off, mine);
+            else fw_merge_range<SM>(A, a0, a1, Bs, b0, b1, w, rec + off, mine);
             __syncwarp();
             fw_update(rec, count, len1, len2, a.max_shift, hist, lane, &median, &absmax);
         }
@@ -836,8 +864,8 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
                 {
                     int i = a0, j = b0;
                     int2 ea = make_int2(0, 0), eb = make_int2(0, 0);
-                    if (i < a1) ea = __ldg(A + i);
-                    if (j < b1) eb = __ldg(Bs + j);
+                    if (i < a1) ea = fw_ld<SM>(A, i);
+                    if (j < b1) eb = fw_ld<SM>(Bs, j);
                     while (i < a1 || j < b1) {
                         const bool ha = i < a1, hb = j < b1;
                         const bool ain = ha & ((uint32_t)(ea.y - wa_lo) < wa_w), bin = hb & ((uint32_t)(eb.y - wb_lo) < wb_w);
@@ -847,8 +875,8 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
                         sa += takea; sbn += takeb; inter_l += takea & takeb;
                         const bool adva = skipa | takea, advb = skipb | takeb;
                         i += adva; j += advb;
-                        if (adva && i < a1) ea = __ldg(A + i);
-                        if (advb && j < b1) eb = __ldg(Bs + j);
+                        if (adva && i < a1) ea = fw_ld<SM>(A, i);
+                        if (advb && j < b1) eb = fw_ld<SM>(Bs, j);
                     }
                 }
                 const int union_l = sa + sbn - inter_l;
@@ -863,12 +891,12 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
                     else if (ubefore < k) {                                       // the range in which the walk stops
                         int i = a0, j = b0, uni = ubefore;
                         while (uni < k) {
-                            while (i < a1 && !((uint32_t)(__ldg(A + i).y - wa_lo) < wa_w)) i++;
-                            while (j < b1 && !((uint32_t)(__ldg(Bs + j).y - wb_lo) < wb_w)) j++;
+                            while (i < a1 && !((uint32_t)(fw_ld<SM>(A, i).y - wa_lo) < wa_w)) i++;
+                            while (j < b1 && !((uint32_t)(fw_ld<SM>(Bs, j).y - wb_lo) < wb_w)) j++;
                             if (i >= a1) { j++; }                                 // only B entries left in range: each is one union step
                             else if (j >= b1) { i++; }
                             else {
-                                const int32_t ha = __ldg(A + i).x, hb = __ldg(Bs + j).x;
+                                const int32_t ha = fw_ld<SM>(A, i).x, hb = fw_ld<SM>(Bs, j).x;
                                 if (ha < hb) i++; else if (ha > hb) j++; else { inter++; i++; j++; }
                             }
                             uni++;
@@ -887,19 +915,57 @@ __global__ void __launch_bounds__(128) k_filter_warp(FilterArgs a)
 cudaError_t launch_filter_warp(cudaStream_t st, FilterArgs a, int *launches)
 {
     if (a.n_cand == 0 && !a.n_cand_dev) return cudaSuccess;
-    const size_t per_warp = (size_t)kFwRecCap * 8 + 256 * 4;
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // tunables (A/B runs): MHAPB_K2C_STAGE=0 keeps the sketches in global memory; MHAPB_K2C_CTAS bounds the pairs in flight
+    static int max_ctas = -1, pf = -1, stage = -1;
+    if (max_ctas < 0) { const char *e = getenv("MHAPB_K2C_CTAS"); max_ctas = e ? atoi(e) : 0; }
+    if (pf < 0) { const char *e = getenv("MHAPB_K2C_PREFETCH"); pf = e ? atoi(e) : 0; }
+    // staging is OFF by default: measured slower on 1xB200 (profiles/r2k_k2c_stage_sweep.txt: 18.8 vs 13.1 ms at configs[1],
+    // 130 vs 94 ms on 2.1 M pairs) -- 30 KB of shared memory per warp leaves 7 warps per SM against 24 without it, and the
+    // merges are chains of dependent loads that need the warps more than they need the bandwidth
+    if (stage < 0) { const char *e = getenv("MHAPB_K2C_STAGE"); stage = e ? atoi(e) : 0; }
+    const int capA = (a.q_stride + a.q_stride / 32 + 2) & ~1, capB = (a.t_stride + a.t_stride / 32 + 2) & ~1;
+    const size_t staged_per_warp = (size_t)(kFwRecCap + capA + capB) * 8 + 256 * 4;
+    if (stage && staged_per_warp <= 48 * 1024) {
+        // as many warps as one SM's shared memory holds, in one CTA
+        int wpb = (int)((size_t)(227 - 2) * 1024 / staged_per_warp);
+        if (wpb > 7) wpb = 7;
+        const size_t smem = staged_per_warp * wpb;
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            cudaError_t e = cudaFuncSetAttribute(k_filter_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_smem = smem;
+        }
+        int per_sm = 1;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_warp<true>, wpb * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        uint64_t grid = (uint64_t)sms * per_sm;
+        if (!a.n_cand_dev) { const uint64_t need = (a.n_cand + wpb - 1) / wpb; if (grid > need) grid = need; }
+        a.prefetch = 0;
+        k_filter_warp<true><<<(unsigned)grid, wpb * 32, smem, st>>>(a, capA, capB);
+        (*launches)++;
+        return cudaGetLastError();
+    }
+    const size_t per_warp = (size_t)kFwRecCap * 8 + 256 * 4;
     const int wpb = 4;
     const size_t smem = per_warp * wpb;
     static int per_sm = 0;
     if (!per_sm) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_warp, wpb * 32, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_warp<false>, wpb * 32, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }
-    uint64_t grid = (uint64_t)sms * per_sm;
+    // measured (profiles/r2j_k2c_sweep.txt, 2.1 M pairs): 9 CTAs/SM 111.9 ms, 6 -> 103.6, 4 -> 130.8, 2 -> 221; prefetching the
+    // next pair towards L2 118.0 vs 111.9 without -- the pairs in flight already fill L2
+    int use = per_sm;
+    const int cap = max_ctas > 0 ? max_ctas : 6;
+    if (use > cap) use = cap;
+    a.prefetch = pf;
+    uint64_t grid = (uint64_t)sms * use;
     if (!a.n_cand_dev) { const uint64_t need = (a.n_cand + wpb - 1) / wpb; if (grid > need) grid = need; }
-    k_filter_warp<<<(unsigned)grid, wpb * 32, smem, st>>>(a);
+    k_filter_warp<false><<<(unsigned)grid, wpb * 32, smem, st>>>(a, 0, 0);
     (*launches)++;
     return cudaGetLastError();
 }
