@@ -55,15 +55,6 @@ int read_status(const mhapb_sketch_params &p, uint64_t len)
 
 struct Elapsed { float hash = 0, minhash = 0, ordered = 0; };
 
-bool overlap_k1c()
-{
-    static int v = -1;
-    // measured on B200 (configs[1]): with K1c sharing the SMs with the alu-bound K1b it stretches from 34 ms to
-    // 434 ms per step and becomes the critical path (1.79 vs 1.96 Gbases/s), so the overlap is off unless asked for
-    if (v < 0) { const char *e = getenv("MHAPB_OVERLAP_K1C"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v != 0;
-}
-
 // Sketch reads whose characters are at d_bases (device).  row_of_slot[slot] (slot = read*per+strand)
 // gives the output row or -1 to skip.  Outputs are device arrays.
 // The weight rule in force for a sketch call: the context's filter (if any) under the call's repeat-weight class.
@@ -108,128 +99,164 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     ctx->timing.kmers_hashed = 0;
     if (all.empty()) return MHAPB_OK;
 
-    const uint64_t chunk_cap = 256ull << 20;   // k-mers of key scratch per chunk (2 GB keys + 1 GB weights)
+    // Work plan.  The strands are cut into CHUNKS of <= 256 M k-mers: a chunk is the unit of the host->device copy (its
+    // characters travel on the copy stream while the previous chunk is hashed) and of the K1a / K1c launches.  K1b -- 76 % of
+    // the step -- is launched ONCE over all chunks of a SUPER-CHUNK: its persistent warps take strands from a queue and a
+    // strand is ~4 ms of warp time, so every launch ends with a tail in which the SMs run dry one by one; eight launches per
+    // 100 k reads paid that tail eight times (profiles/r2l: 267 -> 25x ms).  The price is key scratch for the whole
+    // super-chunk (12 bytes per k-mer: 24 GB for 100 k x 10 kbp reads, both strands), bounded by MHAPB_K1_SUPER_GB (default:
+    // a third of the free memory, at most 64 GB).
+    const uint64_t chunk_cap = 256ull << 20;
     const int max_chunk_strands = 1 << 20;
+    uint64_t super_cap;
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t have = ctx->keys.cap + ctx->wts.cap;
+        double gb = std::min(64.0, (double)(free_b + have) / 3.0 / 1e9);
+        if (const char *e = getenv("MHAPB_K1_SUPER_GB")) gb = atof(e);
+        super_cap = std::max<uint64_t>(chunk_cap, (uint64_t)(gb * 1e9 / 12.0));
+    }
     int launches = 0;
-    std::vector<cudaEvent_t> evs, cevs;
-    auto ev_new = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e); };
-
-    size_t pos = 0;
-    std::vector<StrandDesc> chunk;
+    struct Sub { int begin, n, first_long, max_k_short, max_k_long, max_len_short, max_len_long; uint64_t lo, hi; };
+    auto is_short = [&](const StrandDesc &d) { return (int64_t)d.len - k + 1 <= kShortMaxKmers && (int64_t)d.len - ok + 1 <= kShortMaxKmers + 64; };
+    std::vector<cudaEvent_t> evs;     // per chunk: [before K1a, after K1a, after K1c]; per super-chunk: [before K1b, after K1b]
     std::vector<cudaEvent_t> hevs;
+    auto ev_new = [&](std::vector<cudaEvent_t> &v, cudaStream_t st) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); };
+    std::vector<size_t> k1a_ev, k1b_ev;
     uint64_t copied_hi = 0;
     if (h_bases) CU(ctx, cudaStreamSynchronize(ctx->stream2));   // the previous call's copies are long done; keeps the stream's order simple
+    cudaEvent_t first_ev = nullptr, last_ev = nullptr;
+
+    size_t pos = 0;
+    // strand descriptors are planned into PINNED memory: a copy from pageable memory makes the host wait for the stream, and
+    // then the next chunk's characters are not on their way while this chunk is hashed
+    std::vector<uint32_t> slot_of;                       // want_valid: caller's slot of every strand of the super-chunk
     while (pos < all.size()) {
-        uint64_t tot = 0;
-        chunk.clear();
-        while (pos < all.size() && (int)chunk.size() < max_chunk_strands) {
-            uint64_t nk = all[pos].len - k + 1;
-            if (!chunk.empty() && tot + nk > chunk_cap) break;
-            chunk.push_back(all[pos]); tot += nk; pos++;
+        // ---- extent of one super-chunk (sizes only: the first K1a launch should not wait for the whole plan) ----
+        size_t send = pos; uint64_t total_k = 0; size_t n_chunks = 0;
+        int max_k_short = 1, max_k_long = 1, max_len_long = 1; bool any_short = false, any_long = false;
+        {
+            uint64_t in_chunk = 0; size_t in_chunk_n = 0;
+            while (send < all.size()) {
+                const uint64_t nk = all[send].len - k + 1;
+                if (send > pos && total_k + nk > super_cap) break;
+                if (in_chunk_n == 0 || in_chunk + nk > chunk_cap || (int)in_chunk_n >= max_chunk_strands) { n_chunks++; in_chunk = 0; in_chunk_n = 0; }
+                in_chunk += nk; in_chunk_n++;
+                total_k += nk;
+                if (is_short(all[send])) { any_short = true; max_k_short = std::max(max_k_short, (int)nk); }
+                else { any_long = true; max_k_long = std::max(max_k_long, (int)nk); max_len_long = std::max(max_len_long, (int)all[send].len); }
+                send++;
+            }
         }
-        // short strands first, long (global-table) strands after
-        auto is_short = [&](const StrandDesc &d) { return (int64_t)d.len - k + 1 <= kShortMaxKmers && (int64_t)d.len - ok + 1 <= kShortMaxKmers + 64; };
-        std::stable_partition(chunk.begin(), chunk.end(), is_short);
-        int n = (int)chunk.size(), first_long = n;
-        int max_k_short = 1, max_k_long = 1, max_len_short = 1, max_len_long = 1;
-        uint64_t koff = 0;
-        for (int i = 0; i < n; i++) {
-            StrandDesc &d = chunk[i];
-            d.koff = koff; koff += d.len - k + 1;
-            int nk = (int)d.len - k + 1;
-            if (is_short(d)) { max_k_short = std::max(max_k_short, nk); max_len_short = std::max(max_len_short, (int)d.len); }
-            else { if (first_long == n) first_long = i; max_k_long = std::max(max_k_long, nk); max_len_long = std::max(max_len_long, (int)d.len); }
-            ctx->timing.xorshift_steps += (int64_t)nk * H;
-            ctx->timing.kmers_hashed += nk;
-        }
-        const int n_long = n - first_long;
-        CU(ctx, ctx->desc.ensure((size_t)n * sizeof(StrandDesc)));
-        CU(ctx, ctx->keys.ensure((size_t)koff * 8));
-        CU(ctx, ctx->wts.ensure((size_t)koff * 4));
-        CU(ctx, ctx->nlight.ensure((size_t)n * 4));
-        CU(ctx, ctx->nheavy.ensure((size_t)n * 4));
-        CU(ctx, ctx->counters.ensure(64));
-        const size_t cap_short = dedup_table_slots((uint32_t)max_k_short), cap_long = dedup_table_slots((uint32_t)max_k_long);
+        const int n_all = (int)(send - pos);
+        // ---- scratch for the super-chunk ----
+        CU(ctx, ctx->desc.ensure((size_t)n_all * sizeof(StrandDesc)));
+        CU(ctx, ctx->h_desc.ensure((size_t)n_all * sizeof(StrandDesc)));
+        StrandDesc *hd = ctx->h_desc.as<StrandDesc>();
+        CU(ctx, ctx->keys.ensure((size_t)total_k * 8));
+        CU(ctx, ctx->wts.ensure((size_t)total_k * 4));
+        CU(ctx, ctx->nlight.ensure((size_t)n_all * 4));
+        CU(ctx, ctx->nheavy.ensure((size_t)n_all * 4));
+        const size_t n_counters = (n_chunks + 2) * 4 + 4;        // per chunk: K1a short, K1a long, K1c short, K1c long; + K1b (after the chunks' blocks)
+        CU(ctx, ctx->counters.ensure(n_counters * 4));
         const int g1 = hash_dedup_grid() * 2, g2 = ordered_grid();
-        size_t dup_need = first_long > 0 ? (size_t)g1 * cap_short * 4 : 0;
-        if (n_long) dup_need = std::max(dup_need, (size_t)g1 * cap_long * 4);
+        size_t dup_need = 0;
+        if (any_short) dup_need = (size_t)g1 * dedup_table_slots((uint32_t)max_k_short) * 4;
+        if (any_long) {
+            const size_t cap_long = dedup_table_slots((uint32_t)max_k_long);
+            dup_need = std::max(dup_need, (size_t)g1 * cap_long * 4);
+            CU(ctx, ctx->gtable.ensure((size_t)g1 * cap_long * 8));
+            CU(ctx, ctx->ohash.ensure((size_t)g2 * ((size_t)max_len_long + 32) * 4));
+        }
         if (dup_need > ctx->dupcnt.cap) {
             CU(ctx, ctx->dupcnt.ensure(dup_need));
             CU(ctx, cudaMemsetAsync(ctx->dupcnt.p, 0, ctx->dupcnt.cap, ctx->stream));   // invariant: zero between uses
         }
-        if (n_long) {
-            CU(ctx, ctx->gtable.ensure((size_t)g1 * cap_long * 8));
-            CU(ctx, ctx->ohash.ensure((size_t)g2 * ((size_t)max_len_long + 32) * 4));
-        }
-        CU(ctx, cudaMemcpyAsync(ctx->desc.p, chunk.data(), (size_t)n * sizeof(StrandDesc), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemsetAsync(ctx->counters.p, 0, 64, ctx->stream));
-        if (h_bases) {   // this chunk's characters: H2D on the copy stream, K1a waits for it; the next chunk's copy overlaps this chunk's K1
-            uint64_t lo = ~0ull, hi = 0;
-            for (int i = 0; i < n; i++) { lo = std::min<uint64_t>(lo, chunk[i].base_off); hi = std::max<uint64_t>(hi, chunk[i].base_off + chunk[i].len); }
-            lo = std::max(lo, copied_hi);           // a read whose two strands straddle two chunks was copied with the first
-            if (hi > lo) {
-                cudaEvent_t h0, h1; cudaEventCreate(&h0); cudaEventCreate(&h1);
-                cudaEventRecord(h0, ctx->stream2);
-                CU(ctx, cudaMemcpyAsync(const_cast<uint8_t *>(d_bases) + lo, h_bases + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream2));
-                cudaEventRecord(h1, ctx->stream2);
-                CU(ctx, cudaStreamWaitEvent(ctx->stream, h1, 0));
-                hevs.push_back(h0); hevs.push_back(h1);
-                copied_hi = hi;
-            }
-        }
+        CU(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_counters * 4, ctx->stream));
         SketchScratch sc;
         sc.keys = ctx->keys.as<uint64_t>(); sc.wts = ctx->wts.as<uint32_t>();
         sc.nlight = ctx->nlight.as<int32_t>(); sc.nheavy = ctx->nheavy.as<int32_t>();
         sc.dupcnt = ctx->dupcnt.as<uint32_t>(); sc.gtable = ctx->gtable.as<uint64_t>();
         sc.ohash = ctx->ohash.as<uint32_t>(); sc.counters = ctx->counters.as<uint32_t>();
-        const StrandDesc *dd = ctx->desc.as<StrandDesc>();
-        // K1a -> K1b on the main stream; K1c (independent of both: it only needs the reads) on the second stream,
-        // released when K1a is done so that it shares the SMs with the alu-bound K1b instead of the
-        // shared-memory-hungry K1a.  K1c is launched first with one CTA per SM, K1b fills the rest.
-        ev_new();                                                     // [0] before K1a
-        CU(ctx, launch_hash_dedup(ctx->stream, d_bases, dd, n, first_long, max_k_short, max_k_long, k, filter_unweighted(flt, p.unweighted), flt, sc, &launches));
-        ev_new();                                                     // [1] after K1a
+        StrandDesc *dd = ctx->desc.as<StrandDesc>();
+        if (want_valid) slot_of.assign((size_t)n_all, 0);
+        // ---- per chunk: plan, descriptors + characters in, K1a, K1c (the host plans chunk i+1 while the GPU hashes chunk i) ----
+        uint64_t koff = 0;
+        size_t ci = 0;
+        while (pos < send) {
+            uint64_t tot = 0;
+            size_t q = pos;
+            while (q < send && (int)(q - pos) < max_chunk_strands) {
+                const uint64_t nk = all[q].len - k + 1;
+                if (q > pos && tot + nk > chunk_cap) break;
+                tot += nk; q++;
+            }
+            const int c0 = n_all - (int)(send - pos);             // index of this chunk's first strand in the super-chunk
+            StrandDesc *cd = hd + c0;
+            const int cn = (int)(q - pos);
+            std::copy(all.begin() + pos, all.begin() + q, cd);
+            pos = q;
+            std::stable_partition(cd, cd + cn, is_short);         // short strands first, long (global-table) strands after
+            Sub sb{c0, cn, cn, 1, 1, 1, 1, ~0ull, 0};
+            for (int i = 0; i < sb.n; i++) {
+                StrandDesc &d = cd[i];
+                d.koff = koff; koff += d.len - k + 1;
+                const int nk = (int)d.len - k + 1;
+                if (is_short(d)) { sb.max_k_short = std::max(sb.max_k_short, nk); sb.max_len_short = std::max(sb.max_len_short, (int)d.len); }
+                else { if (sb.first_long == sb.n) sb.first_long = i; sb.max_k_long = std::max(sb.max_k_long, nk); sb.max_len_long = std::max(sb.max_len_long, (int)d.len); }
+                sb.lo = std::min<uint64_t>(sb.lo, d.base_off); sb.hi = std::max<uint64_t>(sb.hi, d.base_off + d.len);
+                ctx->timing.xorshift_steps += (int64_t)nk * H;
+                ctx->timing.kmers_hashed += nk;
+                if (want_valid) slot_of[(size_t)c0 + i] = d.slot;
+            }
+            CU(ctx, cudaMemcpyAsync(dd + c0, cd, (size_t)cn * sizeof(StrandDesc), cudaMemcpyHostToDevice, ctx->stream));
+            if (h_bases) {
+                const uint64_t lo = std::max(sb.lo, copied_hi);   // a read whose two strands straddle two chunks was copied with the first
+                if (sb.hi > lo) {
+                    ev_new(hevs, ctx->stream2);
+                    CU(ctx, cudaMemcpyAsync(const_cast<uint8_t *>(d_bases) + lo, h_bases + lo, (size_t)(sb.hi - lo), cudaMemcpyHostToDevice, ctx->stream2));
+                    ev_new(hevs, ctx->stream2);
+                    CU(ctx, cudaStreamWaitEvent(ctx->stream, hevs.back(), 0));
+                    copied_hi = sb.hi;
+                }
+            }
+            uint32_t *qs = sc.counters + ci * 4;
+            ci++;
+            k1a_ev.push_back(evs.size());
+            ev_new(evs, ctx->stream);                                     // before K1a
+            if (!first_ev) first_ev = evs.back();
+            // table capacities: the super-chunk's maxima (dupcnt rows are strided by the launch's capacity)
+            CU(ctx, launch_hash_dedup(ctx->stream, d_bases, dd, sb.begin, sb.n, sb.first_long, max_k_short, max_k_long, k, filter_unweighted(flt, p.unweighted), flt, sc, qs, &launches));
+            ev_new(evs, ctx->stream);                                     // after K1a
+            if (d_ord) CU(ctx, launch_ordered(ctx->stream, d_bases, dd, sb.begin, sb.n, sb.first_long, sb.max_len_short, std::max(sb.max_len_long, max_len_long), ok, S, ord_stride, sc, d_ord, d_ord_n, 0, qs + 2, &launches));
+            ev_new(evs, ctx->stream);                                     // after K1c
+        }
         if (want_valid) {   // which strands kept at least one k-mer
-            h_nl.resize(n); h_nh.resize(n);
-            CU(ctx, cudaMemcpyAsync(h_nl.data(), sc.nlight, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaMemcpyAsync(h_nh.data(), sc.nheavy, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            h_nl.resize(n_all); h_nh.resize(n_all);
+            CU(ctx, cudaMemcpyAsync(h_nl.data(), sc.nlight, (size_t)n_all * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(h_nh.data(), sc.nheavy, (size_t)n_all * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CU(ctx, cudaStreamSynchronize(ctx->stream));
-            for (int i = 0; i < n; i++) if (h_nl[i] + h_nh[i] == 0) (*slot_valid)[chunk[i].slot] = 0;
+            for (int i = 0; i < n_all; i++) if (h_nl[i] + h_nh[i] == 0) (*slot_valid)[slot_of[(size_t)i]] = 0;
         }
-        cudaEvent_t c0 = nullptr, c1 = nullptr;
-        const bool overlap = overlap_k1c() && d_ord && d_minhash;
-        if (overlap) {
-            CU(ctx, cudaStreamWaitEvent(ctx->stream2, evs.back(), 0));
-            cudaEventCreate(&c0); cudaEventCreate(&c1);
-            cudaEventRecord(c0, ctx->stream2);
-            CU(ctx, launch_ordered(ctx->stream2, d_bases, dd, n, first_long, max_len_short, max_len_long, ok, S, ord_stride, sc, d_ord, d_ord_n, 1, &launches));
-            cudaEventRecord(c1, ctx->stream2);
-        }
-        if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n, k, H, sc, d_minhash, flt.light_weight, &launches));
-        ev_new();                                                     // [2] after K1b
-        if (overlap) {
-            CU(ctx, cudaStreamWaitEvent(ctx->stream, c1, 0));         // the next chunk reuses the descriptors
-            cevs.push_back(c0); cevs.push_back(c1);
-        } else if (d_ord) {
-            CU(ctx, launch_ordered(ctx->stream, d_bases, dd, n, first_long, max_len_short, max_len_long, ok, S, ord_stride, sc, d_ord, d_ord_n, 0, &launches));
-        }
-        ev_new();                                                     // [3] end of chunk
-        // the next chunk reuses desc/keys: the stream orders it, but the pageable host vector is copied synchronously above
+        // ---- K1b: one launch over the whole super-chunk ----
+        k1b_ev.push_back(evs.size());
+        ev_new(evs, ctx->stream);
+        if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n_all, k, H, sc, d_minhash, flt.light_weight, sc.counters + (n_chunks + 2) * 4, &launches));
+        ev_new(evs, ctx->stream);
+        last_ev = evs.back();
+        if (pos < all.size()) CU(ctx, cudaStreamSynchronize(ctx->stream));   // the next super-chunk reuses desc / keys / the pinned plan
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    for (size_t i = 0; i + 3 < evs.size(); i += 4) {
-        float a = 0, b = 0, c = 0;
-        cudaEventElapsedTime(&a, evs[i], evs[i + 1]); cudaEventElapsedTime(&b, evs[i + 1], evs[i + 2]); cudaEventElapsedTime(&c, evs[i + 2], evs[i + 3]);
-        ctx->timing.hash_dedup_ms += a; ctx->timing.minhash_ms += b;
-        if (cevs.empty()) ctx->timing.ordered_ms += c;
+    for (size_t i : k1a_ev) {
+        float a = 0, c = 0;
+        cudaEventElapsedTime(&a, evs[i], evs[i + 1]); cudaEventElapsedTime(&c, evs[i + 1], evs[i + 2]);
+        ctx->timing.hash_dedup_ms += a; ctx->timing.ordered_ms += c;
     }
-    for (size_t i = 0; i + 1 < cevs.size(); i += 2) {   // K1c timed on its own stream (it overlaps K1b)
-        float c = 0; cudaEventElapsedTime(&c, cevs[i], cevs[i + 1]); ctx->timing.ordered_ms += c;
-    }
-    for (auto e : cevs) cudaEventDestroy(e);
+    for (size_t i : k1b_ev) { float b = 0; cudaEventElapsedTime(&b, evs[i], evs[i + 1]); ctx->timing.minhash_ms += b; }
     for (size_t i = 0; i + 1 < hevs.size(); i += 2) { float c = 0; cudaEventElapsedTime(&c, hevs[i], hevs[i + 1]); ctx->timing.h2d_ms += c; }
     for (auto e : hevs) cudaEventDestroy(e);
-    if (evs.size() >= 2) { float t = 0; cudaEventElapsedTime(&t, evs.front(), evs.back()); ctx->timing.sketch_total_ms += t; }
+    if (first_ev && last_ev) { float t = 0; cudaEventElapsedTime(&t, first_ev, last_ev); ctx->timing.sketch_total_ms += t; }
     for (auto e : evs) cudaEventDestroy(e);
     ctx->timing.kernel_launches += launches;
     return MHAPB_OK;
@@ -671,7 +698,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
     for (auto b : bufs) b->release();
     DevBuf *more[] = {&ctx->ovf_q, &ctx->store.fwd_list, &ctx->store.present, &ctx->g_minhash, &ctx->g_ord, &ctx->g_ordn, &ctx->g_lenk, &ctx->g_len, &ctx->g_id, &ctx->g_pack, &ctx->g_small};
     for (auto b : more) b->release();
-    ctx->h_cand.release(); ctx->h_ovl.release();
+    ctx->h_cand.release(); ctx->h_ovl.release(); ctx->h_desc.release();
     comm_release(ctx);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);

@@ -99,6 +99,7 @@ struct mhapb_ctx {
     // search scratch
     mhapb::DevBuf ovf_q;
     mhapb::PinnedBuf h_cand, h_ovl;               // pinned landing buffers of the surviving pairs
+    mhapb::PinnedBuf h_desc;                      // pinned plan of the strand descriptors (sketch_core)
     uint64_t cand_cap_hint = 0; uint32_t ovf_threads_hint = 0;   // sizes the previous search needed
     mhapb::DevBuf qlist, cand, ovl, cand2, ovl2, ovf_list, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
     mhapb::Store store;

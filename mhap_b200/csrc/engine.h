@@ -58,18 +58,19 @@ struct KmerFilterView {
 };
 
 // K1a: hash every k-mer (MurmurHash3_x64_128 h1), de-duplicate with counts, apply the weight rule.
-cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
-                              int first_long /* descs [first_long, n) are long strands */, int max_kmers_short,
+// descs [s_base, s_base + n_strands) of d_desc; queues: two zeroed work-queue counters (short, long) of this launch pair
+cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int s_base, int n_strands,
+                              int first_long /* descs [s_base + first_long, s_base + n) are long strands */, int max_kmers_short,
                               int max_kmers_long, int k, int unweighted, const KmerFilterView &filter,
-                              const SketchScratch &sc, int *launches);
+                              const SketchScratch &sc, uint32_t *queues, int *launches);
 // K1b: H-step XORShift chain per distinct k-mer (light keys advance light_weight steps per word, heavy keys their
 // own weight), per-word signed minimum -> minhash rows.
 cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
-                           const SketchScratch &sc, int32_t *d_minhash, uint32_t light_weight, int *launches);
+                           const SketchScratch &sc, int32_t *d_minhash, uint32_t light_weight, uint32_t *queue, int *launches);
 // K1c: MurmurHash3_x86_32 of every ordered k-mer, bottom-S by (signed hash, position), sorted.
-cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
+cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int s_base, int n_strands,
                            int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,
-                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int max_ctas_per_sm /* 0: default */, int *launches);
+                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int max_ctas_per_sm /* 0: default */, uint32_t *queues, int *launches);
 // independent XORShift chains at full occupancy: the integer-issue ceiling K1b is measured against
 cudaError_t launch_xorshift_peak(cudaStream_t st, unsigned long long *d_sink, double *steps);
 cudaError_t launch_xorshift_peak_bs(cudaStream_t st, unsigned long long *d_sink, double *steps);

@@ -1135,9 +1135,9 @@ size_t dedup_table_cap_short() { return kShortTableCap; }
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
+cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int s_base, int n_strands,
                               int first_long, int max_kmers_short, int max_kmers_long, int k, int unweighted,
-                              const KmerFilterView &filter, const SketchScratch &sc, int *launches)
+                              const KmerFilterView &filter, const SketchScratch &sc, uint32_t *queues, int *launches)
 {
     cudaError_t e;
     if (first_long > 0) {
@@ -1151,7 +1151,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         if (smem <= 113 * 1024) grid *= 2;
         if (grid > first_long) grid = first_long;
         // dupcnt rows are strided by the *launch's* cap so both variants can share the buffer
-        kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, 0, first_long, k, unweighted, cap, chars_cap, sc, sc.counters + 0, filter);
+        kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, s_base, s_base + first_long, k, unweighted, cap, chars_cap, sc, queues + 0, filter);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -1159,7 +1159,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         uint32_t cap = dedup_table_slots((uint32_t)max_kmers_long);
         int grid = hash_dedup_grid();
         if (grid > n_strands - first_long) grid = n_strands - first_long;
-        k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, first_long, n_strands, k, unweighted, cap, 0, sc, sc.counters + 1, filter);
+        k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, s_base + first_long, s_base + n_strands, k, unweighted, cap, 0, sc, queues + 1, filter);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -1177,7 +1177,7 @@ static int k1b_variant()
 
 template <int B>
 static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
-                                    const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w)
+                                    const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, uint32_t *queue)
 {
     cudaError_t e;
     int per_sm = 0;
@@ -1196,7 +1196,7 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         if (grid > need) grid = need;
         static int scalar_keys2 = -1;
         if (scalar_keys2 < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys2 = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys2 < 0) scalar_keys2 = 0; }
-        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys2, (int)light_w);
+        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, scalar_keys2, (int)light_w);
         return cudaGetLastError();
     }
     if (variant == 1 && B <= 32) {
@@ -1211,7 +1211,7 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         if (grid > need) grid = need;
         static int scalar_keys = -1;
         if (scalar_keys < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys < 0) scalar_keys = 0; }
-        k_minhash_bs<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, scalar_keys);
+        k_minhash_bs<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, scalar_keys);
         return cudaGetLastError();
     }
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash<B>, 256, 0);
@@ -1220,31 +1220,31 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
     int grid = sm_count() * per_sm;
     int need = (n_strands + 7) / 8;
     if (grid > need) grid = need;
-    k_minhash<B><<<grid, 256, 0, st>>>(d_desc, n_strands, k, H, sc, d_minhash, sc.counters + 2, light_w);
+    k_minhash<B><<<grid, 256, 0, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, light_w);
     return cudaGetLastError();
 }
 
 cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
-                           const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, int *launches)
+                           const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, uint32_t *queue, int *launches)
 {
     if (n_strands <= 0) return cudaSuccess;
     (*launches)++;
     const int b = (H + 31) / 32;
-    if (b <= 1) return launch_minhash_b<1>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 2) return launch_minhash_b<2>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 4) return launch_minhash_b<4>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 8) return launch_minhash_b<8>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 12) return launch_minhash_b<12>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 16) return launch_minhash_b<16>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 24) return launch_minhash_b<24>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 32) return launch_minhash_b<32>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    if (b <= 48) return launch_minhash_b<48>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
-    return launch_minhash_b<64>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w);
+    if (b <= 1) return launch_minhash_b<1>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 2) return launch_minhash_b<2>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 4) return launch_minhash_b<4>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 8) return launch_minhash_b<8>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 12) return launch_minhash_b<12>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 16) return launch_minhash_b<16>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 24) return launch_minhash_b<24>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 32) return launch_minhash_b<32>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    if (b <= 48) return launch_minhash_b<48>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
+    return launch_minhash_b<64>(st, d_desc, n_strands, k, H, sc, d_minhash, light_w, queue);
 }
 
-cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int n_strands,
+cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int s_base, int n_strands,
                            int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,
-                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int max_ctas_per_sm, int *launches)
+                           const SketchScratch &sc, int32_t *d_ord, int32_t *d_ord_n, int max_ctas_per_sm, uint32_t *queues, int *launches)
 {
     cudaError_t e;
     uint32_t sel_cap = 1; while ((int)sel_cap < S) sel_cap <<= 1;
@@ -1262,7 +1262,7 @@ cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const Strand
         if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
         int grid = sm_count() * per_sm;
         if (grid > first_long) grid = first_long;
-        kern<<<grid, 512, smem, st>>>(d_bases, d_desc, 0, first_long, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 3);
+        kern<<<grid, 512, smem, st>>>(d_bases, d_desc, s_base, s_base + first_long, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, queues + 0);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -1273,7 +1273,7 @@ cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const Strand
         if (e != cudaSuccess) return e;
         int grid = ordered_grid();
         if (grid > n_strands - first_long) grid = n_strands - first_long;
-        k_ordered<true, 0><<<grid, 512, smem, st>>>(d_bases, d_desc, first_long, n_strands, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, sc.counters + 4);
+        k_ordered<true, 0><<<grid, 512, smem, st>>>(d_bases, d_desc, s_base + first_long, s_base + n_strands, ok, S, ord_stride, len_cap, sel_cap, sc, d_ord, d_ord_n, queues + 1);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
