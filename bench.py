@@ -293,6 +293,8 @@ def _main(args, real_stdout):
             n_launch += tq["kernel_launches"]
             xsteps += tq["xorshift_steps"]
         t_c = time.perf_counter()
+        last["tm_add"] = {k: tm[k] for k in ("sketch_total_ms", "h2d_ms", "hash_dedup_ms", "minhash_ms", "ordered_ms")}
+        last["wall_add"] = (t_b - t_a) * 1e3
         if record:
             for k in ("sketch_total_ms", "hash_dedup_ms", "minhash_ms", "ordered_ms", "h2d_ms"):
                 acc[k] += tm[k]
@@ -344,6 +346,7 @@ def _main(args, real_stdout):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item()) / args.steps
+    e2e_add = dict(last["tm_add"], wall_ms=last["wall_add"])      # K1 + H2D of the last host-buffer step (rank 0)
 
     # ---- parity block: proof next to the speed ----
     # digest = sha256 over the sorted integer fields + score bits of the job's whole hit set (order-independent);
@@ -431,6 +434,7 @@ def _main(args, real_stdout):
         "e2e": {"value": total_bases / e2e_s / 1e9, "unit": "Gbases/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int((n_local + nq_local) * L + 8 * (n_local + nq_local + 2)) * world,
                 "d2h_bytes_per_step": int((len(e_hits) + (len(e_qhits) if e_qhits is not None else 0)) * (12 + 32) * world + 64),
+                "store_add_reads_rank0": e2e_add,
                 "api": ("mhapb_store_add_reads + mhapb_search_self" if world == 1 else "mhapb_store_add_reads + mhapb_dist_search_self (NCCL inside the library)") + " (host buffers)"},
         "gpu_launches": int(launches["n"]), "clocks": clocks, "n_hits_rank0": int(len(hits)), "nccl_version": nccl_version,
         "parity": parity,

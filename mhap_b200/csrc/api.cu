@@ -5,6 +5,7 @@
 #include "hash.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -75,6 +76,10 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
                 uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
                 int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid, const char *h_bases)
 {
+    static const bool trace = getenv("MHAPB_TRACE") != nullptr;   // host-side time stamps of the enqueue path, to stderr
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count(); };
+    double t_plan = 0, t_first = 0, t_enq = 0;
     const KmerFilterView flt = filter_view(ctx);
     if (ctx->filter_set && (ctx->filter_params.repeat_weight < 0.0) != (p.unweighted != 0))
         return fail(ctx, MHAPB_EINVAL, "sketch params unweighted=%d contradict the filter's repeat_weight %g", p.unweighted, ctx->filter_params.repeat_weight);
@@ -117,15 +122,16 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         if (const char *e = getenv("MHAPB_K1_SUPER_GB")) gb = atof(e);
         super_cap = std::max<uint64_t>(chunk_cap, (uint64_t)(gb * 1e9 / 12.0));
     }
+    t_plan = since();
     int launches = 0;
     struct Sub { int begin, n, first_long, max_k_short, max_k_long, max_len_short, max_len_long; uint64_t lo, hi; };
     auto is_short = [&](const StrandDesc &d) { return (int64_t)d.len - k + 1 <= kShortMaxKmers && (int64_t)d.len - ok + 1 <= kShortMaxKmers + 64; };
     std::vector<cudaEvent_t> evs;     // per chunk: [before K1a, after K1a, after K1c]; per super-chunk: [before K1b, after K1b]
-    std::vector<cudaEvent_t> hevs;
+    std::vector<cudaEvent_t> hevs, cpevs;
     auto ev_new = [&](std::vector<cudaEvent_t> &v, cudaStream_t st) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); };
     std::vector<size_t> k1a_ev, k1b_ev;
     uint64_t copied_hi = 0;
-    if (h_bases) CU(ctx, cudaStreamSynchronize(ctx->stream2));   // the previous call's copies are long done; keeps the stream's order simple
+    CU(ctx, cudaStreamSynchronize(ctx->stream2));   // the previous call's copies are long done; keeps the stream's order simple
     cudaEvent_t first_ev = nullptr, last_ev = nullptr;
 
     size_t pos = 0;
@@ -154,7 +160,12 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         CU(ctx, ctx->desc.ensure((size_t)n_all * sizeof(StrandDesc)));
         CU(ctx, ctx->h_desc.ensure((size_t)n_all * sizeof(StrandDesc)));
         StrandDesc *hd = ctx->h_desc.as<StrandDesc>();
-        CU(ctx, ctx->keys.ensure((size_t)total_k * 8));
+        // sketches wider than 512 words run as `passes` blocks of <= 512 words (virtual strands, see k_minhash_bs2): block p needs
+        // its own copy of the keys, advanced by 512*p*weight steps
+        static int multipass = -1;
+        if (multipass < 0) { const char *e = getenv("MHAPB_K1B_PASSES"); multipass = e ? atoi(e) : 1; }
+        const int passes = (multipass && H > 512 && H <= kMaxNumHashes && d_minhash) ? (H + 511) / 512 : 1;
+        CU(ctx, ctx->keys.ensure((size_t)total_k * 8 * (size_t)passes));
         CU(ctx, ctx->wts.ensure((size_t)total_k * 4));
         CU(ctx, ctx->nlight.ensure((size_t)n_all * 4));
         CU(ctx, ctx->nheavy.ensure((size_t)n_all * 4));
@@ -174,6 +185,10 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
             CU(ctx, cudaMemsetAsync(ctx->dupcnt.p, 0, ctx->dupcnt.cap, ctx->stream));   // invariant: zero between uses
         }
         CU(ctx, cudaMemsetAsync(ctx->counters.p, 0, n_counters * 4, ctx->stream));
+        {   // the copy stream starts this super-chunk after everything queued so far on the compute stream (buffers may have moved)
+            ev_new(cpevs, ctx->stream);
+            CU(ctx, cudaStreamWaitEvent(ctx->stream2, cpevs.back(), 0));
+        }
         SketchScratch sc;
         sc.keys = ctx->keys.as<uint64_t>(); sc.wts = ctx->wts.as<uint32_t>();
         sc.nlight = ctx->nlight.as<int32_t>(); sc.nheavy = ctx->nheavy.as<int32_t>();
@@ -210,22 +225,27 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
                 ctx->timing.kmers_hashed += nk;
                 if (want_valid) slot_of[(size_t)c0 + i] = d.slot;
             }
-            CU(ctx, cudaMemcpyAsync(dd + c0, cd, (size_t)cn * sizeof(StrandDesc), cudaMemcpyHostToDevice, ctx->stream));
+            // Descriptors and characters of the chunk travel on the COPY stream, the compute stream waits for their event.
+            // (A descriptor copy on the compute stream sits behind the previous chunk's kernels in stream order but in front
+            // of this chunk's characters in the copy engine's queue: head-of-line blocking made every chunk's H2D wait for the
+            // previous chunk's K1a/K1c -- 18 ms of exposed copies per 1 GB of reads, found with MHAPB_TRACE.)
+            CU(ctx, cudaMemcpyAsync(dd + c0, cd, (size_t)cn * sizeof(StrandDesc), cudaMemcpyHostToDevice, ctx->stream2));
             if (h_bases) {
                 const uint64_t lo = std::max(sb.lo, copied_hi);   // a read whose two strands straddle two chunks was copied with the first
                 if (sb.hi > lo) {
                     ev_new(hevs, ctx->stream2);
                     CU(ctx, cudaMemcpyAsync(const_cast<uint8_t *>(d_bases) + lo, h_bases + lo, (size_t)(sb.hi - lo), cudaMemcpyHostToDevice, ctx->stream2));
                     ev_new(hevs, ctx->stream2);
-                    CU(ctx, cudaStreamWaitEvent(ctx->stream, hevs.back(), 0));
                     copied_hi = sb.hi;
                 }
             }
+            ev_new(cpevs, ctx->stream2);
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, cpevs.back(), 0));
             uint32_t *qs = sc.counters + ci * 4;
             ci++;
             k1a_ev.push_back(evs.size());
             ev_new(evs, ctx->stream);                                     // before K1a
-            if (!first_ev) first_ev = evs.back();
+            if (!first_ev) { first_ev = evs.back(); t_first = since(); }
             // table capacities: the super-chunk's maxima (dupcnt rows are strided by the launch's capacity)
             CU(ctx, launch_hash_dedup(ctx->stream, d_bases, dd, sb.begin, sb.n, sb.first_long, max_k_short, max_k_long, k, filter_unweighted(flt, p.unweighted), flt, sc, qs, &launches));
             ev_new(evs, ctx->stream);                                     // after K1a
@@ -242,12 +262,45 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         // ---- K1b: one launch over the whole super-chunk ----
         k1b_ev.push_back(evs.size());
         ev_new(evs, ctx->stream);
-        if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n_all, k, H, sc, d_minhash, flt.light_weight, sc.counters + (n_chunks + 2) * 4, &launches));
+        if (d_minhash && passes > 1) {
+            if (!ctx->t512.p) {   // step^512 as eight byte-indexed tables (the map is linear over GF(2))
+                std::vector<uint64_t> t(8 * 256);
+                for (int b = 0; b < 8; b++)
+                    for (int v = 0; v < 256; v++) {
+                        uint64_t x = (uint64_t)v << (8 * b);
+                        for (int i = 0; i < 512; i++) { x ^= x << 21; x ^= x >> 35; x ^= x << 4; }   // MinHashSketch.java:140-143
+                        t[(size_t)b * 256 + v] = x;
+                    }
+                CU(ctx, ctx->t512.ensure(t.size() * 8));
+                CU(ctx, cudaMemcpyAsync(ctx->t512.p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+                CU(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            // virtual strands, block-major: v = p * n_all + i
+            CU(ctx, ctx->h_vdesc.ensure((size_t)n_all * passes * sizeof(StrandDesc)));
+            CU(ctx, ctx->vdesc.ensure((size_t)n_all * passes * sizeof(StrandDesc)));
+            StrandDesc *hv = ctx->h_vdesc.as<StrandDesc>();
+            for (int pp = 0; pp < passes; pp++)
+                for (int i = 0; i < n_all; i++) {
+                    StrandDesc v = hd[i];
+                    v.base_off = hd[i].koff;                              // the strand's hashes and weights
+                    v.koff = (uint64_t)pp * total_k + hd[i].koff;         // this block's chain starts
+                    v.rc = (uint32_t)std::min(512, H - 512 * pp);         // words in the block
+                    v.slot = (uint32_t)(512 * pp);                        // first word
+                    hv[(size_t)pp * n_all + i] = v;
+                }
+            CU(ctx, cudaMemcpyAsync(ctx->vdesc.p, hv, (size_t)n_all * passes * sizeof(StrandDesc), cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, launch_advance_keys(ctx->stream, dd, n_all, k, sc, ctx->t512.as<uint64_t>(), total_k, passes, flt.light_weight, &launches));
+            CU(ctx, launch_minhash_virtual(ctx->stream, ctx->vdesc.as<StrandDesc>(), n_all * passes, n_all, k, H, sc, d_minhash, flt.light_weight,
+                                           sc.counters + (n_chunks + 2) * 4, &launches));
+        } else if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n_all, k, H, sc, d_minhash, flt.light_weight, sc.counters + (n_chunks + 2) * 4, &launches));
         ev_new(evs, ctx->stream);
         last_ev = evs.back();
         if (pos < all.size()) CU(ctx, cudaStreamSynchronize(ctx->stream));   // the next super-chunk reuses desc / keys / the pinned plan
     }
+    t_enq = since();
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (trace) fprintf(stderr, "[mhapb] sketch_core host ms: strands planned %.2f, first K1a enqueued %.2f, all enqueued %.2f, synced %.2f (h2d %s)\n",
+                       t_plan, t_first, t_enq, since(), h_bases ? "per chunk" : "none");
     for (size_t i : k1a_ev) {
         float a = 0, c = 0;
         cudaEventElapsedTime(&a, evs[i], evs[i + 1]); cudaEventElapsedTime(&c, evs[i + 1], evs[i + 2]);
@@ -256,6 +309,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     for (size_t i : k1b_ev) { float b = 0; cudaEventElapsedTime(&b, evs[i], evs[i + 1]); ctx->timing.minhash_ms += b; }
     for (size_t i = 0; i + 1 < hevs.size(); i += 2) { float c = 0; cudaEventElapsedTime(&c, hevs[i], hevs[i + 1]); ctx->timing.h2d_ms += c; }
     for (auto e : hevs) cudaEventDestroy(e);
+    for (auto e : cpevs) cudaEventDestroy(e);
     if (first_ev && last_ev) { float t = 0; cudaEventElapsedTime(&t, first_ev, last_ev); ctx->timing.sketch_total_ms += t; }
     for (auto e : evs) cudaEventDestroy(e);
     ctx->timing.kernel_launches += launches;
@@ -698,7 +752,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
     for (auto b : bufs) b->release();
     DevBuf *more[] = {&ctx->ovf_q, &ctx->store.fwd_list, &ctx->store.present, &ctx->g_minhash, &ctx->g_ord, &ctx->g_ordn, &ctx->g_lenk, &ctx->g_len, &ctx->g_id, &ctx->g_pack, &ctx->g_small};
     for (auto b : more) b->release();
-    ctx->h_cand.release(); ctx->h_ovl.release(); ctx->h_desc.release();
+    ctx->h_cand.release(); ctx->h_ovl.release(); ctx->h_desc.release(); ctx->h_vdesc.release(); ctx->t512.release(); ctx->vdesc.release();
     comm_release(ctx);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);

@@ -99,7 +99,8 @@ struct mhapb_ctx {
     // search scratch
     mhapb::DevBuf ovf_q;
     mhapb::PinnedBuf h_cand, h_ovl;               // pinned landing buffers of the surviving pairs
-    mhapb::PinnedBuf h_desc;                      // pinned plan of the strand descriptors (sketch_core)
+    mhapb::PinnedBuf h_desc, h_vdesc;             // pinned plan of the strand descriptors (sketch_core)
+    mhapb::DevBuf t512, vdesc;                    // step^512 tables and the virtual strands of sketches wider than 512 words
     uint64_t cand_cap_hint = 0; uint32_t ovf_threads_hint = 0;   // sizes the previous search needed
     mhapb::DevBuf qlist, cand, ovl, cand2, ovl2, ovf_list, fscratch, scounters, tmp_start, block_sums, q_minhash, q_ord, q_ordn, q_lenk, q_len, q_id, eq;
     mhapb::Store store;

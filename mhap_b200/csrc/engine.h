@@ -67,6 +67,11 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
 // own weight), per-word signed minimum -> minhash rows.
 cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
                            const SketchScratch &sc, int32_t *d_minhash, uint32_t light_weight, uint32_t *queue, int *launches);
+// sketches wider than 512 words: chain starts of the later word blocks + the launch over virtual strands (sketch.cu)
+cudaError_t launch_advance_keys(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, const SketchScratch &sc, const uint64_t *d_t512,
+                                uint64_t total_k, int passes, uint32_t light_w, int *launches);
+cudaError_t launch_minhash_virtual(cudaStream_t st, const StrandDesc *d_vdesc, int n_virtual, int n_real, int k, int hstride,
+                                   const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, uint32_t *queue, int *launches);
 // K1c: MurmurHash3_x86_32 of every ordered k-mer, bottom-S by (signed hash, position), sorted.
 cudaError_t launch_ordered(cudaStream_t st, const uint8_t *d_bases, const StrandDesc *d_desc, int s_base, int n_strands,
                            int first_long, int max_len_short, int max_len_long, int ok, int S, int ord_stride,

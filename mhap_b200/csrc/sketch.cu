@@ -13,6 +13,7 @@
 #include "bs_step.cuh"
 #include "bs_filter.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace mhapb {
@@ -283,9 +284,12 @@ __device__ __forceinline__ void xorshift_step32(uint32_t &lo, uint32_t &hi)
     lo = (uint32_t)x; hi = (uint32_t)(x >> 32);
 }
 
+// keys: the k-mer hashes (what ends up in the sketch); xkeys: the chain states the H words of this pass start from -- the same
+// array for words 0..511, the hashes advanced by 512*weight steps per earlier pass for a later block of words (k_advance_keys)
 template <int B, bool WEIGHTED>
-__device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ wts,
-                                                 int n, int dir /* +1 light, -1 heavy */, uint64_t *kring, uint32_t *wbuf, int lane,
+__device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ xkeys,
+                                                 const uint32_t *__restrict__ wts,
+                                                 int n, int dir /* +1 light, -1 heavy */, uint64_t *kring, uint64_t *xring, uint32_t *wbuf, int lane,
                                                  uint32_t uniform_w = 1 /* WEIGHTED with wts == nullptr: every key has this weight */)
 {
     constexpr int G = B < 4 ? B : 4;   // steps per rare-path check
@@ -299,9 +303,9 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
     for (int t0 = 0; t0 < total; t0 += 32) {
         {
             int e = t0 + lane;
-            uint64_t mk = 0; uint32_t mw = 1;
-            if (e < n) { mk = keys[(long long)dir * e]; if (WEIGHTED) mw = wts ? wts[(long long)dir * e] : uniform_w; }
-            kring[e & 63] = mk;
+            uint64_t mk = 0, mx = 0; uint32_t mw = 1;
+            if (e < n) { mk = keys[(long long)dir * e]; mx = xkeys[(long long)dir * e]; if (WEIGHTED) mw = wts ? wts[(long long)dir * e] : uniform_w; }
+            kring[e & 63] = mk; xring[e & 63] = mx;
             if (WEIGHTED) wbuf[lane] = mw;
         }
         __syncwarp();
@@ -309,7 +313,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
 #pragma unroll 1
         for (int j = 0; j < jn; j++) {
             const uint32_t il = __shfl_up_sync(kFull, xl, 1), ih = __shfl_up_sync(kFull, xh, 1);
-            const uint64_t kin = kring[(t0 + j) & 63];
+            const uint64_t kin = xring[(t0 + j) & 63];
             xl = lane == 0 ? (uint32_t)kin : il;
             xh = lane == 0 ? (uint32_t)(kin >> 32) : ih;
             if (WEIGHTED) {
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(256)
 k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
           int32_t *__restrict__ minhash, uint32_t *queue, uint32_t light_w)
 {
-    __shared__ uint64_t s_kbuf[8][64];
+    __shared__ uint64_t s_kbuf[8][64], s_xbuf[8][64];
     __shared__ uint32_t s_wbuf[8][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (;;) {
@@ -391,10 +395,10 @@ k_minhash(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, Sket
         for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
         const uint64_t *keys = sc.keys + d.koff;
         const int nl = sc.nlight[s], nh = sc.nheavy[s];
-        if (light_w == 1) minhash_pipeline<B, false>(m, keys, nullptr, nl, +1, s_kbuf[wib], s_wbuf[wib], lane);
-        else              minhash_pipeline<B, true>(m, keys, nullptr, nl, +1, s_kbuf[wib], s_wbuf[wib], lane, light_w);
+        if (light_w == 1) minhash_pipeline<B, false>(m, keys, keys, nullptr, nl, +1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane);
+        else              minhash_pipeline<B, true>(m, keys, keys, nullptr, nl, +1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane, light_w);
         if (nh > 0)
-            minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
+            minhash_pipeline<B, true>(m, keys + (nk - 1), keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane);
         int32_t *row = minhash + (size_t)d.row * H;
 #pragma unroll
         for (int b = 0; b < B; b++) {
@@ -471,6 +475,7 @@ struct BsState {           // lane-private exact state in shared memory, element
     uint32_t *hi, *lo, *out, *tap;
 };
 
+#ifdef MHAPB_AB_KERNELS   // the superseded bit-sliced systolic kernel, kept for A/B runs only (make AB=1)
 template <int B>
 __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
                                          uint32_t *stage /* [64][kBsStage] */, uint32_t *scratch /* [64] */, int lane)
@@ -576,6 +581,8 @@ __device__ __forceinline__ void bs_phase(const BsState &st, const uint64_t *__re
     }
 }
 
+#endif
+
 // ---- lock-step variant of the bit-sliced phase (the default) --------------------------------------
 // Instead of handing bundles from lane to lane, every lane keeps its own bundle for the whole chain and the
 // 32 lanes walk the H words in lock step, so at any moment the whole warp works on ONE word: its exact
@@ -599,7 +606,8 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t a) { uint32_t v; asm vo
 
 // MULTI: every key advances light_w (> 1) steps per word, each of them compared (a uniform tf-idf weight, MinHashSketch.java:138)
 template <bool MULTI>
-__device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, const uint64_t *__restrict__ keys /* 32*nb keys */, int nb,
+__device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, const uint64_t *__restrict__ keys /* 32*nb chain starts */,
+                                                  const uint64_t *__restrict__ okeys /* the k-mer hashes behind them */, int nb,
                                                   uint32_t hpb /* bytes between the per-word arrays hi|lo|out|depth|scratch */, int lane, int light_w)
 {
     uint32_t R[64];
@@ -670,7 +678,7 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
                     if ((int32_t)xh < bh || ((int32_t)xh == bh && xl < lds_u32(daddr - 2u * hpb))) {   // MinHashSketch.java:144, uniform
                         __syncwarp();
                         if (lane == L) {
-                            const uint64_t key = keys[(size_t)(r0 + L) * 32 + (31 - sb)];
+                            const uint64_t key = okeys[(size_t)(r0 + L) * 32 + (31 - sb)];
                             sts_u32(daddr - 3u * hpb, xh); sts_u32(daddr - 2u * hpb, xl);
                             sts_u32(daddr - hpb, (wd & 1) ? (uint32_t)(key >> 32) : (uint32_t)key);   // :146-149
                             sts_u32(daddr, bs_code_of(xh));
@@ -690,14 +698,20 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
     }
 }
 
+// virt != 0: the descriptors are VIRTUAL strands, one per block of <= 512 words of a sketch wider than 512 (--num-hashes 1024:
+// two per strand).  Block p starts its chains from the k-mer hashes advanced by 512*p*weight steps (k_advance_keys), so it
+// is an ordinary 512-word job that runs in the B = 16 instantiation (94 registers, 20 warps per SM) instead of the B = 32 one
+// (158 registers, 12 warps per SM, int_issue 0.56).  Field use in a virtual descriptor: koff = the advanced keys, base_off =
+// offset of the strand's hashes and weights, rc = words in this block, slot = first word, row as usual; nlight / nheavy are
+// those of strand s % n_real.
 template <int B, bool MULTI>
 __global__ void __launch_bounds__(128, B <= 16 ? 5 : (B <= 32 ? 3 : 1))
 k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
-              int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys, int light_w)
+              int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys, int light_w, int virt, int n_real, int hstride)
 {
-    // per warp: state [4][B*32] | scratch [64] ; static: key ring + weights for the scalar pipeline
+    // per warp: state [4][B*32] | scratch [64] ; static: key rings + weights for the scalar pipeline
     extern __shared__ __align__(16) uint32_t s_dyn[];
-    __shared__ uint64_t s_kbuf[4][64];
+    __shared__ uint64_t s_kbuf[4][64], s_xbuf[4][64];
     __shared__ uint32_t s_wbuf[4][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr int HP = B * 32;
@@ -705,7 +719,6 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
     uint32_t *wbase = s_dyn + (size_t)wib * kPerWarp;
     BsShared st;
     st.hi = wbase; st.lo = wbase + HP; st.out = wbase + 2 * HP; st.depth = wbase + 3 * HP;
-    uint32_t *scratch = wbase + 4 * HP;
     for (;;) {
         int s = 0;
         if (lane == 0) s = (int)atomicAdd(queue, 1u);
@@ -713,8 +726,12 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
         if (s >= n_strands) break;
         const StrandDesc d = desc[s];
         const int nk = (int)d.len - k + 1;
-        const uint64_t *keys = sc.keys + d.koff;
-        const int nl = sc.nlight[s], nh = sc.nheavy[s];
+        const int hloc = virt ? (int)d.rc : H;                               // words of this job
+        const int si = virt ? s % n_real : s;
+        const uint64_t *keys = sc.keys + d.koff;                             // chain starts
+        const uint64_t *okeys = virt ? sc.keys + d.base_off : keys;          // the k-mer hashes
+        const uint32_t *wts = sc.wts + (virt ? d.base_off : d.koff);
+        const int nl = sc.nlight[si], nh = sc.nheavy[si];
         // full bundles, taken from the end; at least scalar_keys keys stay scalar, and when more than one warp-wide set
         // of 32 bundles is available only whole sets are taken (a partial set costs a whole set's plane steps), so
         // between scalar_keys and scalar_keys + 1023 keys go through the scalar pipeline
@@ -724,11 +741,11 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
         LaneMins<B> m;
 #pragma unroll
         for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
-        if constexpr (!MULTI) minhash_pipeline<B, false>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane);
-        else                  minhash_pipeline<B, true>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane, (uint32_t)light_w);
+        if constexpr (!MULTI) minhash_pipeline<B, false>(m, okeys, keys, nullptr, n_sc, +1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane);
+        else                  minhash_pipeline<B, true>(m, okeys, keys, nullptr, n_sc, +1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane, (uint32_t)light_w);
         if (nh > 0)
-            minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
-        int32_t *row = minhash + (size_t)d.row * H;
+            minhash_pipeline<B, true>(m, okeys + (nk - 1), keys + (nk - 1), wts + (nk - 1), nh, -1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane);
+        int32_t *row = minhash + (size_t)d.row * hstride + (virt ? (int)d.slot : 0);
         if (nb > 0) {
             __syncwarp();
 #pragma unroll
@@ -738,17 +755,44 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
                 st.depth[word] = bs_code_of((uint32_t)m.hi[b]);
             }
             __syncwarp();
-            bs_phase_lockstep<MULTI>(st, H, keys + n_sc, nb, (uint32_t)HP * 4u, lane, light_w);
+            bs_phase_lockstep<MULTI>(st, hloc, keys + n_sc, okeys + n_sc, nb, (uint32_t)HP * 4u, lane, light_w);
             __syncwarp();
-            for (int word = lane; word < H; word += 32) row[word] = (int32_t)st.out[word];
+            for (int word = lane; word < hloc; word += 32) row[word] = (int32_t)st.out[word];
             __syncwarp();
         } else {
 #pragma unroll
-            for (int b = 0; b < B; b++) { int word = lane * B + b; if (word < H) row[word] = m.out[b]; }
+            for (int b = 0; b < B; b++) { int word = lane * B + b; if (word < hloc) row[word] = m.out[b]; }
         }
     }
 }
 
+// Chain states for the later word blocks of a wide sketch: block p of a key of weight w starts at step^(512*p*w)(hash).  step^512
+// is a fixed linear map over GF(2): eight table look-ups (one per byte of the state) and seven XORs (c_t512, built on the host).
+__global__ void k_advance_keys(const StrandDesc *__restrict__ desc, int n_strands, int k, SketchScratch sc, const uint64_t *__restrict__ t512,
+                               uint64_t total_k, int passes, uint32_t light_w)
+{
+    for (int s = blockIdx.x; s < n_strands; s += gridDim.x) {
+        const StrandDesc d = desc[s];
+        const int nk = (int)d.len - k + 1;
+        const int nl = sc.nlight[s], nh = sc.nheavy[s];
+        for (int j = threadIdx.x; j < nl + nh; j += blockDim.x) {
+            const size_t idx = d.koff + (j < nl ? (size_t)j : (size_t)(nk - 1 - (j - nl)));
+            const uint32_t w = j < nl ? light_w : sc.wts[idx];
+            uint64_t x = sc.keys[idx];
+            for (int p = 1; p < passes; p++) {
+                for (uint32_t t = 0; t < w; t++) {
+                    uint64_t y = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) y ^= __ldg(&t512[b * 256 + ((x >> (8 * b)) & 0xff)]);
+                    x = y;
+                }
+                sc.keys[(size_t)p * total_k + idx] = x;
+            }
+        }
+    }
+}
+
+#ifdef MHAPB_AB_KERNELS
 template <int B>
 __global__ void __launch_bounds__(128, B <= 16 ? 4 : 2)
 k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
@@ -778,9 +822,9 @@ k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, S
         LaneMins<B> m;
 #pragma unroll
         for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
-        minhash_pipeline<B, false>(m, keys, nullptr, n_sc, +1, s_kbuf[wib], s_wbuf[wib], lane);
+        minhash_pipeline<B, false>(m, keys, keys, nullptr, n_sc, +1, s_kbuf[wib], s_kbuf[wib], s_wbuf[wib], lane);
         if (nh > 0)
-            minhash_pipeline<B, true>(m, keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_wbuf[wib], lane);
+            minhash_pipeline<B, true>(m, keys + (nk - 1), keys + (nk - 1), sc.wts + d.koff + (nk - 1), nh, -1, s_kbuf[wib], s_kbuf[wib], s_wbuf[wib], lane);
         int32_t *row = minhash + (size_t)d.row * H;
         if (nb > 0) {
 #pragma unroll
@@ -800,6 +844,8 @@ k_minhash_bs(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, S
         }
     }
 }
+
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K1c: ordered bottom-S sketch
@@ -1177,8 +1223,10 @@ static int k1b_variant()
 
 template <int B>
 static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
-                                    const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, uint32_t *queue)
+                                    const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, uint32_t *queue,
+                                    int virt = 0, int n_real = 0, int hstride = 0)
 {
+    if (!hstride) hstride = H;
     cudaError_t e;
     int per_sm = 0;
     // the two A/B variants (MHAPB_K1B) only implement light weight 1; a uniform tf-idf weight takes the default kernels
@@ -1196,9 +1244,10 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         if (grid > need) grid = need;
         static int scalar_keys2 = -1;
         if (scalar_keys2 < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys2 = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys2 < 0) scalar_keys2 = 0; }
-        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, scalar_keys2, (int)light_w);
+        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, scalar_keys2, (int)light_w, virt, n_real, hstride);
         return cudaGetLastError();
     }
+#ifdef MHAPB_AB_KERNELS
     if (variant == 1 && B <= 32) {
         const size_t smem = (size_t)4 * (4 * B * 32 + 64 * kBsStage + 64) * 4;
         e = cudaFuncSetAttribute(k_minhash_bs<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1214,6 +1263,7 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         k_minhash_bs<B><<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, scalar_keys);
         return cudaGetLastError();
     }
+#endif
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minhash<B>, 256, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
@@ -1222,6 +1272,25 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
     if (grid > need) grid = need;
     k_minhash<B><<<grid, 256, 0, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, light_w);
     return cudaGetLastError();
+}
+
+// the later word blocks' chain starts (see k_minhash_bs2 / k_advance_keys)
+cudaError_t launch_advance_keys(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, const SketchScratch &sc, const uint64_t *d_t512,
+                                uint64_t total_k, int passes, uint32_t light_w, int *launches)
+{
+    if (n_strands <= 0 || passes < 2) return cudaSuccess;
+    k_advance_keys<<<std::min(n_strands, sm_count() * 16), 256, 0, st>>>(d_desc, n_strands, k, sc, d_t512, total_k, passes, light_w);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
+// virtual strands: n_virtual descriptors of <= 512 words each, rows of hstride words (always the B = 16 instantiation)
+cudaError_t launch_minhash_virtual(cudaStream_t st, const StrandDesc *d_vdesc, int n_virtual, int n_real, int k, int hstride,
+                                   const SketchScratch &sc, int32_t *d_minhash, uint32_t light_w, uint32_t *queue, int *launches)
+{
+    if (n_virtual <= 0) return cudaSuccess;
+    (*launches)++;
+    return launch_minhash_b<16>(st, d_vdesc, n_virtual, k, 512, sc, d_minhash, light_w, queue, 1, n_real, hstride);
 }
 
 cudaError_t launch_minhash(cudaStream_t st, const StrandDesc *d_desc, int n_strands, int k, int H,
