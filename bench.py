@@ -446,8 +446,9 @@ def _main(args, real_stdout):
         out["cpu_baseline"] = {"value": n * L / 1e9 / (ts + tq), "unit": "Gbases/s", "cores": cores, "kind": "port",
                                "sample": f"first {n} of {total_reads} reads x {L} bp, sketch+index+self-search, {cores} threads, {ts + tq:.1f} s",
                                "sketch_gbases_per_s": n * L / 1e9 / ts, "overlaps_per_s": cst["fully_compared"] / tq if tq > 0 else None}
-        if parity is not None and world == 1:
-            # the same sample through the CUDA path: complete hit set + counters against the oracle's
+        if parity is not None:
+            # the same sample (the first n reads of rank 0's shard, a self-contained job at this config's shape) through the CUDA
+            # path: complete hit set + counters against the oracle's
             e1 = native.Engine(local)
             e1.store_reset(p)
             e1.store_add_reads(bases[: n * L], offsets[: n + 1])

@@ -286,7 +286,7 @@ __device__ __forceinline__ void xorshift_step32(uint32_t &lo, uint32_t &hi)
 
 // keys: the k-mer hashes (what ends up in the sketch); xkeys: the chain states the H words of this pass start from -- the same
 // array for words 0..511, the hashes advanced by 512*weight steps per earlier pass for a later block of words (k_advance_keys)
-template <int B, bool WEIGHTED>
+template <int B, bool WEIGHTED, bool XK = false /* xkeys differ from keys */>
 __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ xkeys,
                                                  const uint32_t *__restrict__ wts,
                                                  int n, int dir /* +1 light, -1 heavy */, uint64_t *kring, uint64_t *xring, uint32_t *wbuf, int lane,
@@ -304,8 +304,9 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
         {
             int e = t0 + lane;
             uint64_t mk = 0, mx = 0; uint32_t mw = 1;
-            if (e < n) { mk = keys[(long long)dir * e]; mx = xkeys[(long long)dir * e]; if (WEIGHTED) mw = wts ? wts[(long long)dir * e] : uniform_w; }
-            kring[e & 63] = mk; xring[e & 63] = mx;
+            if (e < n) { mk = keys[(long long)dir * e]; if (XK) mx = xkeys[(long long)dir * e]; if (WEIGHTED) mw = wts ? wts[(long long)dir * e] : uniform_w; }
+            kring[e & 63] = mk;
+            if (XK) xring[e & 63] = mx;
             if (WEIGHTED) wbuf[lane] = mw;
         }
         __syncwarp();
@@ -313,7 +314,7 @@ __device__ __forceinline__ void minhash_pipeline(LaneMins<B> &m, const uint64_t 
 #pragma unroll 1
         for (int j = 0; j < jn; j++) {
             const uint32_t il = __shfl_up_sync(kFull, xl, 1), ih = __shfl_up_sync(kFull, xh, 1);
-            const uint64_t kin = xring[(t0 + j) & 63];
+            const uint64_t kin = XK ? xring[(t0 + j) & 63] : kring[(t0 + j) & 63];
             xl = lane == 0 ? (uint32_t)kin : il;
             xh = lane == 0 ? (uint32_t)(kin >> 32) : ih;
             if (WEIGHTED) {
@@ -704,14 +705,14 @@ __device__ __forceinline__ void bs_phase_lockstep(const BsShared &st, int H, con
 // (158 registers, 12 warps per SM, int_issue 0.56).  Field use in a virtual descriptor: koff = the advanced keys, base_off =
 // offset of the strand's hashes and weights, rc = words in this block, slot = first word, row as usual; nlight / nheavy are
 // those of strand s % n_real.
-template <int B, bool MULTI>
+template <int B, bool MULTI, bool virt>
 __global__ void __launch_bounds__(128, B <= 16 ? 5 : (B <= 32 ? 3 : 1))
 k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, SketchScratch sc,
-              int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys, int light_w, int virt, int n_real, int hstride)
+              int32_t *__restrict__ minhash, uint32_t *queue, int scalar_keys, int light_w, int n_real, int hstride)
 {
     // per warp: state [4][B*32] | scratch [64] ; static: key rings + weights for the scalar pipeline
     extern __shared__ __align__(16) uint32_t s_dyn[];
-    __shared__ uint64_t s_kbuf[4][64], s_xbuf[4][64];
+    __shared__ uint64_t s_kbuf[4][64], s_xbuf[virt ? 4 : 1][64];
     __shared__ uint32_t s_wbuf[4][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr int HP = B * 32;
@@ -741,10 +742,11 @@ k_minhash_bs2(const StrandDesc *__restrict__ desc, int n_strands, int k, int H, 
         LaneMins<B> m;
 #pragma unroll
         for (int b = 0; b < B; b++) { m.hi[b] = 0x7fffffff; m.lo[b] = 0xffffffffu; m.out[b] = 0; }   // Long.MAX_VALUE
-        if constexpr (!MULTI) minhash_pipeline<B, false>(m, okeys, keys, nullptr, n_sc, +1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane);
-        else                  minhash_pipeline<B, true>(m, okeys, keys, nullptr, n_sc, +1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane, (uint32_t)light_w);
+        uint64_t *xr = s_xbuf[virt ? wib : 0];
+        if constexpr (!MULTI) minhash_pipeline<B, false, virt>(m, okeys, keys, nullptr, n_sc, +1, s_kbuf[wib], xr, s_wbuf[wib], lane);
+        else                  minhash_pipeline<B, true, virt>(m, okeys, keys, nullptr, n_sc, +1, s_kbuf[wib], xr, s_wbuf[wib], lane, (uint32_t)light_w);
         if (nh > 0)
-            minhash_pipeline<B, true>(m, okeys + (nk - 1), keys + (nk - 1), wts + (nk - 1), nh, -1, s_kbuf[wib], s_xbuf[wib], s_wbuf[wib], lane);
+            minhash_pipeline<B, true, virt>(m, okeys + (nk - 1), keys + (nk - 1), wts + (nk - 1), nh, -1, s_kbuf[wib], xr, s_wbuf[wib], lane);
         int32_t *row = minhash + (size_t)d.row * hstride + (virt ? (int)d.slot : 0);
         if (nb > 0) {
             __syncwarp();
@@ -1233,7 +1235,9 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
     const int variant = light_w == 1 ? k1b_variant() : 2;
     if (variant == 2 && B <= 32) {
         const size_t smem = (size_t)4 * (4 * B * 32 + 64) * 4;
-        auto kern = light_w == 1 ? k_minhash_bs2<B, false> : k_minhash_bs2<B, true>;
+        auto kern = virt ? (light_w == 1 ? k_minhash_bs2<B, false, B == 16> : k_minhash_bs2<B, true, B == 16>)
+                         : (light_w == 1 ? k_minhash_bs2<B, false, false> : k_minhash_bs2<B, true, false>);
+        if (virt && B != 16) return cudaErrorInvalidValue;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
@@ -1244,7 +1248,7 @@ static cudaError_t launch_minhash_b(cudaStream_t st, const StrandDesc *d_desc, i
         if (grid > need) grid = need;
         static int scalar_keys2 = -1;
         if (scalar_keys2 < 0) { const char *ev = getenv("MHAPB_BS_SCALAR_KEYS"); scalar_keys2 = ev ? atoi(ev) : kBsScalarKeys; if (scalar_keys2 < 0) scalar_keys2 = 0; }
-        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, scalar_keys2, (int)light_w, virt, n_real, hstride);
+        kern<<<grid, 128, smem, st>>>(d_desc, n_strands, k, H, sc, d_minhash, queue, scalar_keys2, (int)light_w, n_real, hstride);
         return cudaGetLastError();
     }
 #ifdef MHAPB_AB_KERNELS
