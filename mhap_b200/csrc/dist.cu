@@ -23,6 +23,7 @@
 
 #include <nccl.h>     // types and enums only; every symbol is resolved with dlsym below
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -79,6 +80,14 @@ NcclApi *nccl_api()
     });
     return &api;
 }
+
+// NCCL prints its version banner with printf when the first communicator is created (NCCL_DEBUG=VERSION/WARN/INFO); stdout
+// is the overlap stream of the command-line driver, so fd 1 points at stderr for the duration of the initialisation
+struct StdoutToStderr {
+    int saved;
+    StdoutToStderr() { fflush(stdout); saved = dup(1); if (saved >= 0) dup2(2, 1); }
+    ~StdoutToStderr() { if (saved >= 0) { fflush(stdout); dup2(saved, 1); close(saved); } }
+};
 
 #define NC(ctx, call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return fail(ctx, MHAPB_ECOMM, "%s: %s (%s:%d)", #call, nccl_api()->GetErrorString(r__), __FILE__, __LINE__); } while (0)
 
@@ -294,7 +303,10 @@ int mhapb_comm_init_rank(mhapb_ctx *ctx, const uint8_t *id, int rank, int nranks
     CU(ctx, cudaSetDevice(ctx->device));
     ncclUniqueId u; memcpy(&u, id, sizeof u);
     ncclComm_t comm = nullptr;
-    NC(ctx, N->CommInitRank(&comm, nranks, u, rank));
+    {
+        StdoutToStderr guard;
+        NC(ctx, N->CommInitRank(&comm, nranks, u, rank));
+    }
     return comm_attach(ctx, comm, rank, nranks);
 }
 
@@ -309,12 +321,15 @@ int mhapb_comm_init_all(mhapb_ctx **ctxs, int n)
     ncclUniqueId u;
     NC(c0, N->GetUniqueId(&u));
     std::vector<ncclComm_t> comms(n, nullptr);
-    NC(c0, N->GroupStart());
-    for (int i = 0; i < n; i++) {
-        CU(c0, cudaSetDevice(ctxs[i]->device));
-        NC(c0, N->CommInitRank(&comms[i], n, u, i));
+    {
+        StdoutToStderr guard;
+        NC(c0, N->GroupStart());
+        for (int i = 0; i < n; i++) {
+            CU(c0, cudaSetDevice(ctxs[i]->device));
+            NC(c0, N->CommInitRank(&comms[i], n, u, i));
+        }
+        NC(c0, N->GroupEnd());
     }
-    NC(c0, N->GroupEnd());
     for (int i = 0; i < n; i++) {
         CU(c0, cudaSetDevice(ctxs[i]->device));
         int rc = comm_attach(ctxs[i], comms[i], i, n);
