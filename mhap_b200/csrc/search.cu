@@ -793,7 +793,11 @@ __global__ void __launch_bounds__(SM ? 224 : 128) k_filter_warp(FilterArgs a, in
             int total;
             const int off = warp_excl_scan(mine, lane, &total);
             count = total;
-            if (total == 0) break;
+            // Fewer than three records cannot end as an overlap: computeEdges needs >= 3 valid ones (:125) and neither the second
+            // pass nor optimizeShifts adds any -- a hash value yields one record, or two when one side holds a run of equal hashes
+            // inside its window, and the second pass only narrows the windows (its matching hashes and runs are subsets of the
+            // first pass's, whose shift test rejects nothing).  Most candidates of unrelated reads stop here, after one merge.
+            if (total < 3) { count = 0; break; }
             if (total > kFwRecCap) { overflow = true; break; }
             const bool fits = __all_sync(kFull, mine <= kFwLaneCap) && total <= kFwRecCap / 2;
             __syncwarp();
