@@ -122,121 +122,247 @@ __device__ __forceinline__ uint32_t kmer_weight(const KmerFilterView &f, uint64_
 // ---------------------------------------------------------------------------------------------
 // K1a: k-mer hashing + exact de-duplication with counts
 // ---------------------------------------------------------------------------------------------
-// One CTA per strand (persistent, work queue).  Distinct hashes go into an open-addressed table
-// (shared memory for strands up to kShortMaxKmers k-mers, HBM scratch beyond); a repeat occurrence
-// bumps a per-slot counter in HBM that is zero between uses (touched only for duplicated k-mers).
-// Output per strand: keys[koff .. koff+nlight) weight-1 hashes, keys[koff+nk-1 .. ] (downwards)
-// the hashes with weight > 1 and their weights.  Order is irrelevant: the XORShift map is a
+// One CTA per strand (persistent, work queue).  Output per strand: keys[koff .. koff+nlight) the hashes of the launch's
+// light weight, keys[koff+nk-1 .. ] (downwards) the others with their weights.  Order is irrelevant: the XORShift map is a
 // bijection, so two distinct keys never tie in the min.
+//
+// Two de-duplication schemes:
+//  * TABLE (round 1; long strands, and the fallback for low-complexity short ones): every hash goes into an open-addressed
+//    table (64-bit CAS), a repeat occurrence bumps a per-slot counter, then the table is scanned.
+//  * BITMAP (short strands, the default): duplicates are rare, so they are isolated first.  Pass 1 hashes every k-mer once
+//    into a shared array and sets one bit per hash in a bitmap of >= 6 bits per k-mer; a k-mer that finds its bit already set
+//    is LATE (a repeat of an earlier k-mer, or a chance collision: n^2/2m, ~7 % of the k-mers).  Only the late ones go into a
+//    small exact table with counts (pass 2); every other k-mer then looks its hash up in that table (pass 3): found = an
+//    earlier occurrence of a repeated k-mer (counted), not found = unique, written out at once.  The table scan emits the
+//    repeated k-mers with their counts.  Per k-mer this is one 32-bit atomicOr + one table look-up instead of a CAS insert
+//    into a 12 k-slot table and a scan of that table with two cursor bumps per slot.
+
+// the TABLE scheme on one strand; table / dupmask in shared (LONG = false) or global (LONG = true) memory, characters through `src`
+template <bool LONG, int KC, class Src>
+__device__ __forceinline__ void dedup_table_strand(const Src &src, const StrandDesc &d, int s, int k, int unweighted, uint64_t *table, uint32_t *dupmask,
+                                                   uint32_t *dupcnt, uint32_t table_cap, const SketchScratch &sc, const KmerFilterView &flt,
+                                                   int *s_nlight, int *s_nheavy, int *s_special)
+{
+    const int nk = (int)d.len - k + 1;
+    // table sized for this strand (load factor <= 0.8)
+    uint32_t C = dedup_table_slots((uint32_t)nk);
+    if (C > table_cap) C = table_cap;
+    for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) table[i] = kEmptyKey;
+    if (!LONG) for (uint32_t i = threadIdx.x; i < (C + 31) / 32; i += blockDim.x) dupmask[i] = 0;
+    __syncthreads();
+    // uniform trip count + __syncwarp: the CAS probe below is a data-dependent loop and without an
+    // explicit reconvergence point the lanes of a warp stay split for the rest of the strand
+    for (int base = 0; base < nk; base += blockDim.x) {
+        const int i = base + (int)threadIdx.x;
+        if (i < nk) {
+            const uint64_t h = murmur3_128_h1_chars([&](int j) { return src(i + j); }, KC ? KC : k);
+            if (flt.remove_unique == 1 && !bloom_might_contain(flt, h)) { /* keepKmer false (MinHashSketch.java:70-71) */ }
+            else if (h == kEmptyKey) atomicAdd(s_special, 1);
+            else {
+                // open addressing with double hashing: the stride is a power of two picked by three hash bits (C is odd,
+                // so every stride is a full cycle); a plain load looks at the slot first and the CAS is only issued on
+                // an empty one.
+                uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * C) >> 32);
+                uint32_t stride = 1u << ((uint32_t)h & 7u);
+                if (stride >= C) stride = 1u;   // tiny strands: keep slot + stride - C inside the table
+                for (;;) {
+                    unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&table[slot]);
+                    if (old == kEmptyKey)
+                        old = atomicCAS(reinterpret_cast<unsigned long long *>(&table[slot]), (unsigned long long)kEmptyKey, (unsigned long long)h);
+                    if (old == kEmptyKey) break;
+                    if (old == h) {
+                        if (!unweighted) {
+                            if (!LONG) atomicOr(&dupmask[slot >> 5], 1u << (slot & 31));
+                            atomicAdd(&dupcnt[slot], 1u);
+                        }
+                        break;
+                    }
+                    slot += stride;
+                    if (slot >= C) slot -= C;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    uint64_t *keys = sc.keys + d.koff;
+    uint32_t *wts = sc.wts + d.koff;
+    const uint32_t Cr = (C + 31u) & ~31u;
+    for (uint32_t i = threadIdx.x; i < Cr; i += blockDim.x) {
+        uint64_t key = (i < C) ? table[i] : kEmptyKey;
+        bool occ = key != kEmptyKey;
+        uint32_t extra = 0;
+        if (occ && !unweighted) {
+            if (LONG) extra = dupcnt[i];
+            else if (dupmask[i >> 5] & (1u << (i & 31))) extra = dupcnt[i];
+            if (extra) dupcnt[i] = 0;   // leave the scratch zeroed for the next strand
+        }
+        // weight rule (MinHashSketch.java:95-130); keys of the launch's light weight go to the front, the rest
+        // (with their weights) to the back, weight 0 (a popular k-mer under --repeat-weight < 0) is dropped
+        uint32_t w = 0;
+        if (occ) w = kmer_weight(flt, key, extra + 1);
+        const bool light = occ && w == flt.light_weight, heavy = occ && w != 0 && w != flt.light_weight;
+        int pl = warp_alloc(s_nlight, light);
+        int ph = warp_alloc(s_nheavy, heavy);
+        if (light) keys[pl] = key;
+        else if (heavy) { keys[nk - 1 - ph] = key; wts[nk - 1 - ph] = w; }
+    }
+    (void)s;
+}
+
+// shared-memory plan of the BITMAP scheme for strands of up to nkmax k-mers (bytes, 16-byte aligned regions)
+struct DedupPlan { uint32_t bits, l2cap, tslots, off_bm, off_l2, off_chars, off_tab, off_cnt, total; };
+__host__ __device__ inline DedupPlan dedup_plan(uint32_t nkmax, uint32_t chars_cap)
+{
+    DedupPlan p;
+    p.bits = 1024; while (p.bits < 6u * nkmax) p.bits <<= 1;          // >= 6 bits per k-mer: late k-mers ~ n / (2 * 6.5)
+    p.l2cap = (nkmax / 8u + 128u + 7u) & ~7u;                          // late k-mers the small table is sized for (1.8x the expectation;
+                                                                       // 10 kbp strands: the whole plan is 110 KB, two CTAs per SM)
+    p.tslots = ((p.l2cap + p.l2cap / 3u + 8u) | 1u);                   // load <= 0.75; odd: power-of-two probe strides cycle
+    auto al = [](uint32_t x) { return (x + 15u) & ~15u; };
+    p.off_bm = al(nkmax * 8u);
+    p.off_l2 = p.off_bm + al(p.bits / 8u);
+    p.off_chars = p.off_l2 + al(p.l2cap * 2u);
+    // the small table reuses the characters' region (dead after pass 1) and extends past it
+    p.off_tab = p.off_chars;
+    p.off_cnt = p.off_tab + al(p.tslots * 8u);
+    p.total = p.off_cnt + al(p.tslots * 4u);
+    if (p.total < p.off_chars + al(chars_cap)) p.total = p.off_chars + al(chars_cap);
+    return p;
+}
+
 template <bool LONG, int KC /* compile-time k, 0 = runtime */>
 __global__ void __launch_bounds__(1024)
 k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc, int s_begin, int s_end,
-             int k, int unweighted, uint32_t table_cap, uint32_t chars_cap, SketchScratch sc, uint32_t *queue,
+             int k, int unweighted, uint32_t table_cap, uint32_t chars_cap, uint32_t nkmax, SketchScratch sc, uint32_t *queue,
              const KmerFilterView flt)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ int s_strand, s_nlight, s_nheavy, s_special;
+    __shared__ int s_strand, s_nlight, s_nheavy, s_special, s_nl2;
 
-    uint64_t *table;
-    uint32_t *dupmask = nullptr;
-    uint8_t *chars = nullptr;
-    if (LONG) {
-        table = sc.gtable + (size_t)blockIdx.x * table_cap;
-    } else {
-        table = reinterpret_cast<uint64_t *>(smem_raw);
-        dupmask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)table_cap * 8);
-        chars = smem_raw + (size_t)table_cap * 8 + (size_t)((table_cap + 31) / 32) * 4;
-    }
     uint32_t *dupcnt = sc.dupcnt + (size_t)blockIdx.x * table_cap;
-    (void)chars_cap;
+    const DedupPlan pl = LONG ? DedupPlan{} : dedup_plan(nkmax, chars_cap);
 
     for (;;) {
         if (threadIdx.x == 0) {
             s_strand = s_begin + (int)atomicAdd(queue, 1u);
-            s_nlight = 0; s_nheavy = 0; s_special = 0;
+            s_nlight = 0; s_nheavy = 0; s_special = 0; s_nl2 = 0;
         }
         __syncthreads();
         const int s = s_strand;
         if (s >= s_end) break;
         const StrandDesc d = desc[s];
         const int nk = (int)d.len - k + 1;
-        // table sized for this strand (load factor <= 0.8)
-        uint32_t C = dedup_table_slots((uint32_t)nk);
-        if (C > table_cap) C = table_cap;
-
-        for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) table[i] = kEmptyKey;
-        if (!LONG) {
-            for (uint32_t i = threadIdx.x; i < (C + 31) / 32; i += blockDim.x) dupmask[i] = 0;
-            stage_chars(chars, bases + d.base_off, d.len, d.rc);
-        }
-        __syncthreads();
-
         const CharsGlobal gsrc{bases + d.base_off, d.len, d.rc};
-        // uniform trip count + __syncwarp: the CAS probe below is a data-dependent loop and without an
-        // explicit reconvergence point the lanes of a warp stay split for the rest of the strand
-        for (int base = 0; base < nk; base += blockDim.x) {
-            const int i = base + (int)threadIdx.x;
-            if (i < nk) {
-                uint64_t h;
-                if (LONG) h = murmur3_128_h1_chars([&](int j) { return gsrc(i + j); }, KC ? KC : k);
-                else      h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, KC ? KC : k);
-                if (flt.remove_unique == 1 && !bloom_might_contain(flt, h)) { /* keepKmer false (MinHashSketch.java:70-71) */ }
-                else if (h == kEmptyKey) atomicAdd(&s_special, 1);
-                else {
-                    // open addressing with double hashing: the stride is a power of two picked by three hash bits (C is odd,
-                    // so every stride is a full cycle); a plain load looks at the slot first and the CAS is only issued on
-                    // an empty one.  ncu on the first version (linear probing, CAS per probe) showed the probe loop running
-                    // 14 times per warp with 4 of 32 lanes active.
-                    uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * C) >> 32);
-                    uint32_t stride = 1u << ((uint32_t)h & 7u);
-                    if (stride >= C) stride = 1u;   // tiny strands: keep slot + stride - C inside the table
-                    for (;;) {
-                        unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&table[slot]);
-                        if (old == kEmptyKey)
-                            old = atomicCAS(reinterpret_cast<unsigned long long *>(&table[slot]), (unsigned long long)kEmptyKey, (unsigned long long)h);
-                        if (old == kEmptyKey) break;
-                        if (old == h) {
-                            if (!unweighted) {
-                                if (!LONG) atomicOr(&dupmask[slot >> 5], 1u << (slot & 31));
-                                atomicAdd(&dupcnt[slot], 1u);
-                            }
-                            break;
-                        }
-                        slot += stride;
-                        if (slot >= C) slot -= C;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-
         uint64_t *keys = sc.keys + d.koff;
         uint32_t *wts = sc.wts + d.koff;
-        const uint32_t Cr = (C + 31u) & ~31u;
-        for (uint32_t i = threadIdx.x; i < Cr; i += blockDim.x) {
-            uint64_t key = (i < C) ? table[i] : kEmptyKey;
-            bool occ = key != kEmptyKey;
-            uint32_t extra = 0;
-            if (occ && !unweighted) {
-                if (LONG) extra = dupcnt[i];
-                else if (dupmask[i >> 5] & (1u << (i & 31))) extra = dupcnt[i];
-                if (extra) dupcnt[i] = 0;   // leave the scratch zeroed for the next strand
+
+        if constexpr (LONG) {
+            dedup_table_strand<true, KC>(gsrc, d, s, k, unweighted, sc.gtable + (size_t)blockIdx.x * table_cap, nullptr, dupcnt, table_cap, sc, flt,
+                                         &s_nlight, &s_nheavy, &s_special);
+        } else {
+            uint64_t *Hh = reinterpret_cast<uint64_t *>(smem_raw);
+            uint32_t *bm = reinterpret_cast<uint32_t *>(smem_raw + pl.off_bm);
+            uint16_t *L2 = reinterpret_cast<uint16_t *>(smem_raw + pl.off_l2);
+            uint8_t *chars = smem_raw + pl.off_chars;
+            uint64_t *T = reinterpret_cast<uint64_t *>(smem_raw + pl.off_tab);
+            uint32_t *Tc = reinterpret_cast<uint32_t *>(smem_raw + pl.off_cnt);
+            // ---- pass 1: hash once, one bit per hash; a k-mer whose bit is already set is late ----
+            for (uint32_t i = threadIdx.x; i < pl.bits / 32; i += blockDim.x) bm[i] = 0;
+            stage_chars(chars, bases + d.base_off, d.len, d.rc);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+                uint64_t h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, KC ? KC : k);
+                if (flt.remove_unique == 1 && !bloom_might_contain(flt, h)) h = kEmptyKey;     // keepKmer false (MinHashSketch.java:70-71)
+                else if (h == kEmptyKey) atomicAdd(&s_special, 1);                             // a hash equal to the marker (p = 2^-64)
+                else {
+                    const uint32_t b = (uint32_t)(h >> 13) & (pl.bits - 1u);
+                    const uint32_t old = atomicOr(&bm[b >> 5], 1u << (b & 31));
+                    if ((old >> (b & 31)) & 1u) { const int q = atomicAdd(&s_nl2, 1); if (q < (int)pl.l2cap) L2[q] = (uint16_t)i; }
+                }
+                Hh[i] = h;
             }
-            // weight rule (MinHashSketch.java:95-130); keys of the launch's light weight go to the front, the rest
-            // (with their weights) to the back, weight 0 (a popular k-mer under --repeat-weight < 0) is dropped
-            uint32_t w = 0;
-            if (occ) w = kmer_weight(flt, key, extra + 1);
-            const bool light = occ && w == flt.light_weight, heavy = occ && w != 0 && w != flt.light_weight;
-            int pl = warp_alloc(&s_nlight, light);
-            int ph = warp_alloc(&s_nheavy, heavy);
-            if (light) keys[pl] = key;
-            else if (heavy) { keys[nk - 1 - ph] = key; wts[nk - 1 - ph] = w; }
+            __syncthreads();
+            const int nl2 = s_nl2;
+            if (nl2 > (int)pl.l2cap) {
+                // low complexity: more repeats than the small table holds -> the TABLE scheme for this strand (characters from global
+                // memory: the table takes the whole shared window)
+                __syncthreads();
+                if (threadIdx.x == 0) s_special = 0;
+                __syncthreads();
+                dedup_table_strand<false, KC>(gsrc, d, s, k, unweighted, reinterpret_cast<uint64_t *>(smem_raw),
+                                              reinterpret_cast<uint32_t *>(smem_raw + (size_t)table_cap * 8), dupcnt, table_cap, sc, flt,
+                                              &s_nlight, &s_nheavy, &s_special);
+            } else {
+                // ---- pass 2: the late k-mers into the small exact table, with counts ----
+                for (uint32_t i = threadIdx.x; i < pl.tslots; i += blockDim.x) { T[i] = kEmptyKey; Tc[i] = 0; }
+                __syncthreads();
+                const uint32_t Tn = pl.tslots;
+                for (int j = threadIdx.x; j < nl2; j += blockDim.x) {
+                    const int idx = L2[j];
+                    const uint64_t h = Hh[idx];
+                    Hh[idx] = kEmptyKey;                                // consumed: pass 3 skips it
+                    uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * Tn) >> 32);
+                    uint32_t stride = 1u << ((uint32_t)h & 7u);
+                    if (stride >= Tn) stride = 1u;
+                    for (;;) {
+                        unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(&T[slot]);
+                        if (old == kEmptyKey) old = atomicCAS(reinterpret_cast<unsigned long long *>(&T[slot]), (unsigned long long)kEmptyKey, (unsigned long long)h);
+                        if (old == kEmptyKey || old == h) { atomicAdd(&Tc[slot], 1u); break; }
+                        slot += stride;
+                        if (slot >= Tn) slot -= Tn;
+                    }
+                }
+                __syncthreads();
+                // ---- pass 3: every other k-mer: an earlier occurrence of a repeated k-mer (counted), or unique (written out) ----
+                const int nkr = (nk + 31) & ~31;
+                for (int i = threadIdx.x; i < nkr; i += blockDim.x) {
+                    const uint64_t h = i < nk ? Hh[i] : kEmptyKey;
+                    bool uniq = false;
+                    if (h != kEmptyKey) {
+                        uniq = true;
+                        if (nl2 > 0) {
+                            uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(h >> 32) * Tn) >> 32);
+                            uint32_t stride = 1u << ((uint32_t)h & 7u);
+                            if (stride >= Tn) stride = 1u;
+                            for (;;) {
+                                const uint64_t t = T[slot];
+                                if (t == kEmptyKey) break;
+                                if (t == h) { atomicAdd(&Tc[slot], 1u); uniq = false; break; }
+                                slot += stride;
+                                if (slot >= Tn) slot -= Tn;
+                            }
+                        }
+                    }
+                    // weight rule (MinHashSketch.java:95-130) for a k-mer seen once
+                    uint32_t w = 0;
+                    if (uniq) w = kmer_weight(flt, h, 1u);
+                    const bool light = uniq && w == flt.light_weight, heavy = uniq && w != 0 && w != flt.light_weight;
+                    const int pl_ = warp_alloc(&s_nlight, light);
+                    const int ph = warp_alloc(&s_nheavy, heavy);
+                    if (light) keys[pl_] = h;
+                    else if (heavy) { keys[nk - 1 - ph] = h; wts[nk - 1 - ph] = w; }
+                }
+                __syncthreads();
+                // ---- the repeated k-mers with their counts ----
+                const uint32_t Tr = (Tn + 31u) & ~31u;
+                for (uint32_t i = threadIdx.x; i < Tr; i += blockDim.x) {
+                    const uint64_t key = i < Tn ? T[i] : kEmptyKey;
+                    const bool occ = key != kEmptyKey;
+                    uint32_t w = 0;
+                    if (occ) w = kmer_weight(flt, key, unweighted ? 1u : Tc[i]);
+                    const bool light = occ && w == flt.light_weight, heavy = occ && w != 0 && w != flt.light_weight;
+                    const int pl_ = warp_alloc(&s_nlight, light);
+                    const int ph = warp_alloc(&s_nheavy, heavy);
+                    if (light) keys[pl_] = key;
+                    else if (heavy) { keys[nk - 1 - ph] = key; wts[nk - 1 - ph] = w; }
+                }
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             int nl = s_nlight, nh = s_nheavy;
-            if (s_special > 0) {   // a k-mer whose hash equals the table's empty marker (p = 2^-64)
+            if (s_special > 0) {   // a k-mer whose hash equals the tables' empty marker (p = 2^-64)
                 const uint32_t w = kmer_weight(flt, kEmptyKey, unweighted ? 1u : (uint32_t)s_special);
                 if (w == flt.light_weight) { keys[nl] = kEmptyKey; nl++; }
                 else if (w != 0) { keys[nk - 1 - nh] = kEmptyKey; wts[nk - 1 - nh] = w; nh++; }
@@ -1191,7 +1317,9 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
     if (first_long > 0) {
         uint32_t cap = dedup_table_slots((uint32_t)max_kmers_short);
         uint32_t chars_cap = (uint32_t)align16((size_t)max_kmers_short + k);
-        size_t smem = (size_t)cap * 8 + (size_t)((cap + 31) / 32) * 4 + chars_cap;
+        // shared window: the BITMAP scheme's plan, and room for the TABLE scheme a low-complexity strand falls back to
+        const DedupPlan plan = dedup_plan((uint32_t)max_kmers_short, chars_cap);
+        size_t smem = std::max<size_t>(plan.total, (size_t)cap * 8 + (size_t)((cap + 31) / 32) * 4);
         auto kern = k == 16 ? k_hash_dedup<false, 16> : k_hash_dedup<false, 0>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1199,7 +1327,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         if (smem <= 113 * 1024) grid *= 2;
         if (grid > first_long) grid = first_long;
         // dupcnt rows are strided by the *launch's* cap so both variants can share the buffer
-        kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, s_base, s_base + first_long, k, unweighted, cap, chars_cap, sc, queues + 0, filter);
+        kern<<<grid, 1024, smem, st>>>(d_bases, d_desc, s_base, s_base + first_long, k, unweighted, cap, chars_cap, (uint32_t)max_kmers_short, sc, queues + 0, filter);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -1207,7 +1335,7 @@ cudaError_t launch_hash_dedup(cudaStream_t st, const uint8_t *d_bases, const Str
         uint32_t cap = dedup_table_slots((uint32_t)max_kmers_long);
         int grid = hash_dedup_grid();
         if (grid > n_strands - first_long) grid = n_strands - first_long;
-        k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, s_base + first_long, s_base + n_strands, k, unweighted, cap, 0, sc, queues + 1, filter);
+        k_hash_dedup<true, 0><<<grid, 1024, 0, st>>>(d_bases, d_desc, s_base + first_long, s_base + n_strands, k, unweighted, cap, 0, 0, sc, queues + 1, filter);
         (*launches)++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
