@@ -404,15 +404,23 @@ int index_build(mhapb_ctx *ctx)
     if (s.indexed) return MHAPB_OK;
     const int H = s.p.num_hashes;
     if ((uint64_t)s.n * (uint64_t)H >= 0xfffffff0ull || s.n >= 0x7fffffff) return fail(ctx, MHAPB_EINVAL, "store too large for 32-bit postings (%lld sketches x %d)", (long long)s.n, H);
-    int lg = 5; while ((1ll << lg) < 2 * s.n) lg++;
+    // Sub-table size: two slots per sketch, the size that can never overflow (a word's sub-table holds its DISTINCT values, at
+    // most one per sketch).  With noisy long reads that bound is nearly reached: at 15 % error only 7 % of the 16-mers are
+    // error-free, so the minimum of a read is almost always a k-mer nobody shares (measured on configs[1]: the optimistic size of
+    // one slot per two sketches overflowed).  MHAPB_INDEX_OPTIMISTIC=1 (read when the context is created) starts with that
+    // smaller size for low-error data -- 4x fewer slots to memset, scan and pack -- and verifies: an insert that needs more
+    // than 128 probes raises IndexView::overflow, K2b then does nothing, and the search rebuilds with the safe size.
+    const long long want = (ctx->index_optimistic && !s.index_safe) ? std::max<long long>(s.n / 2, 1024) : 2 * s.n;
+    int lg = 5; while ((1ll << lg) < want) lg++;
     s.log2capw = lg;
     const size_t nslots = (size_t)H << lg;
     CU(ctx, s.slots.ensure(nslots * 8));
     CU(ctx, s.postings.ensure((size_t)s.n * H * 4));
     CU(ctx, s.present.ensure(nslots / 8 + 64));
+    CU(ctx, s.idx_flag.ensure(64));
     CU(ctx, ctx->tmp_start.ensure(nslots * 4));
     CU(ctx, ctx->block_sums.ensure(((nslots + 4095) / 4096 + 1) * 4));
-    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.present.as<uint32_t>(), lg, H, s.n, 0};
+    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.present.as<uint32_t>(), lg, H, s.n, s.idx_flag.as<uint32_t>(), 0};
     int launches = 0;
     cudaEventRecord(ctx->ev[8], ctx->stream);
     CU(ctx, launch_index_build(ctx->stream, s.minhash.as<int32_t>(), s.n, H, iv, ctx->tmp_start.as<uint32_t>(), ctx->block_sums.as<uint32_t>(), &launches));
@@ -435,7 +443,7 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
     int rc = index_build(ctx);
     if (rc) return rc;
     const int H = s.p.num_hashes;
-    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.present.as<uint32_t>(), s.log2capw, H, s.n,
+    IndexView iv{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.present.as<uint32_t>(), s.log2capw, H, s.n, s.idx_flag.as<uint32_t>(),
                  q.d_minhash != s.minhash.as<int32_t>() ? 1 : 0};
     const int64_t nq = q.list_all ? q.n_all : (q.d_list ? q.n_list : (int64_t)q.list.size());
     mhapb_stats st{};
@@ -505,8 +513,19 @@ int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q
             cudaEventRecord(ctx->ev[3], ctx->stream);
             CU(ctx, launch_compact_hits(ctx->stream, ctx->cand.as<Candidate>(), ctx->ovl.as<OverlapOut>(), cand_cap, dc + 0, jmin, keep_all,
                                         ctx->cand2.as<Candidate>(), ctx->ovl2.as<OverlapOut>(), dc + 5, &launches));
+            uint32_t idx_overflow = 0;
             CU(ctx, cudaMemcpyAsync(cnt, dc, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(&idx_overflow, s.idx_flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
             CU(ctx, cudaStreamSynchronize(ctx->stream));                      // sync 1 of 2: the counters
+            if (idx_overflow) {   // the optimistic sub-table size was too small for this store: rebuild safely, search again
+                if (s.index_safe) return fail(ctx, MHAPB_ECUDA, "index overflow with the safe table size");
+                s.index_safe = true; s.indexed = false;
+                rc = index_build(ctx);
+                if (rc) return rc;
+                iv = IndexView{s.slots.as<uint64_t>(), s.postings.as<uint32_t>(), s.present.as<uint32_t>(), s.log2capw, H, s.n, s.idx_flag.as<uint32_t>(), iv.use_present};
+                attempt = -1;
+                continue;
+            }
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timing.probe_ms += ms;
             cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.filter_ms += ms;
@@ -732,6 +751,7 @@ int mhapb_create(int device_id, mhapb_ctx **out)
     if (prop.major != 10) return fail(nullptr, MHAPB_ENODEV, "device %d is sm_%d%d; this build carries sm_100a code only", device_id, prop.major, prop.minor);
     mhapb_ctx *c = new mhapb_ctx();
     c->device = device_id;
+    { const char *e = getenv("MHAPB_INDEX_OPTIMISTIC"); c->index_optimistic = e && atoi(e) != 0; }
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, MHAPB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     if ((e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return fail(nullptr, MHAPB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     for (auto &ev : c->ev) cudaEventCreate(&ev);
@@ -750,7 +770,7 @@ void mhapb_destroy(mhapb_ctx *ctx)
                       &ctx->q_id, &ctx->eq, &ctx->store.minhash, &ctx->store.ord, &ctx->store.ord_n, &ctx->store.lenk, &ctx->store.len,
                       &ctx->store.id, &ctx->store.slots, &ctx->store.postings, &ctx->f_keys, &ctx->f_idf, &ctx->f_used, &ctx->f_bloom};
     for (auto b : bufs) b->release();
-    DevBuf *more[] = {&ctx->ovf_q, &ctx->store.fwd_list, &ctx->store.present, &ctx->g_minhash, &ctx->g_ord, &ctx->g_ordn, &ctx->g_lenk, &ctx->g_len, &ctx->g_id, &ctx->g_pack, &ctx->g_small};
+    DevBuf *more[] = {&ctx->ovf_q, &ctx->store.fwd_list, &ctx->store.present, &ctx->store.idx_flag, &ctx->g_minhash, &ctx->g_ord, &ctx->g_ordn, &ctx->g_lenk, &ctx->g_len, &ctx->g_id, &ctx->g_pack, &ctx->g_small};
     for (auto b : more) b->release();
     ctx->h_cand.release(); ctx->h_ovl.release(); ctx->h_desc.release(); ctx->h_vdesc.release(); ctx->t512.release(); ctx->vdesc.release();
     comm_release(ctx);

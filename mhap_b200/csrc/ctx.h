@@ -79,7 +79,8 @@ struct Store {
     DevBuf fwd_list; int64_t fwd_list_n = 0; bool fwd_list_valid = false;
     // index
     bool indexed = false;
-    DevBuf slots, postings, present;
+    DevBuf slots, postings, present, idx_flag;
+    bool index_safe = false;          // a build with the optimistic sub-table size overflowed once: use 2 slots per sketch from now on
     int log2capw = 0;
 };
 
@@ -106,6 +107,7 @@ struct mhapb_ctx {
     mhapb::Store store;
     cudaEvent_t ev[12]{};                     // [8],[9]: K2a, read lazily (index_timing_pending)
     bool index_timing_pending = false;
+    bool index_optimistic = false;            // MHAPB_INDEX_OPTIMISTIC at creation: start K2a with the small sub-table size (index_build)
     // the -f k-mer filter (FrequencyCounts); view.mode == 0 when none is set
     mhapb::DevBuf f_keys, f_idf, f_used, f_bloom;
     mhapb::KmerFilterView filter{};

@@ -92,6 +92,8 @@ struct IndexView {
     int       log2capw;
     int       H;
     int64_t   n_store;
+    uint32_t *overflow;      // set by the build when a sub-table was sized too small (a bucket needed > kIdxMaxProbe probes): the
+                             // index is then incomplete, K2b does nothing, and the host rebuilds with the safe size (2 slots per sketch)
     int       use_present;   // probe: consult `present` first (off when the store queries itself: every probe hits, the bitmap is pure overhead)
 };
 

@@ -34,6 +34,7 @@ __device__ __forceinline__ uint32_t slot_hash(uint32_t value, int log2capw)
 // insert into are those of one or two word groups (8 x capw x 8 B = 32 MB for 2*10^5 sketches): they stay in the 126 MB L2 and
 // the CAS / add traffic never goes to DRAM.  (The first version walked the rows linearly, word innermost: consecutive threads
 // hit 512 different sub-tables -- 2 GB of working set, one DRAM sector per atomic; ncu: 31-38 % of DRAM throughput for 8-byte slots.)
+constexpr int kIdxMaxProbe = 128;     // longest probe sequence the build accepts (see IndexView::overflow)
 constexpr int kIdxGroup = 8;          // words per group
 constexpr int kIdxTileRows = 256;     // sketches per tile (small: the CTAs resident at one moment span one or two word groups)
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ bool index_tile(int64_t tile, int64_t tiles_per_group
     return *w0 < H;
 }
 
-__global__ void __launch_bounds__(256) k_index_count(const int32_t *__restrict__ minhash, int64_t n_store, int H, uint64_t *slots, int log2capw)
+__global__ void __launch_bounds__(256) k_index_count(const int32_t *__restrict__ minhash, int64_t n_store, int H, uint64_t *slots, int log2capw, uint32_t *overflow)
 {
     const uint32_t capmask = (1u << log2capw) - 1;
     const int64_t tiles_per_group = (n_store + kIdxTileRows - 1) / kIdxTileRows;
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(256) k_index_count(const int32_t *__restrict__
             const uint32_t v = (uint32_t)minhash[row * H + w];
             uint64_t *sub = slots + ((size_t)w << log2capw);
             uint32_t p = slot_hash(v, log2capw);
-            for (;;) {
+            int steps = 0;
+            for (; steps < kIdxMaxProbe; steps++) {
                 unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&sub[p]);
                 if (cur == kEmptySlot) {
                     cur = atomicCAS(reinterpret_cast<unsigned long long *>(&sub[p]), (unsigned long long)kEmptySlot, (unsigned long long)v);
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(256) k_index_count(const int32_t *__restrict__
                 }
                 p = (p + 1) & capmask;
             }
+            if (steps == kIdxMaxProbe) *overflow = 1u;   // the sub-table is too small for this store: the host rebuilds
         }
     }
 }
@@ -162,7 +165,9 @@ __global__ void __launch_bounds__(256) k_index_fill(const int32_t *__restrict__ 
             const uint32_t v = (uint32_t)minhash[row * H + w];
             const size_t sub = (size_t)w << log2capw;
             uint32_t p = slot_hash(v, log2capw);
-            for (;;) { const uint64_t sl = slots[sub + p]; if (sl != kEmptySlot && (uint32_t)sl == v) break; p = (p + 1) & capmask; }
+            int steps = 0;
+            for (; steps < kIdxMaxProbe; steps++) { const uint64_t sl = slots[sub + p]; if (sl != kEmptySlot && (uint32_t)sl == v) break; p = (p + 1) & capmask; }
+            if (steps == kIdxMaxProbe) continue;          // only after an overflow (the index is discarded)
             const uint32_t pos = atomicAdd(&start[sub + p], 1u);
             postings[pos] = (uint32_t)row;
         }
@@ -194,7 +199,9 @@ cudaError_t launch_index_build(cudaStream_t st, const int32_t *d_minhash, int64_
     const int grid = sms * 8;
     const int64_t n_tiles = ((n_store + kIdxTileRows - 1) / kIdxTileRows) * ((H + kIdxGroup - 1) / kIdxGroup);
     const int tgrid = (int)std::min<int64_t>(n_tiles, 1 << 30);   // one tile per CTA, in tile order: short-lived CTAs also let the collectives' kernels in
-    k_index_count<<<tgrid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw);
+    e = cudaMemsetAsync(iv.overflow, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    k_index_count<<<tgrid, 256, 0, st>>>(d_minhash, n_store, H, iv.slots, iv.log2capw, iv.overflow);
     const size_t nb = (nslots + kScanTile - 1) / kScanTile;
     k_scan_tiles<<<(unsigned)nb, kScanThreads, 0, st>>>(iv.slots, nslots, d_block_sums);
     k_scan_sums<<<1, kScanThreads, 0, st>>>(d_block_sums, nb);
@@ -267,6 +274,7 @@ k_probe(IndexView iv, ProbeArgs a)
     __shared__ int s_distinct, s_overflow;
     __shared__ unsigned long long s_elements;
 
+    if (*iv.overflow) return;                                 // incomplete index (sub-tables sized too small): the host rebuilds and searches again
     const int64_t n_work = SECOND ? (int64_t)a.counters[3] : a.nq_list;
     for (int64_t qi = blockIdx.x; qi < n_work; qi += gridDim.x) {
         const uint32_t q = SECOND ? a.ovf_q[qi] : (a.q_list ? a.q_list[qi] : (uint32_t)qi);

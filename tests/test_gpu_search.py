@@ -2,6 +2,7 @@
 against the CPU oracle: identical hit sets (all integers + score), identical printed lines, identical
 order-independent counters."""
 import ctypes as C
+import os
 import random
 
 import numpy as np
@@ -257,3 +258,32 @@ def test_more_queries_than_stored_sketches():
     res = ost.search_query(oq, keep_all=True, threads=4)
     assert_same_hits(hits, res.hits, stats, res.stats)
     assert len(hits) > 500
+
+
+def test_index_rebuilds_when_the_optimistic_table_size_overflows():
+    # MHAPB_INDEX_OPTIMISTIC=1: K2a sizes a word's sub-table for one slot per two sketches (low-error reads at sequencing coverage
+    # hold few distinct values per word) and verifies; here every sketch is unrelated to every other, so a word has as many
+    # distinct values as there are sketches: the first build overflows, the search rebuilds with two slots per sketch and must
+    # give the oracle's answer.  A fresh context: the option is read at creation, the safe size is remembered once needed.
+    rng = random.Random(77)
+    reads = [rand_seq(rng, 400) for _ in range(1400)] + [rand_seq(rng, 400)] * 3      # 2806 sketches, and one true overlap group
+    bases, offs = native.pack_reads(reads)
+    p = native.SketchParams(16, 64, 12, 200, 0, 116)
+    sp = native.SearchParams(3, 0, 0.2, 0.78, 1, 0, 0, -1)
+    os.environ["MHAPB_INDEX_OPTIMISTIC"] = "1"
+    try:
+        e = native.Engine(0)
+    finally:
+        del os.environ["MHAPB_INDEX_OPTIMISTIC"]
+    e.store_reset(p)
+    e.store_add_reads(bases, offs)
+    hits, stats = e.search_self(sp)
+    st = orc.Store(num_hashes=64, ordered_size=200)
+    st.add_reads(bases, offs)
+    res = st.search_self(keep_all=True, threads=8)
+    assert_same_hits(hits, res.hits, stats, res.stats)
+    assert len(hits) >= 3
+    # the same context again (now on the safe size), and a store that fits the optimistic size
+    hits2, stats2 = e.search_self(sp)
+    assert stats2 == stats and len(hits2) == len(hits)
+    e.close()
