@@ -87,7 +87,8 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     std::vector<int32_t> h_nl, h_nh;
     const int per = both ? 2 : 1;
     const int k = p.kmer_size, ok = p.ordered_kmer_size, H = p.num_hashes, S = p.ordered_sketch_size;
-    std::vector<StrandDesc> all;
+    std::vector<StrandDesc> &all = ctx->plan_all;    // kept across calls: a fresh 6 MB vector per call is a page fault per 4 KB
+    all.clear();
     all.reserve((size_t)n_reads * per);
     for (uint32_t r = 0; r < n_reads; r++) {
         uint64_t len = h_offsets[r + 1] - h_offsets[r];

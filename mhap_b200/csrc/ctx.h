@@ -100,6 +100,7 @@ struct mhapb_ctx {
     // search scratch
     mhapb::DevBuf ovf_q;
     mhapb::PinnedBuf h_cand, h_ovl;               // pinned landing buffers of the surviving pairs
+    std::vector<mhapb::StrandDesc> plan_all;      // the strands of the current sketch call (sketch_core)
     mhapb::PinnedBuf h_desc, h_vdesc;             // pinned plan of the strand descriptors (sketch_core)
     mhapb::DevBuf t512, vdesc;                    // step^512 tables and the virtual strands of sketches wider than 512 words
     uint64_t cand_cap_hint = 0; uint32_t ovf_threads_hint = 0;   // sizes the previous search needed
