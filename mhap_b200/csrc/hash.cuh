@@ -66,6 +66,36 @@ __host__ __device__ __forceinline__ uint64_t murmur3_128_h1_chars(const C &ch, i
     return h1;
 }
 
+#ifdef __CUDACC__
+// The same hash for k = 16 with the (upper-cased) characters in shared memory: the 16 characters are fetched as five aligned
+// 32-bit words and shifted into place with funnel shifts, and each group of four characters is widened to UTF-16LE with two
+// byte permutes -- 17 instructions instead of 16 byte loads and two dozen 64-bit shift/or pairs.  chars must be 4-byte aligned
+// and readable up to 3 bytes past character i+15.
+__device__ __forceinline__ uint64_t murmur3_128_h1_16chars_smem(const uint8_t *chars, int i)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(chars + (i & ~3));
+    const uint32_t sh = (uint32_t)(i & 3) * 8u;
+    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+    const uint32_t c[4] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh)};
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = 0, h2 = 0;
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        uint64_t k1 = ((uint64_t)__byte_perm(c[2 * b], 0, 0x4342) << 32) | __byte_perm(c[2 * b], 0, 0x4140);
+        uint64_t k2 = ((uint64_t)__byte_perm(c[2 * b + 1], 0, 0x4342) << 32) | __byte_perm(c[2 * b + 1], 0, 0x4140);
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+    h1 ^= 32; h2 ^= 32;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2;
+    return h1;
+}
+#endif
+
 // Guava 19.0 BloomFilterStrategies.MURMUR128_MITZ_64 hashes a Long through Funnel (v, sink) -> sink.putLong(v):
 // MurmurHash3_x64_128 (seed 0) of the key's 8 little-endian bytes (tail-only input: one k1 lane).
 // hash1 = lower eight bytes (h1), hash2 = upper eight (h2); probe i tests bit ((h1 + i*h2) & Long.MAX_VALUE) % bitSize.

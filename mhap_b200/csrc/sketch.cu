@@ -38,7 +38,17 @@ struct CharsGlobal {
     }
 };
 
-__device__ __forceinline__ void stage_chars(uint8_t *dst, const uint8_t *g, uint32_t len, uint32_t rc)
+// 256-entry tables of FastaData's upper-casing [0] and of upper-casing followed by Utils.rc's complement [1]: one shared-memory
+// look-up per character instead of a compare/subtract and a 12-way switch (the byte-wise arithmetic was 14 % of K1a's instructions)
+__device__ __forceinline__ void stage_lut_init(uint8_t (*lut)[256])
+{
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        const uint8_t u = upper_char((uint8_t)(i & 255));
+        lut[i >> 8][i & 255] = (i >> 8) ? complement_char(u) : u;
+    }
+}
+
+__device__ __forceinline__ void stage_chars(uint8_t *dst, const uint8_t *g, uint32_t len, uint32_t rc, const uint8_t (*lut)[256])
 {
     // 16-byte loads from the aligned window around the read (its first byte sits anywhere in the batch), one byte store per
     // character with FastaData's upper-casing and, for the reverse strand, Utils.rc applied on the way.  The byte-wise
@@ -47,16 +57,26 @@ __device__ __forceinline__ void stage_chars(uint8_t *dst, const uint8_t *g, uint
     const int head = (int)(reinterpret_cast<uintptr_t>(g) - a0);
     const uint4 *src = reinterpret_cast<const uint4 *>(a0);
     const int nvec = (head + (int)len + 15) >> 4;
+    const uint8_t *t = lut[rc ? 1 : 0];
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
         const uint4 q = __ldg(src + v);
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const int i0 = v * 16 - head;
+        if (i0 >= 0 && i0 + 16 <= (int)len) {            // the whole vector lies inside the read
+            uint8_t *d = rc ? dst + (len - 1 - i0) : dst + i0;
 #pragma unroll
-        for (int b = 0; b < 16; b++) {
-            const int i = v * 16 + b - head;
-            if (i >= 0 && i < (int)len) {
-                const uint8_t c = upper_char((uint8_t)(w[b >> 2] >> ((b & 3) * 8)));
-                if (rc) dst[len - 1 - i] = complement_char(c);
-                else dst[i] = c;
+            for (int b = 0; b < 16; b++) {
+                const uint8_t c = t[(w[b >> 2] >> ((b & 3) * 8)) & 0xffu];
+                if (rc) d[-b] = c; else d[b] = c;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const int i = i0 + b;
+                if (i >= 0 && i < (int)len) {
+                    const uint8_t c = t[(w[b >> 2] >> ((b & 3) * 8)) & 0xffu];
+                    if (rc) dst[len - 1 - i] = c; else dst[i] = c;
+                }
             }
         }
     }
@@ -239,9 +259,12 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int s_strand, s_nlight, s_nheavy, s_special, s_nl2;
+    __shared__ uint8_t s_lut[2][256];
 
     uint32_t *dupcnt = sc.dupcnt + (size_t)blockIdx.x * table_cap;
     const DedupPlan pl = LONG ? DedupPlan{} : dedup_plan(nkmax, chars_cap);
+    if (!LONG) stage_lut_init(s_lut);
+    const bool plain_weight = flt.mode == 0 || flt.mode == 3;      // weight = occurrence count (kmer_weight's first line), hoisted
 
     for (;;) {
         if (threadIdx.x == 0) {
@@ -269,10 +292,12 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
             uint32_t *Tc = reinterpret_cast<uint32_t *>(smem_raw + pl.off_cnt);
             // ---- pass 1: hash once, one bit per hash; a k-mer whose bit is already set is late ----
             for (uint32_t i = threadIdx.x; i < pl.bits / 32; i += blockDim.x) bm[i] = 0;
-            stage_chars(chars, bases + d.base_off, d.len, d.rc);
+            stage_chars(chars, bases + d.base_off, d.len, d.rc, s_lut);
             __syncthreads();
             for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-                uint64_t h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, KC ? KC : k);
+                uint64_t h;
+                if constexpr (KC == 16) h = murmur3_128_h1_16chars_smem(chars, i);
+                else h = murmur3_128_h1_chars([&](int j) { return chars[i + j]; }, KC ? KC : k);
                 if (flt.remove_unique == 1 && !bloom_might_contain(flt, h)) h = kEmptyKey;     // keepKmer false (MinHashSketch.java:70-71)
                 else if (h == kEmptyKey) atomicAdd(&s_special, 1);                             // a hash equal to the marker (p = 2^-64)
                 else {
@@ -336,7 +361,7 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
                     }
                     // weight rule (MinHashSketch.java:95-130) for a k-mer seen once
                     uint32_t w = 0;
-                    if (uniq) w = kmer_weight(flt, h, 1u);
+                    if (uniq) w = plain_weight ? 1u : kmer_weight(flt, h, 1u);
                     const bool light = uniq && w == flt.light_weight, heavy = uniq && w != 0 && w != flt.light_weight;
                     const int pl_ = warp_alloc(&s_nlight, light);
                     const int ph = warp_alloc(&s_nheavy, heavy);
@@ -350,7 +375,7 @@ k_hash_dedup(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ d
                     const uint64_t key = i < Tn ? T[i] : kEmptyKey;
                     const bool occ = key != kEmptyKey;
                     uint32_t w = 0;
-                    if (occ) w = kmer_weight(flt, key, unweighted ? 1u : Tc[i]);
+                    if (occ) w = plain_weight ? (unweighted ? 1u : Tc[i]) : kmer_weight(flt, key, unweighted ? 1u : Tc[i]);
                     const bool light = occ && w == flt.light_weight, heavy = occ && w != 0 && w != flt.light_weight;
                     const int pl_ = warp_alloc(&s_nlight, light);
                     const int ph = warp_alloc(&s_nheavy, heavy);
@@ -996,6 +1021,8 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_digit, s_before, s_bin, s_bstar, s_maxbin, s_nbl, s_wsum[16];
     __shared__ uint64_t s_T, s_bl[kOrdMaxBin];
+    __shared__ uint8_t s_lut[2][256];
+    if (!LONG) stage_lut_init(s_lut);
 
     uint64_t *sel = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *oh;
@@ -1015,7 +1042,7 @@ k_ordered(const uint8_t *__restrict__ bases, const StrandDesc *__restrict__ desc
         if (s >= s_end) break;
         const StrandDesc d = desc[s];
         const int no = (int)d.len - ok + 1;
-        if (!LONG) { stage_chars(chars, bases + d.base_off, d.len, d.rc); __syncthreads(); }
+        if (!LONG) { stage_chars(chars, bases + d.base_off, d.len, d.rc, s_lut); __syncthreads(); }
         const CharsGlobal gsrc{bases + d.base_off, d.len, d.rc};
         if constexpr (!LONG && KC > 0 && (KC & 1) == 0) {
             // MurmurHash3_x86_32 block b of k-mer i is the pair of chars (i+2b, i+2b+1), and its mixed value
