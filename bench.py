@@ -102,13 +102,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Number of samples taken so far (the timed region keeps the rows between two marks)."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        self.rows = self.rows[first:last]
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
@@ -308,12 +313,15 @@ def _main(args, real_stdout):
         return hits, stats, qhits, qstats
 
     # ---- device-resident leg ----
-    for _ in range(args.warmup):
-        step()
+    # the clock sampler is started before the warm-up (nvidia-smi takes a few hundred ms to come up and would otherwise do
+    # so inside the timed region); only the samples taken between the two marks below are reported
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
     barrier()
+    mark0 = sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
@@ -323,7 +331,7 @@ def _main(args, real_stdout):
     dt = time.perf_counter() - t0
     ev1.record(); torch.cuda.synchronize()
     dt_dev = ev0.elapsed_time(ev1) * 1e-3      # CUDA events around the same region (every library call ends synchronised)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, sampler.mark()) if rank == 0 else None
     tt = torch.tensor([dt, dt_dev], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
