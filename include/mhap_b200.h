@@ -197,6 +197,12 @@ int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char
                         const uint64_t *offsets, const int64_t *ids, uint32_t n_reads,
                         int both_strands, uint8_t **out, uint64_t *out_len, uint32_t *n_records);
 
+/* Same with the header string of every record given (headers[i] for read i; NULL entries / NULL array = decimal id):
+ * --store-full-id, where SequenceId.getHeader is the FASTA name (impl/SequenceId.java:102-108, impl/FastaData.java:155-156). */
+int mhapb_sketch_to_dat_named(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases,
+                              const uint64_t *offsets, const int64_t *ids, const char *const *headers, uint32_t n_reads,
+                              int both_strands, uint8_t **out, uint64_t *out_len, uint32_t *n_records);
+
 /* ---- .dat codec (host only) ---------------------------------------------------------------
  * Encode one record (returns bytes; buf==NULL sizes it).  header==NULL => decimal id. */
 int64_t mhapb_dat_encode(int64_t id, int is_fwd, const char *header, int32_t seq_len,

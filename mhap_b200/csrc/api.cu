@@ -1008,6 +1008,13 @@ int mhapb_dat_decode(const uint8_t *buf, uint64_t len, int64_t id_offset, uint32
 int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases, const uint64_t *offsets,
                         const int64_t *ids, uint32_t n_reads, int both_strands, uint8_t **out, uint64_t *out_len, uint32_t *n_records)
 {
+    return mhapb_sketch_to_dat_named(ctx, p, bases, offsets, ids, nullptr, n_reads, both_strands, out, out_len, n_records);
+}
+
+int mhapb_sketch_to_dat_named(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char *bases, const uint64_t *offsets,
+                              const int64_t *ids, const char *const *headers, uint32_t n_reads, int both_strands,
+                              uint8_t **out, uint64_t *out_len, uint32_t *n_records)
+{
     if (!ctx || !out || !out_len) return MHAPB_EINVAL;
     int rc = check_sketch_params(ctx, p);
     if (rc) return rc;
@@ -1022,7 +1029,9 @@ int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char
         for (int s = 0; s < (status[r] == 3 ? 1 : per); s++) {
             size_t j = (size_t)r * per + s;
             int64_t id = ids ? ids[r] : (int64_t)r + 1;
-            total += (uint64_t)mhapb_dat_encode(id, s == 0, nullptr, 0, nullptr, (int32_t)H, 0, 0, nullptr, on[j], nullptr);
+            const int64_t sz = mhapb_dat_encode(id, s == 0, headers ? headers[r] : nullptr, 0, nullptr, (int32_t)H, 0, 0, nullptr, on[j], nullptr);
+            if (sz < 0) { return fail(ctx, MHAPB_EINVAL, "header of read %u is longer than 65535 bytes", r); }
+            total += (uint64_t)sz;
             nrec++;
         }
     }
@@ -1035,7 +1044,7 @@ int mhapb_sketch_to_dat(mhapb_ctx *ctx, const mhapb_sketch_params *p, const char
         for (int s = 0; s < (status[r] == 3 ? 1 : per); s++) {
             size_t j = (size_t)r * per + s;
             int64_t id = ids ? ids[r] : (int64_t)r + 1;
-            w += mhapb_dat_encode(id, s == 0, nullptr, len, mh.data() + j * H, (int32_t)H, len - p->ordered_kmer_size + 1,
+            w += mhapb_dat_encode(id, s == 0, headers ? headers[r] : nullptr, len, mh.data() + j * H, (int32_t)H, len - p->ordered_kmer_size + 1,
                                   p->ordered_kmer_size, ord.data() + j * S * 2, on[j], w);
         }
     }

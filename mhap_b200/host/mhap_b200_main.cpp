@@ -335,7 +335,11 @@ int main(int argc, char **argv)
             uint32_t nrec = 0;
             for_each_fasta_batch(pf, 0, o.num_threads, nullptr, [&](mhapb_host::FastaBatch &b, const std::vector<int64_t> &ids) {
                 uint8_t *blob = nullptr; uint64_t len = 0; uint32_t nr = 0;
-                ck(ctx, mhapb_sketch_to_dat(ctx, &p, b.bases, b.offsets.data(), ids.data(), b.n_reads(), 1, &blob, &len, &nr));
+                // --store-full-id: the record's header string is the FASTA name (SequenceId.getHeader), otherwise the decimal id
+                std::vector<const char *> hdr;
+                if (g_full_ids) for (const std::string &h : b.headers) hdr.push_back(h.c_str());
+                ck(ctx, mhapb_sketch_to_dat_named(ctx, &p, b.bases, b.offsets.data(), ids.data(), hdr.size() == b.n_reads() ? hdr.data() : nullptr,
+                                                  b.n_reads(), 1, &blob, &len, &nr));
                 out.write((const char *)blob, (std::streamsize)len);
                 mhapb_free(blob);
                 nrec += nr;

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libmhap_b200.so")
 # every symbol include/mhap_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "mhapb_version", "mhapb_create", "mhapb_destroy", "mhapb_last_error", "mhapb_free", "mhapb_get_timing",
-    "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_xorshift_peaks", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat",
+    "mhapb_host_alloc", "mhapb_host_free", "mhapb_xorshift_peak", "mhapb_xorshift_peaks", "mhapb_sketch", "mhapb_sketch_device", "mhapb_sketch_to_dat", "mhapb_sketch_to_dat_named",
     "mhapb_dat_encode", "mhapb_dat_decode", "mhapb_store_reset", "mhapb_store_add_reads", "mhapb_store_add_reads_device",
     "mhapb_store_add_sketches", "mhapb_store_add_sketches_device", "mhapb_store_size", "mhapb_store_get",
     "mhapb_store_get_range", "mhapb_store_params", "mhapb_store_device_ptrs", "mhapb_index_build", "mhapb_search_self", "mhapb_search_query_reads",
@@ -109,6 +109,7 @@ def load():
     L.mhapb_sketch.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
     L.mhapb_sketch_device.argtypes = [vp, P(SketchParams), vp, vp, u32, C.c_int, vp, vp, vp, vp]
     L.mhapb_sketch_to_dat.argtypes = [vp, P(SketchParams), vp, vp, vp, u32, C.c_int, P(vp), P(u64), P(u32)]
+    L.mhapb_sketch_to_dat_named.argtypes = [vp, P(SketchParams), vp, vp, vp, vp, u32, C.c_int, P(vp), P(u64), P(u32)]
     L.mhapb_dat_encode.argtypes = [i64, C.c_int, C.c_char_p, i32, vp, i32, i32, i32, vp, i32, vp]
     L.mhapb_dat_encode.restype = i64
     L.mhapb_dat_decode.argtypes = [vp, u64, i64, P(u32), P(i32), P(i32), P(i32), vp, vp, vp, vp, vp, vp, vp]

@@ -194,6 +194,24 @@ def test_store_full_id_prints_fasta_names(tmp_path):
         return " ".join([f"read_{int(f[0]) - 1}", f"read_{int(f[1]) - 1}"] + f[2:])
     assert sorted(map(rename_self, self_num)) == self_named and len(self_named) > 20
     assert sorted(map(rename, num)) == named and len(named) > 50
+    # -p with --store-full-id: the header string stored in every .dat record is the FASTA name (SequenceId.getHeader,
+    # impl/SequenceId.java:102-108; SequenceSketch.getAsByteArray writes it with writeUTF), without it the decimal id
+    d1, d2 = tmp_path / "dat_num", tmp_path / "dat_named"
+    d1.mkdir(); d2.mkdir()
+    _run(["-p", str(fa), "-q", str(d1), "--num-hashes", "64"])
+    _run(["-p", str(fa), "-q", str(d2), "--num-hashes", "64", "--store-full-id"])
+    def headers(blob):
+        out, off = [], 0
+        while off < len(blob):
+            size = int.from_bytes(blob[off + 1:off + 5], "big")
+            hl = int.from_bytes(blob[off + 5 + 9:off + 5 + 11], "big")
+            out.append(blob[off + 5 + 11:off + 5 + 11 + hl].decode())
+            off += 5 + size
+        return out
+    hn, hf = headers((d1 / "store.dat").read_bytes()), headers((d2 / "store.dat").read_bytes())
+    kept = [i for i, r in enumerate(store) if len(r) >= 116]
+    assert hn == [str(i + 1) for i in kept for _ in (0, 1)]
+    assert hf == [f"read_{i}" for i in kept for _ in (0, 1)]
 
 
 def test_bad_arguments_exit_like_the_reference(tmp_path):
