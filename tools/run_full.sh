@@ -17,3 +17,6 @@ try:
 except Exception as e:
     print('bench parse failed', e)
 PY
+# ncu --set full of the K2c kernel at configs[1] (VERDICT r1 missing #6)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_filter_warp" -c 1 -f -o gpurun_out/${tag}_k2c python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-parity > gpurun_out/${tag}_ncu_k2c.log 2>&1
+ls -la gpurun_out | grep ${tag}
