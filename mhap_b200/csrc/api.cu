@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -74,7 +75,8 @@ int filter_unweighted(const KmerFilterView &v, int unweighted) { return v.mode =
 // slot_valid (optional, size n_reads*per): set to 0 for strands whose every k-mer was filtered out.
 int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_bases, const uint64_t *h_offsets,
                 uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
-                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid, const char *h_bases)
+                int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid, const char *h_bases,
+                const std::function<int()> *on_enqueued)
 {
     static const bool trace = getenv("MHAPB_TRACE") != nullptr;   // host-side time stamps of the enqueue path, to stderr
     const auto t_enter = std::chrono::steady_clock::now();
@@ -87,23 +89,45 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     std::vector<int32_t> h_nl, h_nh;
     const int per = both ? 2 : 1;
     const int k = p.kmer_size, ok = p.ordered_kmer_size, H = p.num_hashes, S = p.ordered_sketch_size;
+    // The strands of the call, materialised LAZILY (chunk by chunk, see fill_until): the first K1a launch should not wait for
+    // 2*10^5 descriptors to be written -- on a host whose cores are busy or throttled everything before the first launch is
+    // GPU idle time.
     std::vector<StrandDesc> &all = ctx->plan_all;    // kept across calls: a fresh 6 MB vector per call is a page fault per 4 KB
     all.clear();
     all.reserve((size_t)n_reads * per);
+    uint32_t gen_r = 0; int gen_s = 0;
+    auto gen_next = [&](StrandDesc *out) -> bool {
+        while (gen_r < n_reads) {
+            const uint64_t len = h_offsets[gen_r + 1] - h_offsets[gen_r];
+            if (!read_status(p, len)) {
+                while (gen_s < per) {
+                    const int st = gen_s++;
+                    const int64_t row = row_of_slot[(size_t)gen_r * per + st];
+                    if (row < 0) continue;
+                    out->base_off = h_offsets[gen_r]; out->koff = 0; out->len = (uint32_t)len; out->row = (uint32_t)row; out->rc = (uint32_t)st;
+                    out->slot = (uint32_t)((size_t)gen_r * per + st);
+                    return true;
+                }
+            }
+            gen_r++; gen_s = 0;
+        }
+        return false;
+    };
+    auto fill_until = [&](size_t need) { StrandDesc d; while (all.size() < need && gen_next(&d)) all.push_back(d); };
+    // sizes only: k-mers of strand i of the call, in order (the same walk as gen_next, without writing descriptors)
+    std::vector<uint32_t> &nk_of = ctx->plan_nk;
+    nk_of.clear();
+    nk_of.reserve((size_t)n_reads * per);
     for (uint32_t r = 0; r < n_reads; r++) {
-        uint64_t len = h_offsets[r + 1] - h_offsets[r];
+        const uint64_t len = h_offsets[r + 1] - h_offsets[r];
         if (len > 0x7fffff00ull) return fail(ctx, MHAPB_EINVAL, "read %u longer than 2^31 bases", r);
         if (read_status(p, len)) continue;
-        for (int s = 0; s < per; s++) {
-            int64_t row = row_of_slot[(size_t)r * per + s];
-            if (row < 0) continue;
-            StrandDesc d; d.base_off = h_offsets[r]; d.koff = 0; d.len = (uint32_t)len; d.row = (uint32_t)row; d.rc = (uint32_t)s; d.slot = (uint32_t)((size_t)r * per + s);
-            all.push_back(d);
-        }
+        for (int st = 0; st < per; st++) if (row_of_slot[(size_t)r * per + st] >= 0) nk_of.push_back((uint32_t)(len - k + 1));
     }
+    const size_t n_total = nk_of.size();
     ctx->timing.xorshift_steps = 0;
     ctx->timing.kmers_hashed = 0;
-    if (all.empty()) return MHAPB_OK;
+    if (!n_total) { if (on_enqueued) return (*on_enqueued)(); return MHAPB_OK; }
 
     // Work plan.  The strands are cut into CHUNKS of <= 256 M k-mers: a chunk is the unit of the host->device copy (its
     // characters travel on the copy stream while the previous chunk is hashed) and of the K1a / K1c launches.  K1b -- 76 % of
@@ -114,19 +138,20 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     // a third of the free memory, at most 64 GB).
     const uint64_t chunk_cap = 256ull << 20;
     const int max_chunk_strands = 1 << 20;
-    uint64_t super_cap;
-    {
+    uint64_t super_cap = ctx->super_cap;
+    if (!super_cap) {   // once per context: cudaMemGetInfo is a driver round trip (0.1-1 ms, occasionally far more)
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const size_t have = ctx->keys.cap + ctx->wts.cap;
         double gb = std::min(64.0, (double)(free_b + have) / 3.0 / 1e9);
         if (const char *e = getenv("MHAPB_K1_SUPER_GB")) gb = atof(e);
-        super_cap = std::max<uint64_t>(chunk_cap, (uint64_t)(gb * 1e9 / 12.0));
+        super_cap = ctx->super_cap = std::max<uint64_t>(chunk_cap, (uint64_t)(gb * 1e9 / 12.0));
     }
     t_plan = since();
     int launches = 0;
     struct Sub { int begin, n, first_long, max_k_short, max_k_long, max_len_short, max_len_long; uint64_t lo, hi; };
-    auto is_short = [&](const StrandDesc &d) { return (int64_t)d.len - k + 1 <= kShortMaxKmers && (int64_t)d.len - ok + 1 <= kShortMaxKmers + 64; };
+    auto is_short_len = [&](uint64_t len) { return (int64_t)len - k + 1 <= kShortMaxKmers && (int64_t)len - ok + 1 <= kShortMaxKmers + 64; };
+    auto is_short = [&](const StrandDesc &d) { return is_short_len(d.len); };
     std::vector<cudaEvent_t> evs;     // per chunk: [before K1a, after K1a, after K1c]; per super-chunk: [before K1b, after K1b]
     std::vector<cudaEvent_t> hevs, cpevs;
     auto ev_new = [&](std::vector<cudaEvent_t> &v, cudaStream_t st) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); };
@@ -139,20 +164,21 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     // strand descriptors are planned into PINNED memory: a copy from pageable memory makes the host wait for the stream, and
     // then the next chunk's characters are not on their way while this chunk is hashed
     std::vector<uint32_t> slot_of;                       // want_valid: caller's slot of every strand of the super-chunk
-    while (pos < all.size()) {
+    while (pos < n_total) {
         // ---- extent of one super-chunk (sizes only: the first K1a launch should not wait for the whole plan) ----
         size_t send = pos; uint64_t total_k = 0; size_t n_chunks = 0;
         int max_k_short = 1, max_k_long = 1, max_len_long = 1; bool any_short = false, any_long = false;
         {
             uint64_t in_chunk = 0; size_t in_chunk_n = 0;
-            while (send < all.size()) {
-                const uint64_t nk = all[send].len - k + 1;
+            while (send < n_total) {
+                const uint64_t nk = nk_of[send];
                 if (send > pos && total_k + nk > super_cap) break;
                 if (in_chunk_n == 0 || in_chunk + nk > chunk_cap || (int)in_chunk_n >= max_chunk_strands) { n_chunks++; in_chunk = 0; in_chunk_n = 0; }
                 in_chunk += nk; in_chunk_n++;
                 total_k += nk;
-                if (is_short(all[send])) { any_short = true; max_k_short = std::max(max_k_short, (int)nk); }
-                else { any_long = true; max_k_long = std::max(max_k_long, (int)nk); max_len_long = std::max(max_len_long, (int)all[send].len); }
+                const uint64_t len_s = nk + (uint64_t)k - 1;
+                if (is_short_len(len_s)) { any_short = true; max_k_short = std::max(max_k_short, (int)nk); }
+                else { any_long = true; max_k_long = std::max(max_k_long, (int)nk); max_len_long = std::max(max_len_long, (int)len_s); }
                 send++;
             }
         }
@@ -204,10 +230,11 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
             uint64_t tot = 0;
             size_t q = pos;
             while (q < send && (int)(q - pos) < max_chunk_strands) {
-                const uint64_t nk = all[q].len - k + 1;
+                const uint64_t nk = nk_of[q];
                 if (q > pos && tot + nk > chunk_cap) break;
                 tot += nk; q++;
             }
+            fill_until(q);                                        // this chunk's descriptors (the later ones while the GPU hashes this chunk)
             const int c0 = n_all - (int)(send - pos);             // index of this chunk's first strand in the super-chunk
             StrandDesc *cd = hd + c0;
             const int cn = (int)(q - pos);
@@ -296,9 +323,11 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         } else if (d_minhash) CU(ctx, launch_minhash(ctx->stream, dd, n_all, k, H, sc, d_minhash, flt.light_weight, sc.counters + (n_chunks + 2) * 4, &launches));
         ev_new(evs, ctx->stream);
         last_ev = evs.back();
-        if (pos < all.size()) CU(ctx, cudaStreamSynchronize(ctx->stream));   // the next super-chunk reuses desc / keys / the pinned plan
+        if (pos < n_total) CU(ctx, cudaStreamSynchronize(ctx->stream));   // the next super-chunk reuses desc / keys / the pinned plan
     }
     t_enq = since();
+    int cb_rc = MHAPB_OK;
+    if (on_enqueued) cb_rc = (*on_enqueued)();      // host work of the caller that can run while the GPU sketches (store metadata)
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (trace) fprintf(stderr, "[mhapb] sketch_core host ms: strands planned %.2f, first K1a enqueued %.2f, all enqueued %.2f, synced %.2f (h2d %s)\n",
                        t_plan, t_first, t_enq, since(), h_bases ? "per chunk" : "none");
@@ -314,7 +343,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     if (first_ev && last_ev) { float t = 0; cudaEventElapsedTime(&t, first_ev, last_ev); ctx->timing.sketch_total_ms += t; }
     for (auto e : evs) cudaEventDestroy(e);
     ctx->timing.kernel_launches += launches;
-    return MHAPB_OK;
+    return cb_rc;
 }
 
 void reset_sketch_timing(mhapb_ctx *ctx)
@@ -657,19 +686,23 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
     const int64_t added = next - n0;
     if (n_added) *n_added = added;
     if (!added) return MHAPB_OK;
-    // metadata first (duplicate ids abort before any device work)
+    // The per-sketch host columns (ids, lengths, the duplicate-id check of MinHashSearch.java:112-117) are filled WHILE the GPU
+    // sketches: sketch_core runs this once everything is enqueued.  A duplicate id then surfaces after the device work, which
+    // wrote rows beyond s.n that nobody reads; the store is left exactly as it was (s.n is only advanced at the end).
     const size_t meta0 = s.h_id.size();
-    for (uint32_t r = 0; r < n_reads; r++) {
-        uint64_t len = offsets[r + 1] - offsets[r];
-        if (read_status(s.p, len)) continue;
-        for (int st = 0; st < per; st++) {
-            if (!strand_kept(r, st)) continue;
-            int32_t no = (int32_t)len - s.p.ordered_kmer_size + 1;
-            int rc = store_push_meta(ctx, ids ? ids[r] : (int64_t)r + 1, st == 0, (int32_t)len, no, std::min(no, s.p.ordered_sketch_size));
-            if (rc) { store_rollback_meta(s, meta0); return rc; }
+    const std::function<int()> push_meta = [&]() -> int {
+        for (uint32_t r = 0; r < n_reads; r++) {
+            uint64_t len = offsets[r + 1] - offsets[r];
+            if (read_status(s.p, len)) continue;
+            for (int st = 0; st < per; st++) {
+                if (!strand_kept(r, st)) continue;
+                int32_t no = (int32_t)len - s.p.ordered_kmer_size + 1;
+                int rc = store_push_meta(ctx, ids ? ids[r] : (int64_t)r + 1, st == 0, (int32_t)len, no, std::min(no, s.p.ordered_sketch_size));
+                if (rc) return rc;
+            }
         }
-    }
-    // any failure below leaves the store exactly as it was (s.n is only advanced at the end)
+        return MHAPB_OK;
+    };
     auto device_part = [&]() -> int {
         int rc = store_reserve(ctx, added);
         if (rc) return rc;
@@ -678,7 +711,7 @@ int add_reads_locked(mhapb_ctx *ctx, const char *bases, const uint64_t *offsets,
         const size_t S = (size_t)s.ord_stride;
         CU(ctx, cudaMemsetAsync(s.ord.as<int32_t>() + (size_t)n0 * S * 2, 0, (size_t)added * S * 8, ctx->stream));
         rc = sketch_core(ctx, s.p, dev_bases(), offsets, n_reads, both, rows, s.minhash.as<int32_t>(), s.ord.as<int32_t>(), s.ord_stride, s.ord_n.as<int32_t>(),
-                         nullptr, stream_h2d ? bases : nullptr);
+                         nullptr, stream_h2d ? bases : nullptr, &push_meta);
         if (rc) return rc;
         if (!stream_h2d && !d_resident) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.h2d_ms += ms; }
         s.n = next;

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <unordered_set>
@@ -101,6 +102,8 @@ struct mhapb_ctx {
     mhapb::DevBuf ovf_q;
     mhapb::PinnedBuf h_cand, h_ovl;               // pinned landing buffers of the surviving pairs
     std::vector<mhapb::StrandDesc> plan_all;      // the strands of the current sketch call (sketch_core)
+    std::vector<uint32_t> plan_nk;                // their k-mer counts
+    uint64_t super_cap = 0;                       // k-mers of key scratch one K1b launch may cover (sized once from the free memory)
     mhapb::PinnedBuf h_desc, h_vdesc;             // pinned plan of the strand descriptors (sketch_core)
     mhapb::DevBuf t512, vdesc;                    // step^512 tables and the virtual strands of sketches wider than 512 words
     uint64_t cand_cap_hint = 0; uint32_t ovf_threads_hint = 0;   // sizes the previous search needed
@@ -150,7 +153,9 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
                 uint32_t n_reads, int both, const std::vector<int64_t> &row_of_slot, int32_t *d_minhash,
                 int32_t *d_ord, int ord_stride, int32_t *d_ord_n, std::vector<uint8_t> *slot_valid = nullptr,
                 const char *h_bases = nullptr /* host copy of the reads: each chunk's characters are copied to d_bases (= ctx->bases) on the
-                                                 second stream right before its K1a, so the H2D of chunk i+1 runs under K1 of chunk i */);
+                                                 second stream right before its K1a, so the H2D of chunk i+1 runs under K1 of chunk i */,
+                const std::function<int()> *on_enqueued = nullptr /* run once everything is enqueued, before the final synchronisation;
+                                                 a non-zero result is returned after the GPU work has completed */);
 int index_build(mhapb_ctx *ctx);
 int search_core(mhapb_ctx *ctx, const mhapb_search_params *sp, const QuerySet &q, int to_self,
                 mhapb_hit **out, uint64_t *n_out, mhapb_stats *stats);
