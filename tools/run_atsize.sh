@@ -28,7 +28,7 @@ if [ -n "$small" ]; then
   h=$((n/2)); [ $h -lt 1 ] && h=1
   CUDA_VISIBLE_DEVICES=$(seq -s, 0 $((h-1))) run c3_n$h $h --config 3 --steps 2 --warmup 1 --no-cpu-baseline --reads 8000 --query-reads 8000
 else
-  run c1_n$n $n --steps 3 --warmup 2 --no-cpu-baseline
+  run c1_n$n $n --steps 5 --warmup 3
   run c4_n$n $n --config 4 --steps 2 --warmup 1 --no-cpu-baseline
   h=$((n/2))
   CUDA_VISIBLE_DEVICES=$(seq -s, 0 $((h-1))) run c3_n$h $h --config 3 --steps 2 --warmup 1 --no-cpu-baseline
