@@ -396,7 +396,7 @@ def _main(args, real_stdout):
     total_bases = (total_reads + total_queries) * L
     k_ms = {k: v / args.steps for k, v in acc.items()}
     stats = last["stats"]
-    n_chunks = max(1, -(-(n_local * 2 * (L - 15)) // (256 << 20)))
+    n_chunks = 1      # K1b is launched once per sketch call (one super-chunk: the key scratch of the whole shard fits)
     alg_bytes = alg_bytes_per_read(L, H, S) * n_local + (alg_bytes_per_read(L, H, S, strands=1) * nq_local if args.mode == "query" else 0)
     peaks = {}
     try:
@@ -411,7 +411,7 @@ def _main(args, real_stdout):
         with open(os.path.join(ROOT, "profiles", "k1b_dram_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("num_hashes") == H and tj.get("read_len") == L:
-            traffic = tj["dram_bytes_per_read"] * n_local / n_chunks
+            traffic = tj["dram_bytes_per_read"] * (n_local + 0.5 * nq_local) / n_chunks
             traffic_src = tj.get("source")
     except Exception:
         pass
