@@ -152,9 +152,11 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     struct Sub { int begin, n, first_long, max_k_short, max_k_long, max_len_short, max_len_long; uint64_t lo, hi; };
     auto is_short_len = [&](uint64_t len) { return (int64_t)len - k + 1 <= kShortMaxKmers && (int64_t)len - ok + 1 <= kShortMaxKmers + 64; };
     auto is_short = [&](const StrandDesc &d) { return is_short_len(d.len); };
-    std::vector<cudaEvent_t> evs;     // per chunk: [before K1a, after K1a, after K1c]; per super-chunk: [before K1b, after K1b]
-    std::vector<cudaEvent_t> hevs, cpevs;
-    auto ev_new = [&](std::vector<cudaEvent_t> &v, cudaStream_t st) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); };
+    // events of the call; destroyed on every way out of the function
+    struct EventBag : std::vector<cudaEvent_t> { ~EventBag() { for (cudaEvent_t e : *this) cudaEventDestroy(e); } };
+    EventBag evs;     // per chunk: [before K1a, after K1a, after K1c]; per super-chunk: [before K1b, after K1b]
+    EventBag hevs, cpevs;
+    auto ev_new = [&](EventBag &v, cudaStream_t st) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); };
     std::vector<size_t> k1a_ev, k1b_ev;
     uint64_t copied_hi = 0;
     CU(ctx, cudaStreamSynchronize(ctx->stream2));   // the previous call's copies are long done; keeps the stream's order simple
@@ -192,8 +194,17 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
         static int multipass = -1;
         if (multipass < 0) { const char *e = getenv("MHAPB_K1B_PASSES"); multipass = e ? atoi(e) : 1; }
         const int passes = (multipass && H > 512 && H <= kMaxNumHashes && d_minhash) ? (H + 511) / 512 : 1;
-        CU(ctx, ctx->keys.ensure((size_t)total_k * 8 * (size_t)passes));
-        CU(ctx, ctx->wts.ensure((size_t)total_k * 4));
+        {   // the key scratch is the big allocation: if the memory is not there (the store grew since the bound was sized), halve the
+            // super-chunk and plan again instead of failing
+            cudaError_t ek = ctx->keys.ensure((size_t)total_k * 8 * (size_t)passes);
+            if (ek == cudaSuccess) ek = ctx->wts.ensure((size_t)total_k * 4);
+            if (ek == cudaErrorMemoryAllocation && super_cap > chunk_cap && n_chunks > 1) {
+                (void)cudaGetLastError();
+                super_cap = ctx->super_cap = std::max<uint64_t>(chunk_cap, super_cap / 2);
+                continue;
+            }
+            CU(ctx, ek);
+        }
         CU(ctx, ctx->nlight.ensure((size_t)n_all * 4));
         CU(ctx, ctx->nheavy.ensure((size_t)n_all * 4));
         const size_t n_counters = (n_chunks + 2) * 4 + 4;        // per chunk: K1a short, K1a long, K1c short, K1c long; + K1b (after the chunks' blocks)
@@ -338,10 +349,7 @@ int sketch_core(mhapb_ctx *ctx, const mhapb_sketch_params &p, const uint8_t *d_b
     }
     for (size_t i : k1b_ev) { float b = 0; cudaEventElapsedTime(&b, evs[i], evs[i + 1]); ctx->timing.minhash_ms += b; }
     for (size_t i = 0; i + 1 < hevs.size(); i += 2) { float c = 0; cudaEventElapsedTime(&c, hevs[i], hevs[i + 1]); ctx->timing.h2d_ms += c; }
-    for (auto e : hevs) cudaEventDestroy(e);
-    for (auto e : cpevs) cudaEventDestroy(e);
     if (first_ev && last_ev) { float t = 0; cudaEventElapsedTime(&t, first_ev, last_ev); ctx->timing.sketch_total_ms += t; }
-    for (auto e : evs) cudaEventDestroy(e);
     ctx->timing.kernel_launches += launches;
     return cb_rc;
 }
