@@ -136,7 +136,7 @@ def test_filter_argument_errors():
 
 
 def test_long_read_h1024_with_filter():
-    # strands above 16384 k-mers take K1a's global-table path, H = 1024 the B=32 lock-step instantiation; both with tf-idf
+    # strands above 16384 k-mers take K1a's global-table path, H = 1024 runs as two 512-word blocks (virtual strands, MULTI); both with tf-idf
     # weights (light weight 3) and a few repeat k-mers carrying their own weights
     rng = random.Random(12)
     g = "".join(rng.choice("ACGT") for _ in range(21000))
