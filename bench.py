@@ -199,7 +199,7 @@ def workload_config(args, world):
             "num_hashes": args.num_hashes, "ordered_kmer_size": 12, "ordered_sketch_size": args.ordered_sketch_size, "error_rate": args.err,
             "coverage": 20, "seed": args.seed,
             "l2_policy": f"inputs larger than L2 ({args.reads * args.read_len / 1e9:.2f} GB of reads per GPU per step, sketches {2 * args.reads * (4 * args.num_hashes + 8 * args.ordered_sketch_size) / 1e9:.2f} GB)",
-            "parallelism": f"reads sharded over {world} GPU(s); each rank indexes its shard; NCCL all-gather of the forward sketch blocks inside the library; every rank queries its index with all forward sketches"}
+            "parallelism": f"reads sharded over {world} GPU(s) (two folded half-shards per rank: equal K2c load); each rank indexes its shard; NCCL all-gather of the forward sketch blocks inside the library; every rank queries its index with all forward sketches"}
 
 
 def main():
@@ -222,7 +222,7 @@ def _main(args, real_stdout):
     import torch
     import torch.distributed as dist
     from mhap_b200 import native, synth
-    from mhap_b200.distributed import bootstrap_comm, gather_hits, hits_digest
+    from mhap_b200.distributed import bootstrap_comm, folded_shard_ranges, gather_hits, hits_digest
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,10 +243,19 @@ def _main(args, real_stdout):
     n_local, nq_local = args.reads, args.query_reads
     total_reads, total_queries = n_local * world, nq_local * world
     g = make_genome(args, world)
+    # this rank's reads: two half-shards of the job's read stream, folded so that every rank stores the same number of
+    # (lower id, higher id) pairs to score -- a contiguous shard leaves rank 0 with ~2x the K2c work of one GPU and the last
+    # rank with none (distributed.folded_shard_ranges); ids are the global 1-based positions, the job's hit set is unchanged
+    parts = folded_shard_ranges(total_reads, rank, world)
+    assert sum(c for _, c in parts) == n_local, "reads per GPU must be even"
     host = torch.empty(n_local * L, dtype=torch.uint8).pin_memory()
     bases = host.numpy()
-    _, offsets = synth.reads(g, READ_SEED(args.seed), rank * n_local, n_local, L, args.err, out=bases)
-    ids = np.arange(1, n_local + 1, dtype=np.int64) + rank * n_local
+    at = 0
+    for first, cnt in parts:
+        synth.reads(g, READ_SEED(args.seed), first, cnt, L, args.err, out=bases[at * L:(at + cnt) * L])
+        at += cnt
+    offsets = np.arange(n_local + 1, dtype=np.uint64) * np.uint64(L)
+    ids = np.concatenate([np.arange(first + 1, first + cnt + 1, dtype=np.int64) for first, cnt in parts])
     qbases = qoffsets = qids = d_qbases = None
     if args.mode == "query":
         qhost = torch.empty(nq_local * L, dtype=torch.uint8).pin_memory()
@@ -336,6 +345,10 @@ def _main(args, real_stdout):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     step_s = float(tt[0].item()) / args.steps
+    kmax = torch.tensor([acc[k] / args.steps for k in TKEYS], dtype=torch.float64, device="cuda")     # balance check: slowest rank per kernel
+    if world > 1:
+        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+    k_ms_max = {k: float(v) for k, v in zip(TKEYS, kmax.tolist())}
     step_dev_s = float(tt[1].item()) / args.steps
     free_b, total_b = torch.cuda.mem_get_info()
     mem = torch.tensor([float(total_b - free_b)], dtype=torch.float64, device="cuda")
@@ -426,7 +439,7 @@ def _main(args, real_stdout):
         "config": workload_config(args, world),
         "sketch_gbases_per_s": (n_local + nq_local) * L / (k_ms["sketch_total_ms"] * 1e-3) / 1e9 * world,
         "overlaps_per_s": compared / (search_ms * 1e-3) if search_ms > 0 else None,
-        "kernel_ms_per_step_rank0": k_ms,
+        "kernel_ms_per_step_rank0": k_ms, "kernel_ms_per_step_max_over_ranks": k_ms_max,
         "wall_ms_rank0": {"sketch": last["wall_sketch"] * 1e3, "exchange_index_search": last["wall_search"] * 1e3},
         "counters": stats, "query_counters": last["qstats"], "n_store_rank0": last["n_store"],
         "hbm_high_water_gb_max_rank": float(mem.item()) / 1e9,

@@ -33,6 +33,19 @@ def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
     return first, base + (1 if rank < rem else 0)
 
 
+def folded_shard_ranges(n_items: int, rank: int, world: int) -> list[tuple[int, int]]:
+    """Two (first, count) ranges for `rank`: stripes `rank` and `2*world-1-rank` of [0, n_items) cut into 2*world stripes.
+
+    Why not one contiguous range: in a self-overlap the pair {a, b} is reported once, by the rank that STORES the read with
+    the lower id (MinHashSearch.java:215-219 keeps `to` < `from`), so the rank holding the lowest ids would score almost
+    all of its reads' overlaps and the rank holding the highest ids almost none.  Stripe s stores reads whose share of
+    higher-id partners is 1-(s+.5)/(2*world); stripes r and 2*world-1-r sum to exactly 1, every rank gets the same K2c load.
+    Ids stay ascending within the rank (lower stripe first), the hit set of the job does not depend on the partition."""
+    cuts = [n_items * s // (2 * world) for s in range(2 * world + 1)]
+    lo, hi = rank, 2 * world - 1 - rank
+    return [(cuts[lo], cuts[lo + 1] - cuts[lo]), (cuts[hi], cuts[hi + 1] - cuts[hi])]
+
+
 def bootstrap_comm(engine, dist=None, make_id=native.comm_unique_id):
     """Join this rank's context to the job's communicator.  Rank 0 makes the NCCL unique id inside the library
     (mhapb_comm_unique_id); `dist` (an initialised torch.distributed, any backend) only carries its 128 bytes."""

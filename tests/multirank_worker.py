@@ -18,7 +18,7 @@ def main():
     out_dir, n_total, L, nq_total = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     import torch.distributed as dist
     from mhap_b200 import native, synth
-    from mhap_b200.distributed import GpuBackend, bootstrap_comm, shard_range, sharded_query_overlap, sharded_self_overlap
+    from mhap_b200.distributed import GpuBackend, bootstrap_comm, folded_shard_ranges, shard_range, sharded_query_overlap, sharded_self_overlap
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group("gloo")
@@ -30,9 +30,16 @@ def main():
     p = native.SketchParams(16, 256, 12, 1536, 0, 116)
     sp = native.SearchParams(3, 0, 0.2, 0.78, 1, 0, 0, -1)       # keep_all: also the rejected candidates
     g = synth.genome(11, max(L + 1, n_total * L // 12))
-    first, cnt = shard_range(n_total, rank, world)               # ragged when world does not divide n_total
-    bases, offs = synth.reads(g, 77, first, cnt, L, 0.12)
-    ids = np.arange(first + 1, first + cnt + 1, dtype=np.int64)
+    # the store shard: two folded stripes (what bench.py uses; equal K2c load per rank), ragged when 2*world does not divide n_total
+    parts = folded_shard_ranges(n_total, rank, world)
+    n_mine = sum(c for _, c in parts)
+    bases = np.empty(n_mine * L, dtype=np.uint8)
+    at = 0
+    for first, cnt in parts:
+        synth.reads(g, 77, first, cnt, L, 0.12, out=bases[at * L:(at + cnt) * L])
+        at += cnt
+    offs = np.arange(n_mine + 1, dtype=np.uint64) * np.uint64(L)
+    ids = np.concatenate([np.arange(first + 1, first + cnt + 1, dtype=np.int64) for first, cnt in parts])
     be = GpuBackend(eng, p, sp)
     hits, stats = sharded_self_overlap(be, bases, offs, ids, dist)
     np.save(os.path.join(out_dir, f"self_{rank}.npy"), hits)

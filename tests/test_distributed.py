@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from mhap_b200 import native
-from mhap_b200.distributed import bootstrap_comm, gather_hits, hits_digest, shard_range, sharded_query_overlap, sharded_self_overlap
+from mhap_b200.distributed import bootstrap_comm, folded_shard_ranges, gather_hits, hits_digest, shard_range, sharded_query_overlap, sharded_self_overlap
 from oracle import oracle as orc
 from tests.dist_standin import OracleBackend, SketchBlock, all_gather_blocks
 
@@ -47,13 +47,13 @@ def _key(h):
     return tuple(int(h[k]) for k in ("from_id", "to_id", "to_fwd", "hit_count", "a1", "a2", "b1", "b2", "valid_count", "intersect", "kmin", "accepted"))
 
 
-def _worker(rank, world, port, n_reads, q):
+def _worker(rank, world, port, n_reads, folded, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     reads = _reads(n_reads, 500, 5)
-    first, cnt = shard_range(n_reads, rank, world)
-    bases, offs = orc.pack_reads(reads[first:first + cnt])
-    ids = np.arange(first + 1, first + cnt + 1, dtype=np.int64)
+    parts = folded_shard_ranges(n_reads, rank, world) if folded else [shard_range(n_reads, rank, world)]
+    bases, offs = orc.pack_reads([r for first, cnt in parts for r in reads[first:first + cnt]])
+    ids = np.concatenate([np.arange(first + 1, first + cnt + 1, dtype=np.int64) for first, cnt in parts])
     eng = FakeEngine()
     assert bootstrap_comm(eng, dist, make_id=lambda: bytes(range(128))) == (rank, world)
     assert eng.joined == (bytes(range(128)), rank, world)        # rank 0's id reached every rank
@@ -88,8 +88,8 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_self_overlap_equals_single_process(world):
+@pytest.mark.parametrize("world,folded", [(2, False), (3, False), (2, True), (3, True)])
+def test_sharded_self_overlap_equals_single_process(world, folded):
     n_reads = 41
     reads = _reads(n_reads, 500, 5)
     st = orc.Store(num_hashes=H, ordered_size=S)
@@ -101,7 +101,7 @@ def test_sharded_self_overlap_equals_single_process(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_reads, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_reads, folded, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]
@@ -158,6 +158,22 @@ def test_shard_range_covers_everything():
             assert sum(c for _, c in parts) == n
             assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_folded_shard_ranges_cover_and_balance():
+    for n in (0, 1, 7, 100, 100000):
+        for w in (1, 2, 3, 8):
+            parts = [folded_shard_ranges(n, r, w) for r in range(w)]
+            flat = sorted(p for pr in parts for p in pr)
+            assert sum(c for _, c in flat) == n
+            assert all(flat[i][0] + flat[i][1] == flat[i + 1][0] for i in range(len(flat) - 1))      # disjoint, no hole
+            assert all(pr[0][0] + pr[0][1] <= pr[1][0] for pr in parts)                                # ids ascend within a rank
+    # the point of the folding: every rank stores the same number of (stored id < other id) pairs
+    n, w = 80000, 8
+    load = [sum(cnt * (n - first) - cnt * (cnt + 1) // 2 for first, cnt in folded_shard_ranges(n, r, w)) for r in range(w)]
+    assert max(load) - min(load) <= 1e-9 * max(load)
+    contiguous = [cnt * (n - first) - cnt * (cnt + 1) // 2 for first, cnt in (shard_range(n, r, w) for r in range(w))]
+    assert max(contiguous) > 1.8 * (sum(contiguous) / w)
 
 
 def test_all_gather_blocks_single_process_is_identity():
